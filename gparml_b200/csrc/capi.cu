@@ -1,0 +1,559 @@
+// C ABI (include/gparml_b200.h): context management, transfers, phase sequencing.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void gp_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *gparml_last_error(void) { return g_err; }
+extern "C" int gparml_abi_version(void) { return 1; }
+
+extern "C" int gparml_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+#define CHECK_CTX(c)                                  \
+    do {                                              \
+        if (!(c)) {                                   \
+            gp_set_error("null context");             \
+            return GPARML_ERR_ARG;                    \
+        }                                             \
+        GP_CUDA(cudaSetDevice((c)->device));          \
+    } while (0)
+
+template <typename T>
+static int dev_alloc(T **p, size_t count)
+{
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (count == 0) count = 1;
+    GP_CUDA(cudaMalloc((void **)p, count * sizeof(T)));
+    return GPARML_OK;
+}
+
+int gp_ensure_ws(gparml_ctx *c, size_t bytes)
+{
+    if (bytes <= c->ws_bytes) return GPARML_OK;
+    // growing the workspace must not race with kernels still using the old one
+    GP_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->ws) { cudaFree(c->ws); c->ws = nullptr; c->ws_bytes = 0; }
+    size_t want = bytes + bytes / 4 + 4096;
+    GP_CUDA(cudaMalloc((void **)&c->ws, want));
+    c->ws_bytes = want;
+    return GPARML_OK;
+}
+
+extern "C" int gparml_create(gparml_ctx **out, int device, int M, int Q, int D, int64_t n_total, int flags)
+{
+    if (!out) { gp_set_error("gparml_create: out is null"); return GPARML_ERR_ARG; }
+    *out = nullptr;
+    int ndev = gparml_device_count();
+    if (ndev <= 0) {
+        gp_set_error("gparml_create: no CUDA device visible -- gparml_b200 has no CPU path");
+        return GPARML_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= ndev) { gp_set_error("gparml_create: device %d out of range (0..%d)", device, ndev - 1); return GPARML_ERR_ARG; }
+    if (M < 1 || Q < 1 || Q > GP_MAX_Q || D < 1 || n_total < 0) {
+        gp_set_error("gparml_create: unsupported shape M=%d Q=%d (1..%d) D=%d N=%lld", M, Q, GP_MAX_Q, D, (long long)n_total);
+        return GPARML_ERR_ARG;
+    }
+    GP_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    GP_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        gp_set_error("gparml_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return GPARML_ERR_NO_DEVICE;
+    }
+    gparml_ctx *c = new gparml_ctx();
+    c->device = device; c->M = M; c->Q = Q; c->D = D; c->n_total = n_total; c->flags = flags;
+    c->sm_count = prop.multiProcessorCount;
+    c->L = gp_make_layout(M, Q, D);
+    int r = GPARML_OK;
+    auto fail = [&](int code) { gparml_destroy(c); return code; };
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { gp_set_error("stream create failed"); return fail(GPARML_ERR_CUDA); }
+    c->stream = c->own_stream;
+    const size_t MM = (size_t)M * M;
+#define A_(ptr, count) if ((r = dev_alloc(&(ptr), (count))) != GPARML_OK) return fail(r)
+    A_(c->Z, (size_t)M * Q);
+    A_(c->d_glob, 1);
+    A_(c->pair_idx, (size_t)c->L.P);
+    A_(c->pair_lk, (size_t)c->L.P);
+    A_(c->pair_g, (size_t)c->L.P);
+    A_(c->stats, (size_t)c->L.count);
+    A_(c->red_ws, 4096);
+    A_(c->d_status, 1);
+    A_(c->kmm, MM); A_(c->kmm_inv, MM); A_(c->a_inv, MM);
+    A_(c->g_k, MM); A_(c->g_2, MM); A_(c->g_1, (size_t)M * D); A_(c->c_mat, (size_t)M * D);
+    A_(c->scratch_x, MM); A_(c->scratch_w, MM);
+    A_(c->glob_out, (size_t)M * Q + Q + 16);
+#undef A_
+    if (cudaMemsetAsync(c->stats, 0, c->L.count * sizeof(double), c->stream) != cudaSuccess ||
+        cudaMemsetAsync(c->d_status, 0, sizeof(int), c->stream) != cudaSuccess) { gp_set_error("memset failed"); return fail(GPARML_ERR_CUDA); }
+    for (int i = 0; i < 8; ++i)
+        if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { gp_set_error("event create failed"); return fail(GPARML_ERR_CUDA); }
+    *out = c;
+    return GPARML_OK;
+}
+
+extern "C" int gparml_destroy(gparml_ctx *c)
+{
+    if (!c) return GPARML_OK;
+    cudaSetDevice(c->device);
+    if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+    void *ptrs[] = {c->Y, c->x_mu, c->x_s, c->grad_d, c->grad_latest, c->grad_new, c->grad_old, c->rec1, c->rec2, c->s_pos, c->s_sig,
+                    c->gx_mu, c->gx_s, c->psi1, c->Z, c->d_glob, c->pair_idx, c->pair_lk, c->pair_g, c->stats, c->ws, c->red_ws,
+                    c->d_status, c->kmm, c->kmm_inv, c->a_inv, c->g_k, c->g_1, c->g_2, c->scratch_x, c->scratch_w, c->c_mat,
+                    c->glob_out, c->named_tmp};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return GPARML_OK;
+}
+
+extern "C" int gparml_set_stream(gparml_ctx *c, void *s)
+{
+    CHECK_CTX(c);
+    GP_CUDA(cudaStreamSynchronize(c->stream));
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return GPARML_OK;
+}
+
+extern "C" int gparml_synchronize(gparml_ctx *c)
+{
+    CHECK_CTX(c);
+    GP_CUDA(cudaStreamSynchronize(c->stream));
+    return GPARML_OK;
+}
+
+extern "C" int gparml_set_n_total(gparml_ctx *c, int64_t n_total)
+{
+    CHECK_CTX(c);
+    c->n_total = n_total;
+    return GPARML_OK;
+}
+
+extern "C" int64_t gparml_n_local(const gparml_ctx *c) { return c ? c->n : -1; }
+extern "C" int64_t gparml_stats_count(const gparml_ctx *c) { return c ? c->L.count : -1; }
+extern "C" int64_t gparml_launch_count(const gparml_ctx *c) { return c ? c->launches : -1; }
+
+static int ensure_shard_capacity(gparml_ctx *c, int64_t n)
+{
+    if (n <= c->n_cap) return GPARML_OK;
+    GP_CUDA(cudaStreamSynchronize(c->stream));
+    const size_t nq = (size_t)n * c->Q, R = gp_rec_len(c->Q);
+    GP_TRY(dev_alloc(&c->Y, (size_t)n * c->D));
+    GP_TRY(dev_alloc(&c->x_mu, nq));
+    GP_TRY(dev_alloc(&c->x_s, nq));
+    GP_TRY(dev_alloc(&c->grad_d, 2 * nq));
+    GP_TRY(dev_alloc(&c->grad_latest, 2 * nq));
+    GP_TRY(dev_alloc(&c->grad_new, 2 * nq));
+    GP_TRY(dev_alloc(&c->grad_old, 2 * nq));
+    GP_TRY(dev_alloc(&c->rec1, (size_t)n * R));
+    GP_TRY(dev_alloc(&c->rec2, (size_t)n * R));
+    GP_TRY(dev_alloc(&c->s_pos, nq));
+    GP_TRY(dev_alloc(&c->s_sig, nq));
+    GP_TRY(dev_alloc(&c->gx_mu, nq));
+    GP_TRY(dev_alloc(&c->gx_s, nq));
+    if (c->psi1) { cudaFree(c->psi1); c->psi1 = nullptr; }
+    c->n_cap = n;
+    return GPARML_OK;
+}
+
+extern "C" int gparml_upload_shard(gparml_ctx *c, const double *Y, const double *X_mu, const double *X_S, int64_t n, int domain)
+{
+    CHECK_CTX(c);
+    if (n < 0 || (n > 0 && (!Y || !X_mu || !X_S))) { gp_set_error("upload_shard: null array or negative n"); return GPARML_ERR_ARG; }
+    if (domain != GPARML_VARIANCE_UNCONSTRAINED && domain != GPARML_VARIANCE_POSITIVE) { gp_set_error("upload_shard: bad variance domain %d", domain); return GPARML_ERR_ARG; }
+    GP_TRY(ensure_shard_capacity(c, n));
+    const size_t nq = (size_t)n * c->Q;
+    if (n > 0) {
+        GP_CUDA(cudaMemcpyAsync(c->Y, Y, (size_t)n * c->D * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        GP_CUDA(cudaMemcpyAsync(c->x_mu, X_mu, nq * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        GP_CUDA(cudaMemcpyAsync(c->x_s, X_S, nq * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    }
+    if (n != c->n) {
+        c->have_dir = false;
+        if (c->psi1) { cudaFree(c->psi1); c->psi1 = nullptr; }
+    }
+    c->n = n;
+    c->variance_domain = domain;
+    c->have_shard = true;
+    c->have_prep = c->have_stats = c->have_global_step = false;
+    GP_TRY(gp_launch_yyt(c, &c->yyt));
+    return GPARML_OK;
+}
+
+extern "C" int gparml_set_globals(gparml_ctx *c, const double *Z, double sf2, const double *alpha, double beta)
+{
+    CHECK_CTX(c);
+    if (!Z || !alpha) { gp_set_error("set_globals: null array"); return GPARML_ERR_ARG; }
+    if (!(sf2 > 0.0) || !(beta > 0.0)) { gp_set_error("set_globals: sf2 and beta must be positive (kernels.py:57 assert)"); return GPARML_ERR_ARG; }
+    memset(&c->h_glob, 0, sizeof(c->h_glob));
+    c->h_glob.sf2 = sf2;
+    c->h_glob.beta = beta;
+    c->h_glob.log_sf2 = log(sf2);
+    for (int q = 0; q < c->Q; ++q) {
+        if (!(alpha[q] >= 0.0)) { gp_set_error("set_globals: alpha[%d] negative (kernel_exp.py:30 assert)", q); return GPARML_ERR_ARG; }
+        c->h_glob.alpha[q] = alpha[q];
+    }
+    // pageable host memory: the async copies below stage synchronously, so Z/alpha may be reused by the caller on return
+    GP_CUDA(cudaMemcpyAsync(c->Z, Z, (size_t)c->M * c->Q * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    GP_CUDA(cudaMemcpyAsync(c->d_glob, &c->h_glob, sizeof(GlobalsDev), cudaMemcpyHostToDevice, c->stream));
+    GP_TRY(gp_launch_pair_table(c));
+    c->have_globals = true;
+    c->have_prep = c->have_stats = c->have_global_step = false;
+    return GPARML_OK;
+}
+
+extern "C" int gparml_set_step(gparml_ctx *c, double step)
+{
+    CHECK_CTX(c);
+    c->step_size = step;
+    c->have_prep = false;
+    return GPARML_OK;
+}
+
+static int check_status(gparml_ctx *c, bool sync_needed)
+{
+    int st = 0;
+    GP_CUDA(cudaMemcpyAsync(&st, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    GP_CUDA(cudaStreamSynchronize(c->stream));
+    (void)sync_needed;
+    if (st) {
+        GP_CUDA(cudaMemsetAsync(c->d_status, 0, sizeof(int), c->stream));
+        if (st & 4) { gp_set_error("unconstrained variance outside (-36.04, 36.04) (supporting_functions.py:154 assert)"); return GPARML_ERR_RANGE; }
+        if (st & 1) { gp_set_error("Kmm is not positive definite (Cholesky pivot <= 0)"); return GPARML_ERR_NOT_PD; }
+        if (st & 2) { gp_set_error("Kmm + beta*Psi2 is not positive definite (Cholesky pivot <= 0)"); return GPARML_ERR_NOT_PD; }
+    }
+    return GPARML_OK;
+}
+
+static int record(gparml_ctx *c, int i)
+{
+    if (c->timing) GP_CUDA(cudaEventRecord(c->ev[i], c->stream));
+    return GPARML_OK;
+}
+
+static int prep_if_needed(gparml_ctx *c)
+{
+    if (!c->have_shard || !c->have_globals) { gp_set_error("upload_shard and set_globals must precede this call"); return GPARML_ERR_STATE; }
+    if (!c->have_prep) {
+        GP_TRY(gp_launch_prep(c));
+        c->have_prep = true;
+    }
+    return GPARML_OK;
+}
+
+extern "C" int gparml_statistics(gparml_ctx *c)
+{
+    CHECK_CTX(c);
+    if (!c->have_shard || !c->have_globals) { gp_set_error("statistics: upload_shard and set_globals first"); return GPARML_ERR_STATE; }
+    GP_TRY(record(c, 0));
+    GP_TRY(gp_launch_prep(c));          // always: it also rewrites the header of the packed buffer
+    c->have_prep = true;
+    GP_TRY(record(c, 1));
+    GP_TRY(gp_launch_psi1_stats(c));
+    GP_TRY(record(c, 2));
+    GP_TRY(gp_launch_psi2_stats(c));
+    GP_TRY(record(c, 3));
+    c->have_stats = true;
+    c->have_global_step = false;
+    if (!(c->flags & GPARML_FLAG_FIXED_EMBEDDINGS) && c->variance_domain == GPARML_VARIANCE_UNCONSTRAINED)
+        GP_TRY(check_status(c, true));
+    return GPARML_OK;
+}
+
+extern "C" int gparml_stats_device_ptr(gparml_ctx *c, void **p)
+{
+    CHECK_CTX(c);
+    if (!p) { gp_set_error("null out pointer"); return GPARML_ERR_ARG; }
+    *p = c->stats;
+    return GPARML_OK;
+}
+
+extern "C" int gparml_stats_add(gparml_ctx *c, const void *other, double scale)
+{
+    CHECK_CTX(c);
+    if (!other) { gp_set_error("stats_add: null pointer"); return GPARML_ERR_ARG; }
+    GP_TRY(gp_launch_stats_add(c, (const double *)other, scale));
+    c->have_global_step = false;
+    return GPARML_OK;
+}
+
+extern "C" int gparml_stats_copy(gparml_ctx *c, const void *other)
+{
+    CHECK_CTX(c);
+    if (!other) { gp_set_error("stats_copy: null pointer"); return GPARML_ERR_ARG; }
+    GP_CUDA(cudaMemcpyAsync(c->stats, other, (size_t)c->L.count * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    c->have_stats = true;
+    c->have_global_step = false;
+    return GPARML_OK;
+}
+
+extern "C" int gparml_update_global_statistics(gparml_ctx *c)
+{
+    CHECK_CTX(c);
+    if (!c->have_globals) { gp_set_error("update_global_statistics: set_globals first"); return GPARML_ERR_STATE; }
+    GP_TRY(gp_launch_global_step(c, true));
+    return check_status(c, true);
+}
+
+extern "C" int gparml_global_step(gparml_ctx *c, double *F, double *grad)
+{
+    CHECK_CTX(c);
+    if (!c->have_globals) { gp_set_error("global_step: set_globals first"); return GPARML_ERR_STATE; }
+    GP_TRY(record(c, 4));
+    GP_TRY(gp_launch_global_step(c, false));
+    GP_TRY(record(c, 5));
+    GP_TRY(check_status(c, true));
+    c->have_global_step = true;
+    const size_t ng = (size_t)c->M * c->Q + c->Q + 2;
+    if (F) GP_CUDA(cudaMemcpyAsync(F, c->glob_out, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (grad) GP_CUDA(cudaMemcpyAsync(grad, c->glob_out + 1, ng * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    GP_CUDA(cudaStreamSynchronize(c->stream));
+    return GPARML_OK;
+}
+
+extern "C" int gparml_embedding_grads(gparml_ctx *c)
+{
+    CHECK_CTX(c);
+    if (c->flags & GPARML_FLAG_FIXED_EMBEDDINGS) { gp_set_error("embedding_grads: context has fixed embeddings"); return GPARML_ERR_STATE; }
+    if (!c->have_global_step) { gp_set_error("embedding_grads: global_step first"); return GPARML_ERR_STATE; }
+    GP_TRY(prep_if_needed(c));
+    GP_TRY(record(c, 6));
+    GP_TRY(gp_launch_embed_grads(c));
+    GP_TRY(record(c, 7));
+    return GPARML_OK;
+}
+
+// ---------------------------------------------------------------------------
+// generic arrays
+// ---------------------------------------------------------------------------
+static int resolve(gparml_ctx *c, int id, double **ptr, int64_t *count, bool for_write)
+{
+    const int64_t nq = c->n * c->Q, MM = (int64_t)c->M * c->M;
+    switch (id) {
+        case GPARML_A_X_MU: *ptr = c->x_mu; *count = nq; break;
+        case GPARML_A_X_S: *ptr = c->x_s; *count = nq; break;
+        case GPARML_A_GRAD_D: *ptr = c->grad_d; *count = 2 * nq; break;
+        case GPARML_A_GRAD_LATEST: *ptr = c->grad_latest; *count = 2 * nq; break;
+        case GPARML_A_GRAD_NEW: *ptr = c->grad_new; *count = 2 * nq; break;
+        case GPARML_A_GRAD_OLD: *ptr = c->grad_old; *count = 2 * nq; break;
+        case GPARML_A_STATS: *ptr = c->stats; *count = c->L.count; break;
+        case GPARML_A_KMM: *ptr = c->kmm; *count = MM; break;
+        case GPARML_A_KMM_INV: *ptr = c->kmm_inv; *count = MM; break;
+        case GPARML_A_A_INV: *ptr = c->a_inv; *count = MM; break;
+        case GPARML_A_DF_DKMM: *ptr = c->g_k; *count = MM; break;
+        case GPARML_A_DF_DPSI1Y: *ptr = c->g_1; *count = (int64_t)c->M * c->D; break;
+        case GPARML_A_DF_DPSI2: *ptr = c->g_2; *count = MM; break;
+        case GPARML_A_PSI1: *ptr = c->psi1; *count = c->n * c->M; break;
+        case GPARML_A_GRAD_X_MU: *ptr = c->gx_mu; *count = nq; break;
+        case GPARML_A_GRAD_X_S: *ptr = c->gx_s; *count = nq; break;
+        case GPARML_A_Y: *ptr = c->Y; *count = c->n * c->D; break;
+        case GPARML_A_GRAD_GLOBAL: *ptr = c->glob_out + 1; *count = (int64_t)c->M * c->Q + c->Q + 2; break;
+        default: gp_set_error("unknown array id %d", id); return GPARML_ERR_ARG;
+    }
+    (void)for_write;
+    return GPARML_OK;
+}
+
+extern "C" int64_t gparml_array_count(const gparml_ctx *c, int id)
+{
+    if (!c) return -1;
+    double *p; int64_t n;
+    if (resolve(const_cast<gparml_ctx *>(c), id, &p, &n, false) != GPARML_OK) return -1;
+    return n;
+}
+
+extern "C" int gparml_array_device_ptr(gparml_ctx *c, int id, void **out)
+{
+    CHECK_CTX(c);
+    double *p; int64_t n;
+    GP_TRY(resolve(c, id, &p, &n, false));
+    *out = p;
+    return GPARML_OK;
+}
+
+extern "C" int gparml_download(gparml_ctx *c, int id, double *dst, int64_t count)
+{
+    CHECK_CTX(c);
+    if (id == GPARML_A_PSI1) {
+        GP_TRY(prep_if_needed(c));
+        if (!c->psi1) GP_TRY(dev_alloc(&c->psi1, (size_t)c->n * c->M));
+        GP_TRY(gp_launch_psi1_matrix(c));
+    }
+    double *p; int64_t n;
+    GP_TRY(resolve(c, id, &p, &n, false));
+    if (count != n) { gp_set_error("download(%d): count %lld != %lld", id, (long long)count, (long long)n); return GPARML_ERR_ARG; }
+    if (n > 0 && (!p || !dst)) { gp_set_error("download(%d): array not available", id); return GPARML_ERR_STATE; }
+    if (n > 0) GP_CUDA(cudaMemcpyAsync(dst, p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    GP_CUDA(cudaStreamSynchronize(c->stream));
+    return GPARML_OK;
+}
+
+extern "C" int gparml_upload(gparml_ctx *c, int id, const double *src, int64_t count)
+{
+    CHECK_CTX(c);
+    if (id >= GPARML_A_KMM && id != GPARML_A_KMM && id != GPARML_A_KMM_INV) { gp_set_error("upload(%d): array is read-only", id); return GPARML_ERR_ARG; }
+    double *p; int64_t n;
+    GP_TRY(resolve(c, id, &p, &n, true));
+    if (count != n) { gp_set_error("upload(%d): count %lld != %lld", id, (long long)count, (long long)n); return GPARML_ERR_ARG; }
+    if (n > 0 && (!p || !src)) { gp_set_error("upload(%d): array not available", id); return GPARML_ERR_STATE; }
+    if (n > 0) GP_CUDA(cudaMemcpyAsync(p, src, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    GP_CUDA(cudaStreamSynchronize(c->stream));
+    if (id == GPARML_A_GRAD_D) c->have_dir = true;
+    if (id == GPARML_A_X_MU || id == GPARML_A_X_S) c->have_prep = c->have_stats = false;
+    if (id == GPARML_A_STATS) c->have_stats = true;
+    return GPARML_OK;
+}
+
+// ---------------------------------------------------------------------------
+// named statistics
+// ---------------------------------------------------------------------------
+static int ensure_named_tmp(gparml_ctx *c)
+{
+    const size_t need = (size_t)c->Q * c->M * c->M * 2 + (size_t)c->M * c->M + 16;
+    if (c->named_tmp_count >= need) return GPARML_OK;
+    GP_TRY(dev_alloc(&c->named_tmp, need));
+    c->named_tmp_count = need;
+    return GPARML_OK;
+}
+
+static int d2h(gparml_ctx *c, double *dst, const double *src, size_t count)
+{
+    GP_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    return GPARML_OK;
+}
+
+extern "C" int gparml_stats_expand(gparml_ctx *c, const gparml_named_stats *o)
+{
+    CHECK_CTX(c);
+    if (!o) { gp_set_error("null output struct"); return GPARML_ERR_ARG; }
+    if (!c->have_globals) { gp_set_error("stats_expand: set_globals first"); return GPARML_ERR_STATE; }
+    GP_TRY(ensure_named_tmp(c));
+    const size_t MM = (size_t)c->M * c->M, MD = (size_t)c->M * c->D, QMM = MM * c->Q, MQD = MD * c->Q;
+    double head[ST_HEAD];
+    GP_TRY(d2h(c, head, c->stats, ST_HEAD));
+    GP_CUDA(cudaStreamSynchronize(c->stream));
+    if (o->sum_YYT) *o->sum_YYT = head[ST_YYT];
+    if (o->sum_exp_K_ii) *o->sum_exp_K_ii = head[ST_PSI0];
+    if (o->sum_KL) *o->sum_KL = head[ST_KL];
+    if (o->sum_d_exp_K_ii_d_sf2) *o->sum_d_exp_K_ii_d_sf2 = head[ST_NLOCAL];
+    if (o->sum_exp_K_miY) GP_TRY(d2h(c, o->sum_exp_K_miY, c->stats + c->L.off_p1y, MD));
+    if (o->sum_d_exp_K_miY_d_Z) GP_TRY(d2h(c, o->sum_d_exp_K_miY_d_Z, c->stats + c->L.off_d1z, MQD));
+    if (o->sum_d_exp_K_miY_d_alpha) GP_TRY(d2h(c, o->sum_d_exp_K_miY_d_alpha, c->stats + c->L.off_d1a, MQD));
+    if (o->sum_exp_K_mi_K_im) { GP_TRY(gp_launch_expand(c, c->named_tmp, 0)); GP_TRY(d2h(c, o->sum_exp_K_mi_K_im, c->named_tmp, MM)); GP_CUDA(cudaStreamSynchronize(c->stream)); }
+    if (o->sum_d_exp_K_mi_K_im_d_Z) { GP_TRY(gp_launch_expand(c, c->named_tmp, 1)); GP_TRY(d2h(c, o->sum_d_exp_K_mi_K_im_d_Z, c->named_tmp, QMM)); GP_CUDA(cudaStreamSynchronize(c->stream)); }
+    if (o->sum_d_exp_K_mi_K_im_d_alpha) { GP_TRY(gp_launch_expand(c, c->named_tmp, 2)); GP_TRY(d2h(c, o->sum_d_exp_K_mi_K_im_d_alpha, c->named_tmp, QMM)); GP_CUDA(cudaStreamSynchronize(c->stream)); }
+    if (o->sum_d_exp_K_miY_d_sf2) { GP_TRY(gp_launch_expand(c, c->named_tmp, 3)); GP_TRY(d2h(c, o->sum_d_exp_K_miY_d_sf2, c->named_tmp, MD)); GP_CUDA(cudaStreamSynchronize(c->stream)); }
+    if (o->sum_d_exp_K_mi_K_im_d_sf2) { GP_TRY(gp_launch_expand(c, c->named_tmp, 4)); GP_TRY(d2h(c, o->sum_d_exp_K_mi_K_im_d_sf2, c->named_tmp, MM)); GP_CUDA(cudaStreamSynchronize(c->stream)); }
+    GP_CUDA(cudaStreamSynchronize(c->stream));
+    return GPARML_OK;
+}
+
+extern "C" int gparml_stats_set_named(gparml_ctx *c, const gparml_named_stats *in)
+{
+    CHECK_CTX(c);
+    if (!in) { gp_set_error("null input struct"); return GPARML_ERR_ARG; }
+    if (!c->have_globals) { gp_set_error("stats_set_named: set_globals first"); return GPARML_ERR_STATE; }
+    GP_TRY(ensure_named_tmp(c));
+    const size_t MM = (size_t)c->M * c->M, MD = (size_t)c->M * c->D, QMM = MM * c->Q, MQD = MD * c->Q;
+    double head[ST_HEAD];
+    GP_TRY(d2h(c, head, c->stats, ST_HEAD));
+    GP_CUDA(cudaStreamSynchronize(c->stream));
+    if (in->sum_YYT) head[ST_YYT] = *in->sum_YYT;
+    if (in->sum_exp_K_ii) head[ST_PSI0] = *in->sum_exp_K_ii;
+    if (in->sum_KL) head[ST_KL] = *in->sum_KL;
+    if (in->sum_d_exp_K_ii_d_sf2) head[ST_NLOCAL] = *in->sum_d_exp_K_ii_d_sf2;
+    GP_CUDA(cudaMemcpyAsync(c->stats, head, sizeof(head), cudaMemcpyHostToDevice, c->stream));
+    if (in->sum_exp_K_miY) GP_CUDA(cudaMemcpyAsync(c->stats + c->L.off_p1y, in->sum_exp_K_miY, MD * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (in->sum_d_exp_K_miY_d_Z) GP_CUDA(cudaMemcpyAsync(c->stats + c->L.off_d1z, in->sum_d_exp_K_miY_d_Z, MQD * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (in->sum_d_exp_K_miY_d_alpha) GP_CUDA(cudaMemcpyAsync(c->stats + c->L.off_d1a, in->sum_d_exp_K_miY_d_alpha, MQD * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (in->sum_exp_K_mi_K_im) {
+        double *t_p2 = c->named_tmp, *t_dz = c->named_tmp + MM, *t_da = t_dz + QMM;
+        GP_CUDA(cudaMemcpyAsync(t_p2, in->sum_exp_K_mi_K_im, MM * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        if (in->sum_d_exp_K_mi_K_im_d_Z) GP_CUDA(cudaMemcpyAsync(t_dz, in->sum_d_exp_K_mi_K_im_d_Z, QMM * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        if (in->sum_d_exp_K_mi_K_im_d_alpha) GP_CUDA(cudaMemcpyAsync(t_da, in->sum_d_exp_K_mi_K_im_d_alpha, QMM * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        GP_TRY(gp_launch_compact(c, t_p2, in->sum_d_exp_K_mi_K_im_d_Z ? t_dz : nullptr, in->sum_d_exp_K_mi_K_im_d_alpha ? t_da : nullptr));
+    } else if (in->sum_d_exp_K_mi_K_im_d_Z || in->sum_d_exp_K_mi_K_im_d_alpha) {
+        gp_set_error("stats_set_named: derivative tensors of Psi2 need sum_exp_K_mi_K_im as well");
+        return GPARML_ERR_ARG;
+    }
+    GP_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_stats = true;
+    c->have_global_step = false;
+    return GPARML_OK;
+}
+
+// ---------------------------------------------------------------------------
+// optimiser local state
+// ---------------------------------------------------------------------------
+#define SCG_GUARD(c)                                                                               \
+    CHECK_CTX(c);                                                                                  \
+    if (!(c)->have_shard) { gp_set_error("scg op: upload_shard first"); return GPARML_ERR_STATE; }
+
+extern "C" int gparml_scg_set_grads(gparml_ctx *c) { SCG_GUARD(c); c->have_dir = true; return gp_scg_update(c, 0, 0.0); }
+extern "C" int gparml_scg_get_mu(gparml_ctx *c, double *o) { SCG_GUARD(c); return gp_scg_reduce(c, 0, 0.0, o); }
+extern "C" int gparml_scg_get_kappa(gparml_ctx *c, double *o) { SCG_GUARD(c); return gp_scg_reduce(c, 1, 0.0, o); }
+extern "C" int gparml_scg_get_theta(gparml_ctx *c, double *o) { SCG_GUARD(c); return gp_scg_reduce(c, 2, 0.0, o); }
+extern "C" int gparml_scg_get_current_grad(gparml_ctx *c, double *o) { SCG_GUARD(c); return gp_scg_reduce(c, 3, 0.0, o); }
+extern "C" int gparml_scg_get_gamma(gparml_ctx *c, double *o) { SCG_GUARD(c); return gp_scg_reduce(c, 4, 0.0, o); }
+extern "C" int gparml_scg_get_max_d(gparml_ctx *c, double a, double *o) { SCG_GUARD(c); return gp_scg_reduce(c, 5, a, o); }
+extern "C" int gparml_scg_reset_d(gparml_ctx *c) { SCG_GUARD(c); c->have_dir = true; return gp_scg_update(c, 1, 0.0); }
+extern "C" int gparml_scg_update_d(gparml_ctx *c, double g) { SCG_GUARD(c); return gp_scg_update(c, 2, g); }
+extern "C" int gparml_scg_update_X(gparml_ctx *c, double a)
+{
+    SCG_GUARD(c);
+    c->have_prep = c->have_stats = false;
+    return gp_scg_update(c, 3, a);
+}
+extern "C" int gparml_scg_update_grad_old(gparml_ctx *c) { SCG_GUARD(c); return gp_scg_update(c, 4, 0.0); }
+extern "C" int gparml_scg_update_grad_new(gparml_ctx *c) { SCG_GUARD(c); return gp_scg_update(c, 5, 0.0); }
+
+// ---------------------------------------------------------------------------
+// timing / probes
+// ---------------------------------------------------------------------------
+extern "C" int gparml_enable_timing(gparml_ctx *c, int on)
+{
+    CHECK_CTX(c);
+    c->timing = on != 0;
+    return GPARML_OK;
+}
+
+extern "C" int gparml_phase_times(gparml_ctx *c, double *out5)
+{
+    CHECK_CTX(c);
+    if (!c->timing) { gp_set_error("phase_times: timing not enabled"); return GPARML_ERR_STATE; }
+    GP_CUDA(cudaStreamSynchronize(c->stream));
+    const int pairs[5][2] = {{0, 1}, {1, 2}, {2, 3}, {4, 5}, {6, 7}};
+    for (int i = 0; i < 5; ++i) {
+        float ms = 0.f;
+        cudaError_t e = cudaEventElapsedTime(&ms, c->ev[pairs[i][0]], c->ev[pairs[i][1]]);
+        if (e != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
+        out5[i] = ms;
+    }
+    return GPARML_OK;
+}
+
+extern "C" int gparml_measure_dfma_peak(gparml_ctx *c, double *out)
+{
+    CHECK_CTX(c);
+    return gp_measure_dfma(c, out);
+}

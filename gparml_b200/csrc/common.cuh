@@ -1,0 +1,242 @@
+// Internal declarations shared by the gparml_b200 translation units (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/gparml_b200.h"
+
+#define GP_MAX_Q 16
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+void gp_set_error(const char *fmt, ...);
+#define GP_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            gp_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return GPARML_ERR_CUDA;                                                            \
+        }                                                                                      \
+    } while (0)
+#define GP_TRY(call)                      \
+    do {                                  \
+        int r__ = (call);                 \
+        if (r__ != GPARML_OK) return r__; \
+    } while (0)
+#define GP_LAUNCH_CHECK(ctx)                                                          \
+    do {                                                                              \
+        (ctx)->launches++;                                                            \
+        cudaError_t e__ = cudaGetLastError();                                         \
+        if (e__ != cudaSuccess) {                                                     \
+            gp_set_error("%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return GPARML_ERR_CUDA;                                                   \
+        }                                                                             \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// per-point record layout (written by prep_points, read by the Psi kernels)
+//   rec[0 .. 2Q)   : (mu_q, c_q) interleaved;  c = w (Psi2 records) or a (Psi1 records)
+//   rec[2Q .. 3Q)  : v_q = alpha_q * S_q * c_q
+//   rec[3Q]        : log prefactor  (lc2 = log sf^4 - 1/2 sum log(2 a S + 1),  lc1 = log sf^2 - 1/2 sum log(a S + 1))
+//   padded to an even number of doubles so every record is 16-byte aligned.
+// ---------------------------------------------------------------------------
+__host__ __device__ inline int gp_rec_len(int Q) { return (3 * Q + 2) & ~1; }
+
+// packed partial-sum buffer (see DESIGN.md "packed statistics")
+struct StatLayout {
+    int M, Q, D;
+    int64_t P;        // M (M + 1) / 2 upper-triangular pairs (m <= m'), row-major
+    int64_t off_p1y;  // (M, D)
+    int64_t off_d1z;  // (M, Q, D)
+    int64_t off_d1a;  // (Q, M, D)
+    int64_t off_s0;   // (P)      Psi2
+    int64_t off_tz;   // (Q, P)   sum_n Psi2_n w (mu - zbar)
+    int64_t off_ta;   // (Q, P)   sum_n Psi2_n ((w (mu - zbar))^2 + alpha S w)
+    int64_t count;
+};
+enum { ST_YYT = 0, ST_PSI0 = 1, ST_KL = 2, ST_NLOCAL = 3, ST_HEAD = 4 };
+
+__host__ __device__ inline int64_t gp_pair_index(int M, int a, int b)  // a <= b
+{
+    return (int64_t)a * M - ((int64_t)a * (a - 1)) / 2 + (b - a);
+}
+
+inline StatLayout gp_make_layout(int M, int Q, int D)
+{
+    StatLayout L;
+    L.M = M; L.Q = Q; L.D = D;
+    L.P = (int64_t)M * (M + 1) / 2;
+    L.off_p1y = ST_HEAD;
+    L.off_d1z = L.off_p1y + (int64_t)M * D;
+    L.off_d1a = L.off_d1z + (int64_t)M * Q * D;
+    L.off_s0 = L.off_d1a + (int64_t)Q * M * D;
+    L.off_tz = L.off_s0 + L.P;
+    L.off_ta = L.off_tz + (int64_t)Q * L.P;
+    L.count = L.off_ta + (int64_t)Q * L.P;
+    return L;
+}
+
+// globals as the kernels see them
+struct GlobalsDev {
+    double sf2, beta;
+    double log_sf2;
+    double alpha[GP_MAX_Q];
+};
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+struct gparml_ctx {
+    int device = 0;
+    int M = 0, Q = 0, D = 0;
+    int64_t n_total = 0;
+    int flags = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+
+    // shard
+    int64_t n = 0;         // points in this shard
+    int64_t n_cap = 0;     // allocated capacity
+    int variance_domain = GPARML_VARIANCE_UNCONSTRAINED;
+    bool have_shard = false, have_globals = false, have_prep = false, have_stats = false, have_global_step = false;
+    bool have_dir = false;
+    double *Y = nullptr;        // (n, D)
+    double *x_mu = nullptr;     // (n, Q)
+    double *x_s = nullptr;      // (n, Q) uploaded domain
+    double *grad_d = nullptr, *grad_latest = nullptr, *grad_new = nullptr, *grad_old = nullptr;  // (2, n, Q)
+    double *rec1 = nullptr, *rec2 = nullptr;   // (n, R)
+    double *s_pos = nullptr;    // (n, Q) positive variance of this evaluation
+    double *s_sig = nullptr;    // (n, Q) d softplus / d raw (sigmoid) of this evaluation, 1 if positive domain
+    double *gx_mu = nullptr, *gx_s = nullptr;  // (n, Q) positive-domain gradients
+    double *psi1 = nullptr;     // (n, M) on demand
+    double yyt = 0.0;           // sum_n y_n . y_n of the shard (host copy)
+
+    // globals
+    double *Z = nullptr;        // (M, Q)
+    GlobalsDev h_glob;          // host copy
+    GlobalsDev *d_glob = nullptr;
+    double step_size = 0.0;
+    int2 *pair_idx = nullptr;   // (P) (m, m')
+    double *pair_lk = nullptr;  // (P) -1/4 sum_q alpha_q (z_mq - z_m'q)^2
+    double2 *pair_g = nullptr;  // (P) (lk, Gs) for embed_grads
+
+    // statistics
+    StatLayout L;
+    double *stats = nullptr;    // packed (L.count)
+    double *ws = nullptr;       // workspace for split partial sums
+    size_t ws_bytes = 0;
+    double *red_ws = nullptr;   // small reduction workspace (4096 doubles)
+    int *d_status = nullptr;    // device status word (range / not-PD flags)
+
+    // global step outputs (device)
+    double *kmm = nullptr, *kmm_inv = nullptr, *a_inv = nullptr;
+    double *g_k = nullptr, *g_1 = nullptr, *g_2 = nullptr;
+    double *scratch_x = nullptr, *scratch_w = nullptr;   // (M, M) each, used when M*M does not fit shared memory
+    double *c_mat = nullptr;    // (M, D)
+    double *glob_out = nullptr; // [0]=F, [1..] grad (M*Q + Q + 2), then scalars
+    double *named_tmp = nullptr;  // expansion buffer
+    size_t named_tmp_count = 0;
+
+    // timing
+    bool timing = false;
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double phase_ms[5] = {0, 0, 0, 0, 0};
+};
+
+int gp_ensure_ws(gparml_ctx *c, size_t bytes);
+
+// kernels' host launchers (each returns GPARML_* codes)
+int gp_launch_yyt(gparml_ctx *c, double *host_out);
+int gp_launch_prep(gparml_ctx *c);
+int gp_launch_pair_table(gparml_ctx *c);
+int gp_launch_psi1_stats(gparml_ctx *c);
+int gp_launch_psi2_stats(gparml_ctx *c);
+int gp_launch_psi1_matrix(gparml_ctx *c);
+int gp_launch_global_step(gparml_ctx *c, bool kmm_only);
+int gp_launch_embed_grads(gparml_ctx *c);
+int gp_launch_expand(gparml_ctx *c, double *dev_out, int which);
+int gp_launch_compact(gparml_ctx *c, const double *dev_full_psi2, const double *dev_d2z, const double *dev_d2a);
+int gp_launch_stats_add(gparml_ctx *c, const double *src, double scale);
+int gp_scg_reduce(gparml_ctx *c, int op, double scale, double *host_out);
+int gp_scg_update(gparml_ctx *c, int op, double scale);
+int gp_measure_dfma(gparml_ctx *c, double *out);
+
+// ---------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ double gp_warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic block-wide sum (fixed tree); result valid in every thread.
+// `sh` must hold >= 33 doubles.  blockDim.x must be a multiple of 32.
+__device__ __forceinline__ double gp_block_sum(double v, double *sh)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = gp_warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        double t = (lane < nw) ? sh[lane] : 0.0;
+        t = gp_warp_sum(t);
+        if (lane == 0) sh[32] = t;
+    }
+    __syncthreads();
+    return sh[32];
+}
+
+// ---- mbarrier + 1-D bulk async copy (TMA unit, SASS UBLKCP) -----------------
+__device__ __forceinline__ uint32_t gp_smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void gp_mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gp_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void gp_fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void gp_fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void gp_mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gp_smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void gp_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            gp_smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(gp_smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void gp_mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(gp_smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+#endif

@@ -1,0 +1,216 @@
+// K5: embed_grads -- per-point gradients of the bound w.r.t. the variational means and
+// variances (the reference's second map, "embeddings_mapper").
+//
+// Replaces (citations relative to /root/reference)
+//   partial_terms.py:367-398   grad_X_mu
+//   partial_terms.py:400-431   grad_X_S
+//   local_MapReduce.py:357-360 grad_latest = -[g_mu, g_S * sigmoid(S_raw)]
+// and recomputes Psi2_n on the fly instead of re-building the (n, M, M) tensor a second time
+// (local_MapReduce.py:348 -> partial_terms.py:45-48).
+//
+// With G1 = dF/dPsi1Y (M,D), Gs[p] = G2[m,m'] + G2[m',m] (m<m'), G2[m,m] (m=m'),
+// B[n,m] = sum_d Y[n,d] G1[m,d], wd_q = w_nq (mu_nq - zbar_q), ad_q = a_nq (mu_nq - z_mq):
+//   g_mu[n,q] = -mu_nq - sum_m B Psi1 ad_q - 2 sum_p Gs Psi2_n wd_q
+//   g_S[n,q]  = -1/2 (1 - 1/S_nq) + 1/2 sum_m B Psi1 (ad_q^2 - a_nq) + sum_p Gs Psi2_n (2 wd_q^2 - w_nq)
+//
+// Mapping: the reduction runs over pairs for each point (the opposite direction to psi2_stats),
+// so one thread owns one point and keeps w (Q), mu - z_m/2 (Q), wd (Q) and the 2Q accumulators
+// in registers; Z/2 sits in shared memory and is read as broadcasts; (lk, Gs) per pair is a
+// warp-uniform 16-byte global load.  The grid is (point tiles) x (splits of the m range,
+// balanced by pair count); split partials are combined by embed_finish in a fixed order.
+//
+// Bound: FP64 pipe, 6Q + 21 FP64 instructions per (point, pair).
+#include <math.h>
+
+#include "common.cuh"
+
+#define EMB_THREADS 128
+#define EMB_MAX_SPLITS 32
+
+struct EmbedParams {
+    const double *rec1, *rec2, *Y, *Z, *G1;
+    const double2 *pair_g;
+    int64_t n;
+    int M, D;
+    int m_bounds[EMB_MAX_SPLITS + 1];
+    double *partial;     // [splits][n][2Q + 2]
+};
+
+template <int Q>
+__global__ void __launch_bounds__(EMB_THREADS, (Q <= 10) ? 3 : ((Q <= 13) ? 2 : 1))
+embed_grads_kernel(EmbedParams p)
+{
+    constexpr int R = (3 * Q + 2) & ~1;
+    extern __shared__ __align__(16) double hz[];        // [M][Q] = Z / 2
+    const int tid = threadIdx.x;
+    const int M = p.M;
+    for (int idx = tid; idx < M * Q; idx += EMB_THREADS) hz[idx] = 0.5 * p.Z[idx];
+    __syncthreads();
+
+    int64_t i = (int64_t)blockIdx.x * EMB_THREADS + tid;
+    const bool valid = i < p.n;
+    if (!valid) i = p.n - 1;                             // compute on a real record, never store
+    const double *r1 = p.rec1 + i * R, *r2 = p.rec2 + i * R;
+    const double *y = p.Y + i * p.D;
+    const double lc1 = r1[3 * Q], lc2 = r2[3 * Q];
+    double w[Q], dm[Q], wd[Q], acc_mu[Q], acc_s[Q];
+    double acc_h = 0.0, acc_b = 0.0;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        w[q] = r2[2 * q + 1];
+        acc_mu[q] = 0.0;
+        acc_s[q] = 0.0;
+    }
+    const int m_lo = p.m_bounds[blockIdx.y], m_hi = p.m_bounds[blockIdx.y + 1];
+
+    for (int m = m_lo; m < m_hi; ++m) {
+        const double *hm = hz + m * Q;
+        // ---- Psi1 side (partial_terms.py:388-390, 421-423) -----------------------------
+        {
+            double e = lc1;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const double2 ma = *reinterpret_cast<const double2 *>(r1 + 2 * q);   // (mu_q, a_q)
+                dm[q] = ma.x - hm[q];
+                const double d = dm[q] - hm[q];                                       // mu - z_m
+                wd[q] = ma.y * d;                                                     // ad_q
+                e = fma(-0.5 * wd[q], d, e);
+            }
+            double b = 0.0;
+            const double *g1 = p.G1 + (size_t)m * p.D;
+            for (int d = 0; d < p.D; ++d) b = fma(y[d], g1[d], b);
+            const double h1 = 0.5 * b * exp(e);          // accumulators are scaled by 2 at the end
+            acc_b += h1;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const double t = h1 * wd[q];
+                acc_mu[q] += t;
+                acc_s[q] = fma(0.5 * t, wd[q], acc_s[q]);
+            }
+        }
+        // ---- Psi2 side (partial_terms.py:393, 425-426), pairs (m, m' >= m) -------------
+        const double2 *pg = p.pair_g + gp_pair_index(M, m, m);
+        for (int b = m; b < M; ++b) {
+            const double2 g = __ldg(pg + (b - m));      // (lk, Gs), warp-uniform
+            const double *hb = hz + b * Q;
+            double e0 = g.x + lc2, e1 = 0.0;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const double d = dm[q] - hb[q];          // mu - zbar
+                wd[q] = w[q] * d;
+                if (q & 1) e1 = fma(-wd[q], d, e1);
+                else e0 = fma(-wd[q], d, e0);
+            }
+            const double h = g.y * exp(e0 + e1);
+            acc_h += h;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const double t = h * wd[q];
+                acc_mu[q] += t;
+                acc_s[q] = fma(t, wd[q], acc_s[q]);
+            }
+        }
+    }
+    if (valid) {
+        double *out = p.partial + ((size_t)blockIdx.y * p.n + i) * (2 * Q + 2);
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            out[q] = acc_mu[q];
+            out[Q + q] = acc_s[q];
+        }
+        out[2 * Q] = acc_h;
+        out[2 * Q + 1] = acc_b;
+    }
+}
+
+// Combine the split partials, add the KL terms (partial_terms.py:385,418), apply the softplus
+// chain and the sign flip (local_MapReduce.py:357-360).
+__global__ void __launch_bounds__(256) embed_finish_kernel(const double *__restrict__ partial, int splits, int64_t n, int Q, int R,
+                                                           const double *__restrict__ rec1, const double *__restrict__ rec2,
+                                                           const double *__restrict__ s_pos, const double *__restrict__ s_sig,
+                                                           double *__restrict__ gx_mu, double *__restrict__ gx_s,
+                                                           double *__restrict__ grad_latest)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * Q) return;
+    const int64_t i = idx / Q;
+    const int q = (int)(idx % Q);
+    const int W = 2 * Q + 2;
+    double amu = 0.0, as = 0.0, ah = 0.0, ab = 0.0;
+    for (int s = 0; s < splits; ++s) {
+        const double *pr = partial + ((size_t)s * n + i) * W;
+        amu += pr[q];
+        as += pr[Q + q];
+        ah += pr[2 * Q];
+        ab += pr[2 * Q + 1];
+    }
+    const double mu = rec2[i * R + 2 * q], w = rec2[i * R + 2 * q + 1], a = rec1[i * R + 2 * q + 1];
+    const double S = s_pos[idx];
+    const double gmu = -mu - 2.0 * amu;
+    const double gs = -0.5 * (1.0 - 1.0 / S) + 2.0 * as - w * ah - a * ab;
+    gx_mu[idx] = gmu;
+    gx_s[idx] = gs;
+    grad_latest[idx] = -gmu;
+    grad_latest[n * Q + idx] = -(gs * s_sig[idx]);
+}
+
+template <int Q>
+static int launch_q(gparml_ctx *c)
+{
+    const size_t smem = (size_t)c->M * Q * sizeof(double);
+    GP_CUDA(cudaFuncSetAttribute(embed_grads_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, embed_grads_kernel<Q>, EMB_THREADS, smem));
+    if (occ < 1) occ = 1;
+    const int64_t ntiles = (c->n + EMB_THREADS - 1) / EMB_THREADS;
+    const int64_t slots = (int64_t)c->sm_count * occ;
+    int max_splits = c->M < EMB_MAX_SPLITS ? c->M : EMB_MAX_SPLITS;
+    int best = 1;
+    double best_eff = -1.0;
+    for (int s = 1; s <= max_splits; ++s) {
+        const int64_t total = ntiles * s;
+        const int64_t waves = (total + slots - 1) / slots;
+        const double eff = (double)total / (double)(waves * slots);
+        if (eff > best_eff + 0.02) { best_eff = eff; best = s; }   // prefer fewer splits unless clearly better
+        if (waves >= 8) break;
+    }
+    const int splits = best;
+    EmbedParams p;
+    p.rec1 = c->rec1; p.rec2 = c->rec2; p.Y = c->Y; p.Z = c->Z; p.G1 = c->g_1; p.pair_g = c->pair_g;
+    p.n = c->n; p.M = c->M; p.D = c->D;
+    // split the m range so that every split owns about P / splits pairs (row m has M - m pairs)
+    const double P = (double)c->L.P;
+    p.m_bounds[0] = 0;
+    int m = 0;
+    for (int s = 1; s < splits; ++s) {
+        const double target = P * s / splits;
+        while (m < c->M && (double)gp_pair_index(c->M, m, m) < target) ++m;
+        if (m <= p.m_bounds[s - 1]) m = p.m_bounds[s - 1] + 1;
+        if (m > c->M) m = c->M;
+        p.m_bounds[s] = m;
+    }
+    p.m_bounds[splits] = c->M;
+    GP_TRY(gp_ensure_ws(c, (size_t)splits * c->n * (2 * Q + 2) * sizeof(double)));
+    p.partial = c->ws;
+    dim3 grid((unsigned)ntiles, splits);
+    embed_grads_kernel<Q><<<grid, EMB_THREADS, smem, c->stream>>>(p);
+    GP_LAUNCH_CHECK(c);
+    const int64_t total = c->n * Q;
+    embed_finish_kernel<<<(int)((total + 255) / 256), 256, 0, c->stream>>>(c->ws, splits, c->n, Q, gp_rec_len(Q), c->rec1, c->rec2,
+                                                                           c->s_pos, c->s_sig, c->gx_mu, c->gx_s, c->grad_latest);
+    GP_LAUNCH_CHECK(c);
+    return GPARML_OK;
+}
+
+int gp_launch_embed_grads(gparml_ctx *c)
+{
+    if (c->n == 0) return GPARML_OK;
+    switch (c->Q) {
+#define CASE_Q(q) case q: return launch_q<q>(c);
+        CASE_Q(1) CASE_Q(2) CASE_Q(3) CASE_Q(4) CASE_Q(5) CASE_Q(6) CASE_Q(7) CASE_Q(8)
+        CASE_Q(9) CASE_Q(10) CASE_Q(11) CASE_Q(12) CASE_Q(13) CASE_Q(14) CASE_Q(15) CASE_Q(16)
+#undef CASE_Q
+    }
+    gp_set_error("embed_grads: unsupported Q=%d (1..%d)", c->Q, GP_MAX_Q);
+    return GPARML_ERR_ARG;
+}

@@ -1,0 +1,257 @@
+// Layout conversion between the packed (symmetric-compact) statistics and the reference's
+// named arrays, the optimiser's local-state vector operations (K6), and the DFMA peak probe.
+#include <math.h>
+
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------
+// expand: packed -> reference layouts (parallel_GPLVM.py:142-151)
+//   which 0: sum_exp_K_mi_K_im           (M, M)      = S0[p(m,m')] * scale
+//   which 1: sum_d_exp_K_mi_K_im_d_Z     (M, Q, M)   partial_terms.py:201-203
+//   which 2: sum_d_exp_K_mi_K_im_d_alpha (Q, M, M)   partial_terms.py:279-282
+//   which 3: sum_exp_K_miY * scale       (M, D)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) expand_kernel(const double *__restrict__ stats, int64_t off_s0, int64_t off_tz, int64_t off_ta,
+                                                     int64_t off_p1y, int64_t P, const double *__restrict__ Z,
+                                                     const GlobalsDev *__restrict__ glob, int M, int Q, int D, int which,
+                                                     double scale, double *__restrict__ out)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (which == 0) {
+        if (idx >= (int64_t)M * M) return;
+        const int a = (int)(idx / M), b = (int)(idx % M);
+        const int64_t p = (a <= b) ? gp_pair_index(M, a, b) : gp_pair_index(M, b, a);
+        out[idx] = scale * stats[off_s0 + p];
+    } else if (which == 1) {
+        if (idx >= (int64_t)M * Q * M) return;
+        const int b = (int)(idx % M), q = (int)((idx / M) % Q), a = (int)(idx / ((int64_t)M * Q));
+        const int64_t p = (a <= b) ? gp_pair_index(M, a, b) : gp_pair_index(M, b, a);
+        const double dz = Z[a * Q + q] - Z[b * Q + q];
+        out[idx] = -0.5 * glob->alpha[q] * dz * stats[off_s0 + p] + stats[off_tz + (int64_t)q * P + p];
+    } else if (which == 2) {
+        if (idx >= (int64_t)Q * M * M) return;
+        const int b = (int)(idx % M), a = (int)((idx / M) % M), q = (int)(idx / ((int64_t)M * M));
+        const int64_t p = (a <= b) ? gp_pair_index(M, a, b) : gp_pair_index(M, b, a);
+        const double dz = Z[a * Q + q] - Z[b * Q + q];
+        const double al = glob->alpha[q];
+        out[idx] = -0.25 * dz * dz * stats[off_s0 + p] - stats[off_ta + (int64_t)q * P + p] / (al * al);
+    } else {
+        if (idx >= (int64_t)M * D) return;
+        out[idx] = scale * stats[off_p1y + idx];
+    }
+}
+
+int gp_launch_expand(gparml_ctx *c, double *dev_out, int which)
+{
+    int64_t total;
+    double scale = 1.0;
+    int w = which;
+    switch (which) {
+        case 0: total = (int64_t)c->M * c->M; break;
+        case 1: total = (int64_t)c->M * c->Q * c->M; break;
+        case 2: total = (int64_t)c->Q * c->M * c->M; break;
+        case 3: total = (int64_t)c->M * c->D; scale = 1.0 / c->h_glob.sf2; break;               // partial_terms.py:310-312
+        case 4: total = (int64_t)c->M * c->M; scale = 2.0 / c->h_glob.sf2; w = 0; break;        // partial_terms.py:314-316
+        default: gp_set_error("expand: bad selector %d", which); return GPARML_ERR_ARG;
+    }
+    expand_kernel<<<(int)((total + 255) / 256), 256, 0, c->stream>>>(c->stats, c->L.off_s0, c->L.off_tz, c->L.off_ta, c->L.off_p1y,
+                                                                    c->L.P, c->Z, c->d_glob, c->M, c->Q, c->D, w, scale, dev_out);
+    GP_LAUNCH_CHECK(c);
+    return GPARML_OK;
+}
+
+// compact: reference layouts -> packed (inverse of expand; for set_local_statistics)
+__global__ void __launch_bounds__(256) compact_kernel(const double *__restrict__ psi2, const double *__restrict__ d2z,
+                                                      const double *__restrict__ d2a, const double *__restrict__ Z,
+                                                      const GlobalsDev *__restrict__ glob, int M, int Q, int64_t P,
+                                                      const int2 *__restrict__ pair_idx, double *__restrict__ s0,
+                                                      double *__restrict__ tz, double *__restrict__ ta)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const int2 ab = pair_idx[p];
+    const int a = ab.x, b = ab.y;
+    const double ps = 0.5 * (psi2[(size_t)a * M + b] + psi2[(size_t)b * M + a]);
+    s0[p] = ps;
+    for (int q = 0; q < Q; ++q) {
+        const double dz = Z[a * Q + q] - Z[b * Q + q];
+        const double al = glob->alpha[q];
+        if (d2z) tz[(int64_t)q * P + p] = d2z[((size_t)a * Q + q) * M + b] + 0.5 * al * dz * ps;
+        if (d2a) ta[(int64_t)q * P + p] = -(al * al) * (d2a[((size_t)q * M + a) * M + b] + 0.25 * dz * dz * ps);
+    }
+}
+
+int gp_launch_compact(gparml_ctx *c, const double *dev_full_psi2, const double *dev_d2z, const double *dev_d2a)
+{
+    const int64_t P = c->L.P;
+    compact_kernel<<<(int)((P + 255) / 256), 256, 0, c->stream>>>(dev_full_psi2, dev_d2z, dev_d2a, c->Z, c->d_glob, c->M, c->Q, P,
+                                                                 c->pair_idx, c->stats + c->L.off_s0, c->stats + c->L.off_tz,
+                                                                 c->stats + c->L.off_ta);
+    GP_LAUNCH_CHECK(c);
+    return GPARML_OK;
+}
+
+// stats = (stats + other) * scale  -- in-process reduce of several shards on one device
+__global__ void __launch_bounds__(256) stats_add_kernel(double *__restrict__ dst, const double *__restrict__ src, int64_t count, double scale)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) dst[i] = (dst[i] + src[i]) * scale;
+}
+
+int gp_launch_stats_add(gparml_ctx *c, const double *src, double scale)
+{
+    stats_add_kernel<<<(int)((c->L.count + 255) / 256), 256, 0, c->stream>>>(c->stats, src, c->L.count, scale);
+    GP_LAUNCH_CHECK(c);
+    return GPARML_OK;
+}
+
+// ---------------------------------------------------------------------------
+// K6: optimiser local state (scg_adapted_local_MapReduce.py:29-243) on the device-resident
+// (2, n, Q) vectors.  HBM-bound streaming; reductions are two-stage and deterministic.
+//   reduce ops: 0 mu = <new, d>   1 kappa = <d, d>   2 theta = <d, latest - new>
+//               3 current_grad = <new, new>   4 gamma = <new, old>   5 max |scale * d|
+//   update ops: 0 set_grads (new = old = latest, d = -latest)   1 reset_d (d = -new)
+//               2 update_d (d = scale * d - new)   3 update_X (X += scale * d)
+//               4 grad_old = grad_new   5 grad_new = grad_latest
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) scg_reduce_kernel(int op, double scale, int64_t len, const double *__restrict__ latest,
+                                                         const double *__restrict__ gnew, const double *__restrict__ gold,
+                                                         const double *__restrict__ d, double *__restrict__ partials)
+{
+    __shared__ double sh[33];
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        switch (op) {
+            case 0: acc = fma(gnew[i], d[i], acc); break;
+            case 1: acc = fma(d[i], d[i], acc); break;
+            case 2: acc = fma(d[i], latest[i] - gnew[i], acc); break;
+            case 3: acc = fma(gnew[i], gnew[i], acc); break;
+            case 4: acc = fma(gnew[i], gold[i], acc); break;
+            default: acc = fmax(acc, fabs(scale * d[i])); break;
+        }
+    }
+    if (op == 5) {
+        // block max (order independent, exact)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc = fmax(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double m = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, sh[w]);
+            partials[blockIdx.x] = m;
+        }
+    } else {
+        acc = gp_block_sum(acc, sh);
+        if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) scg_final_kernel(int op, const double *__restrict__ partials, int k, double *__restrict__ dst)
+{
+    __shared__ double sh[33];
+    if (op == 5) {
+        if (threadIdx.x == 0) {
+            double m = 0.0;
+            for (int i = 0; i < k; ++i) m = fmax(m, partials[i]);
+            dst[0] = m;
+        }
+        return;
+    }
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) acc += partials[i];
+    acc = gp_block_sum(acc, sh);
+    if (threadIdx.x == 0) dst[0] = acc;
+}
+
+int gp_scg_reduce(gparml_ctx *c, int op, double scale, double *host_out)
+{
+    const int64_t len = 2 * c->n * c->Q;
+    int blocks = (int)((len + 256 * 8 - 1) / (256 * 8));
+    if (blocks < 1) blocks = 1;
+    if (blocks > 1024) blocks = 1024;
+    scg_reduce_kernel<<<blocks, 256, 0, c->stream>>>(op, scale, len, c->grad_latest, c->grad_new, c->grad_old, c->grad_d, c->red_ws);
+    GP_LAUNCH_CHECK(c);
+    scg_final_kernel<<<1, 256, 0, c->stream>>>(op, c->red_ws, blocks, c->red_ws + 2048);
+    GP_LAUNCH_CHECK(c);
+    GP_CUDA(cudaMemcpyAsync(host_out, c->red_ws + 2048, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    GP_CUDA(cudaStreamSynchronize(c->stream));
+    return GPARML_OK;
+}
+
+__global__ void __launch_bounds__(256) scg_update_kernel(int op, double scale, int64_t len, int64_t half, double *__restrict__ latest,
+                                                         double *__restrict__ gnew, double *__restrict__ gold, double *__restrict__ d,
+                                                         double *__restrict__ x_mu, double *__restrict__ x_s)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        switch (op) {
+            case 0: { const double g = latest[i]; gnew[i] = g; gold[i] = g; d[i] = -g; } break;
+            case 1: d[i] = -gnew[i]; break;
+            case 2: d[i] = __dsub_rn(__dmul_rn(scale, d[i]), gnew[i]); break;   // no FMA contraction: bit-equal to numpy
+            case 3:
+                if (i < half) x_mu[i] = __dadd_rn(x_mu[i], __dmul_rn(scale, d[i]));
+                else x_s[i - half] = __dadd_rn(x_s[i - half], __dmul_rn(scale, d[i]));
+                break;
+            case 4: gold[i] = gnew[i]; break;
+            default: gnew[i] = latest[i]; break;
+        }
+    }
+}
+
+int gp_scg_update(gparml_ctx *c, int op, double scale)
+{
+    const int64_t half = c->n * c->Q, len = 2 * half;
+    if (len == 0) return GPARML_OK;
+    int blocks = (int)((len + 256 * 4 - 1) / (256 * 4));
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    scg_update_kernel<<<blocks, 256, 0, c->stream>>>(op, scale, len, half, c->grad_latest, c->grad_new, c->grad_old, c->grad_d,
+                                                     c->x_mu, c->x_s);
+    GP_LAUNCH_CHECK(c);
+    return GPARML_OK;
+}
+
+// ---------------------------------------------------------------------------
+// FP64 pipe peak probe: 8 independent DFMA chains per thread, no memory traffic.  Gives the
+// denominator for "% of FP64 pipe peak" measured on the box (MEASURED_PEAKS.json has no FP64).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dfma_probe_kernel(int iters, double a, double b, double *__restrict__ sink)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 123.456) sink[0] = s;
+}
+
+int gp_measure_dfma(gparml_ctx *c, double *out)
+{
+    cudaEvent_t e0, e1;
+    GP_CUDA(cudaEventCreate(&e0));
+    GP_CUDA(cudaEventCreate(&e1));
+    const int blocks = c->sm_count * 8, iters = 4096;
+    dfma_probe_kernel<<<blocks, 256, 0, c->stream>>>(64, 0.999999, 1e-9, c->red_ws);   // warm-up
+    GP_LAUNCH_CHECK(c);
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        GP_CUDA(cudaEventRecord(e0, c->stream));
+        dfma_probe_kernel<<<blocks, 256, 0, c->stream>>>(iters, 0.999999, 1e-9, c->red_ws);
+        GP_LAUNCH_CHECK(c);
+        GP_CUDA(cudaEventRecord(e1, c->stream));
+        GP_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        GP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double ops = (double)blocks * 256.0 * (double)iters * 16.0 * 8.0;
+        const double rate = ops / (ms * 1e-3);
+        if (rate > best) best = rate;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *out = best;
+    return GPARML_OK;
+}

@@ -1,0 +1,208 @@
+// K0: prep_points -- per-point derived quantities, KL, tr(YY^T), pair constants.
+//
+// Replaces the mapper glue of the reference (all citations relative to /root/reference):
+//   local_MapReduce.py:205-214 / 333-341  X += step * grad_d (in memory only), S = softplus(S_raw)
+//   partial_terms.py:40                    sum_YYT
+//   partial_terms.py:83-87                 KL
+// and hoists everything that depends on a point but not on an inducing point out of the
+// Psi kernels (SURVEY.md section 7 "compute once per point in K0 and stream them").
+//
+// HBM-bound streaming kernels: each point reads (2 or 4)*Q doubles and writes
+// 2*R + 2*Q doubles (R = 3Q+1 padded to even), fully coalesced through L1.
+#include <math.h>
+
+#include "common.cuh"
+
+#define LIM_VAL 36.04365338911715  // -log(DBL_EPSILON), supporting_functions.py:125
+
+// ---------------------------------------------------------------------------
+// sum of squares of Y (partial_terms.py:40), deterministic two-stage reduction
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sumsq_kernel(const double *__restrict__ y, int64_t count, double *__restrict__ partials)
+{
+    __shared__ double sh[33];
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = y[i];
+        acc = fma(v, v, acc);
+    }
+    acc = gp_block_sum(acc, sh);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+
+// sums `k` partials (stride 1) in a fixed order and writes dst[0] = scale * sum
+__global__ void __launch_bounds__(256) final_sum_kernel(const double *__restrict__ partials, int k, double scale, double *__restrict__ dst)
+{
+    __shared__ double sh[33];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) acc += partials[i];
+    acc = gp_block_sum(acc, sh);
+    if (threadIdx.x == 0) dst[0] = scale * acc;
+}
+
+int gp_launch_yyt(gparml_ctx *c, double *host_out)
+{
+    const int64_t count = c->n * c->D;
+    int blocks = (int)((count + 256 * 8 - 1) / (256 * 8));
+    if (blocks < 1) blocks = 1;
+    if (blocks > 1024) blocks = 1024;
+    sumsq_kernel<<<blocks, 256, 0, c->stream>>>(c->Y, count, c->red_ws);
+    GP_LAUNCH_CHECK(c);
+    final_sum_kernel<<<1, 256, 0, c->stream>>>(c->red_ws, blocks, 1.0, c->red_ws + 2048);
+    GP_LAUNCH_CHECK(c);
+    GP_CUDA(cudaMemcpyAsync(host_out, c->red_ws + 2048, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    GP_CUDA(cudaStreamSynchronize(c->stream));
+    return GPARML_OK;
+}
+
+// ---------------------------------------------------------------------------
+// prep_points
+// ---------------------------------------------------------------------------
+struct PrepParams {
+    int64_t n;
+    int Q, R;
+    const double *x_mu, *x_s, *grad_d;  // grad_d may be null
+    double step;
+    int mode;  // 0 = unconstrained variance (softplus), 1 = positive as given, 2 = fixed embeddings (S as given, KL = 0)
+    const GlobalsDev *glob;
+    double *rec1, *rec2, *s_pos, *s_sig;
+    double *kl_partials;    // [gridDim.x][2]: (kl sum, number of exactly-zero variances)
+    int *status;
+};
+
+__global__ void __launch_bounds__(128) prep_points_kernel(PrepParams p)
+{
+    __shared__ double sh[33];
+    __shared__ GlobalsDev g;
+    if (threadIdx.x == 0) g = *p.glob;
+    __syncthreads();
+    const int Q = p.Q, R = p.R;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double kl = 0.0, zeros = 0.0;
+    if (i < p.n) {
+        double *r1 = p.rec1 + i * R, *r2 = p.rec2 + i * R;
+        double prod1 = 1.0, prod2 = 1.0, klq = 0.0;
+        bool bad = false;
+        for (int q = 0; q < Q; ++q) {
+            double mu = p.x_mu[i * Q + q];
+            double sr = p.x_s[i * Q + q];
+            double S, sig;
+            if (p.mode == 0) {
+                if (p.grad_d != nullptr && p.step != 0.0) {            // local_MapReduce.py:205-211
+                    mu = fma(p.grad_d[i * Q + q], p.step, mu);
+                    sr = fma(p.grad_d[(p.n + i) * Q + q], p.step, sr);
+                }
+                if (!(fabs(sr) < LIM_VAL)) bad = true;                  // supporting_functions.py:154
+                S = log(1.0 + exp(sr));                                // supporting_functions.py:155 (same naive form)
+                sig = 1.0 / (exp(-sr) + 1.0);                          // supporting_functions.py:167
+            } else {
+                S = sr;
+                sig = 1.0;
+            }
+            const double al = g.alpha[q];
+            const double den1 = fma(al, S, 1.0), den2 = fma(2.0 * al, S, 1.0);
+            const double a = al / den1, w = al / den2;
+            prod1 *= den1;
+            prod2 *= den2;
+            r1[2 * q] = mu;  r1[2 * q + 1] = a;  r1[2 * Q + q] = al * S * a;
+            r2[2 * q] = mu;  r2[2 * q + 1] = w;  r2[2 * Q + q] = al * S * w;
+            p.s_pos[i * Q + q] = S;
+            p.s_sig[i * Q + q] = sig;
+            if (p.mode != 2) {                                         // partial_terms.py:83-87
+                if (S == 0.0) { zeros += 1.0; klq = fma(mu, mu, klq); }
+                else klq += S - log(S) + mu * mu;
+            }
+        }
+        r1[3 * Q] = g.log_sf2 - 0.5 * log(prod1);
+        r2[3 * Q] = 2.0 * g.log_sf2 - 0.5 * log(prod2);
+        if (3 * Q + 1 < R) { r1[3 * Q + 1] = 0.0; r2[3 * Q + 1] = 0.0; }
+        kl = 0.5 * (klq - (double)Q);
+        if (bad) atomicOr(p.status, 4);
+    }
+    kl = gp_block_sum(kl, sh);
+    zeros = gp_block_sum(zeros, sh);
+    if (threadIdx.x == 0) {
+        p.kl_partials[2 * blockIdx.x] = kl;
+        p.kl_partials[2 * blockIdx.x + 1] = zeros;
+    }
+}
+
+// Final KL + header of the packed statistics buffer.  One block.
+__global__ void __launch_bounds__(256) prep_finish_kernel(const double *__restrict__ kl_partials, int k, double n_local, int Q, int mode,
+                                                          double yyt, double sf2, double *__restrict__ stats)
+{
+    __shared__ double sh[33];
+    double a = 0.0, z = 0.0;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        a += kl_partials[2 * i];
+        z += kl_partials[2 * i + 1];
+    }
+    a = gp_block_sum(a, sh);
+    z = gp_block_sum(z, sh);
+    if (threadIdx.x == 0) {
+        double kl;
+        if (mode == 2 || z == n_local * (double)Q) kl = 0.0;        // all variances zero: fixed embeddings (partial_terms.py:86-87)
+        else if (z > 0.0) kl = INFINITY;                              // -log(0) for some but not all entries, as numpy would give
+        else kl = a;
+        stats[ST_YYT] = yyt;
+        stats[ST_PSI0] = sf2 * n_local;                               // partial_terms.py:81
+        stats[ST_KL] = kl;
+        stats[ST_NLOCAL] = n_local;                                   // partial_terms.py:318-320
+    }
+}
+
+int gp_launch_prep(gparml_ctx *c)
+{
+    PrepParams p;
+    p.n = c->n;
+    p.Q = c->Q;
+    p.R = gp_rec_len(c->Q);
+    p.x_mu = c->x_mu;
+    p.x_s = c->x_s;
+    p.grad_d = c->have_dir ? c->grad_d : nullptr;
+    p.step = c->step_size;
+    p.mode = (c->flags & GPARML_FLAG_FIXED_EMBEDDINGS) ? 2 : (c->variance_domain == GPARML_VARIANCE_POSITIVE ? 1 : 0);
+    p.glob = c->d_glob;
+    p.rec1 = c->rec1;
+    p.rec2 = c->rec2;
+    p.s_pos = c->s_pos;
+    p.s_sig = c->s_sig;
+    p.status = c->d_status;
+    const int blocks = (int)((c->n + 127) / 128);
+    GP_TRY(gp_ensure_ws(c, (size_t)blocks * 2 * sizeof(double)));
+    p.kl_partials = c->ws;
+    prep_points_kernel<<<blocks, 128, 0, c->stream>>>(p);
+    GP_LAUNCH_CHECK(c);
+    prep_finish_kernel<<<1, 256, 0, c->stream>>>(c->ws, blocks, (double)c->n, c->Q, p.mode, c->yyt, c->h_glob.sf2, c->stats);
+    GP_LAUNCH_CHECK(c);
+    return GPARML_OK;
+}
+
+// ---------------------------------------------------------------------------
+// pair table: (m, m') indices of the upper triangle and the point-independent part
+// of the Psi2 exponent, lk = -1/4 sum_q alpha_q (z_mq - z_m'q)^2  (kernel_exp.py:143)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pair_table_kernel(const double *__restrict__ Z, int M, int Q, const GlobalsDev *__restrict__ glob,
+                                                         int2 *__restrict__ pair_idx, double *__restrict__ pair_lk)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)M * M) return;
+    const int a = (int)(idx / M), b = (int)(idx % M);
+    if (b < a) return;
+    double s = 0.0;
+    for (int q = 0; q < Q; ++q) {
+        const double dz = Z[a * Q + q] - Z[b * Q + q];
+        s = fma(glob->alpha[q] * dz, dz, s);
+    }
+    const int64_t p = gp_pair_index(M, a, b);
+    pair_idx[p] = make_int2(a, b);
+    pair_lk[p] = -0.25 * s;
+}
+
+int gp_launch_pair_table(gparml_ctx *c)
+{
+    const int64_t total = (int64_t)c->M * c->M;
+    pair_table_kernel<<<(int)((total + 255) / 256), 256, 0, c->stream>>>(c->Z, c->M, c->Q, c->d_glob, c->pair_idx, c->pair_lk);
+    GP_LAUNCH_CHECK(c);
+    return GPARML_OK;
+}

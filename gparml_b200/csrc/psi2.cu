@@ -1,0 +1,194 @@
+// K2: psi2_stats -- the (n, m, m', q) exp-product reduction over n.
+//
+// Replaces (citations relative to /root/reference)
+//   partial_terms.py:45-48 -> kernel_exp.py:126-148   Psi2_n (per point, M x M) and its sum :79
+//   partial_terms.py:190-205                          sum_n dPsi2_n/dZ      (M, Q, M)
+//   partial_terms.py:273-284                          sum_n dPsi2_n/dalpha  (Q, M, M)
+// without ever materialising the (n, M, M) tensor the reference keeps (partial_terms.py:45).
+//
+// Formulation.  With w_nq = alpha_q / (2 alpha_q S_nq + 1), zbar = (z_m + z_m')/2,
+// wd_q = w_nq (mu_nq - zbar_q):
+//   Psi2_n[m,m'] = exp( lk[m,m'] + lc2_n - sum_q wd_q (mu_nq - zbar_q) )
+//   S0[p]    = sum_n Psi2_n                     -> sum_exp_K_mi_K_im
+//   TZ[q][p] = sum_n Psi2_n wd_q                -> symmetric part of dPsi2/dZ
+//   TA[q][p] = sum_n Psi2_n (wd_q^2 + v_nq)     -> -alpha_q^2 * (point part of dPsi2/dalpha)
+// over the P = M(M+1)/2 pairs m <= m' only (all three are symmetric in (m, m'); the
+// antisymmetric Kmm-like part of dPsi2/dZ is point independent and added on expansion).
+//
+// Mapping.  One thread owns one pair and keeps its 1 + 2Q accumulators, zbar (Q) and wd (Q) in
+// registers; a CTA of 256 threads owns 256 pairs and walks its slice of the points.  Point
+// records (prep_points) are staged through shared memory by 1-D bulk async copies (TMA unit,
+// SASS UBLKCP) into a 2-stage ring guarded by mbarriers; every thread reads the same record
+// at the same time, so all shared-memory reads are broadcasts.  The grid is
+// (pair tiles) x (n splits), sized to whole waves of resident CTAs; per-split partial sums go
+// to a workspace and are added in a fixed order (deterministic, no atomics).
+//
+// Bound: FP64 pipe.  6Q + 20 FP64 instructions per (point, pair) of which exp() is 18.
+#include <math.h>
+
+#include "common.cuh"
+
+#define PSI2_THREADS 256
+#define PSI2_TN 64       // points per stage
+#define PSI2_STAGES 2
+
+template <int Q>
+__global__ void __launch_bounds__(PSI2_THREADS, 2)
+psi2_stats_kernel(const double *__restrict__ rec2, int64_t n, const double *__restrict__ Z, int64_t P,
+                  const int2 *__restrict__ pair_idx, const double *__restrict__ pair_lk, int64_t n_per_split,
+                  double *__restrict__ partial)
+{
+    constexpr int R = (3 * Q + 2) & ~1;
+    constexpr int NT2 = (Q + 2) / 2;          // double2 loads covering v_0..v_{Q-1} and lc2
+    extern __shared__ __align__(16) double tile[];       // [STAGES][TN][R]
+    __shared__ __align__(8) uint64_t bar[PSI2_STAGES];
+
+    const int tid = threadIdx.x;
+    const int64_t p = (int64_t)blockIdx.x * PSI2_THREADS + tid;
+    const bool valid = p < P;
+    const int2 ab = valid ? pair_idx[p] : make_int2(0, 0);
+    const double lk = valid ? pair_lk[p] : 0.0;
+    double zb[Q], acc[1 + 2 * Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) zb[q] = 0.5 * (Z[ab.x * Q + q] + Z[ab.y * Q + q]);
+#pragma unroll
+    for (int j = 0; j < 1 + 2 * Q; ++j) acc[j] = 0.0;
+
+    const int64_t n_lo = (int64_t)blockIdx.y * n_per_split;
+    const int64_t n_hi = (n_lo + n_per_split < n) ? (n_lo + n_per_split) : n;
+    const int64_t span = n_hi > n_lo ? n_hi - n_lo : 0;
+    const int ntiles = (int)((span + PSI2_TN - 1) / PSI2_TN);
+
+    if (tid == 0) {
+        for (int s = 0; s < PSI2_STAGES; ++s) gp_mbar_init(&bar[s], 1);
+        gp_fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < PSI2_STAGES && s < ntiles; ++s) {
+            const int64_t base = n_lo + (int64_t)s * PSI2_TN;
+            const int cnt = (int)((n_hi - base < PSI2_TN) ? (n_hi - base) : PSI2_TN);
+            const uint32_t bytes = (uint32_t)cnt * R * sizeof(double);
+            gp_mbar_expect_tx(&bar[s], bytes);
+            gp_bulk_g2s(tile + (size_t)s * PSI2_TN * R, rec2 + base * R, bytes, &bar[s]);
+        }
+    }
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int s = t % PSI2_STAGES;
+        const uint32_t parity = (uint32_t)((t / PSI2_STAGES) & 1);
+        const int64_t base = n_lo + (int64_t)t * PSI2_TN;
+        const int cnt = (int)((n_hi - base < PSI2_TN) ? (n_hi - base) : PSI2_TN);
+        gp_mbar_wait(&bar[s], parity);
+        const double *tb = tile + (size_t)s * PSI2_TN * R;
+#pragma unroll 2
+        for (int i = 0; i < cnt; ++i) {
+            const double2 *r = reinterpret_cast<const double2 *>(tb + i * R);
+            double tv[2 * NT2];
+#pragma unroll
+            for (int k = 0; k < NT2; ++k) {
+                const double2 t2 = r[Q + k];
+                tv[2 * k] = t2.x;
+                tv[2 * k + 1] = t2.y;
+            }
+            double wd[Q];
+            double e0 = lk + tv[Q], e1 = 0.0;      // tv[Q] = lc2
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const double2 mw = r[q];           // (mu_q, w_q), broadcast
+                const double d = mw.x - zb[q];
+                wd[q] = mw.y * d;
+                if (q & 1) e1 = fma(-wd[q], d, e1);
+                else e0 = fma(-wd[q], d, e0);
+            }
+            const double psi = exp(e0 + e1);
+            acc[0] += psi;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                acc[1 + q] = fma(psi, wd[q], acc[1 + q]);
+                const double g = fma(wd[q], wd[q], tv[q]);
+                acc[1 + Q + q] = fma(psi, g, acc[1 + Q + q]);
+            }
+        }
+        __syncthreads();      // every thread is done reading stage s
+        if (tid == 0 && t + PSI2_STAGES < ntiles) {
+            const int64_t nb = n_lo + (int64_t)(t + PSI2_STAGES) * PSI2_TN;
+            const int ncnt = (int)((n_hi - nb < PSI2_TN) ? (n_hi - nb) : PSI2_TN);
+            const uint32_t bytes = (uint32_t)ncnt * R * sizeof(double);
+            gp_mbar_expect_tx(&bar[s], bytes);
+            gp_bulk_g2s(tile + (size_t)s * PSI2_TN * R, rec2 + nb * R, bytes, &bar[s]);
+        }
+    }
+
+    if (valid) {
+        double *out = partial + (size_t)blockIdx.y * (1 + 2 * Q) * P + p;
+#pragma unroll
+        for (int j = 0; j < 1 + 2 * Q; ++j) out[(size_t)j * P] = acc[j];
+    }
+}
+
+// stats[off_s0 + j * P + p] = sum over splits (fixed order)
+__global__ void __launch_bounds__(256) psi2_reduce_kernel(const double *__restrict__ partial, int splits, int64_t rows_x_P,
+                                                          double *__restrict__ dst)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows_x_P) return;
+    double a = 0.0;
+    for (int s = 0; s < splits; ++s) a += partial[(size_t)s * rows_x_P + i];
+    dst[i] = a;
+}
+
+template <int Q>
+static int launch_q(gparml_ctx *c)
+{
+    constexpr int R = (3 * Q + 2) & ~1;
+    const size_t smem = (size_t)PSI2_STAGES * PSI2_TN * R * sizeof(double);
+    static bool configured = false;
+    static int occ = 2;
+    if (!configured) {
+        GP_CUDA(cudaFuncSetAttribute(psi2_stats_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, psi2_stats_kernel<Q>, PSI2_THREADS, smem));
+        if (occ < 1) occ = 1;
+        configured = true;
+    }
+    const int64_t P = c->L.P;
+    const int tiles = (int)((P + PSI2_THREADS - 1) / PSI2_THREADS);
+    const int64_t slots = (int64_t)c->sm_count * occ;
+    // number of n-splits: whole waves of resident CTAs, >= 4 point tiles per split, bounded workspace
+    const int64_t rows_x_P = (int64_t)(1 + 2 * Q) * P;
+    int64_t max_splits = (c->n + 4 * PSI2_TN - 1) / (4 * PSI2_TN);
+    const int64_t ws_cap = ((int64_t)256 << 20) / (rows_x_P * (int64_t)sizeof(double));
+    if (max_splits > ws_cap) max_splits = ws_cap;
+    if (max_splits > 65535) max_splits = 65535;
+    if (max_splits < 1) max_splits = 1;
+    int64_t best = 1;
+    double best_eff = -1.0;
+    for (int64_t s = 1; s <= max_splits; ++s) {
+        const int64_t total = (int64_t)tiles * s;
+        const int64_t waves = (total + slots - 1) / slots;
+        if (waves > 8) break;
+        const double eff = (double)total / (double)(waves * slots);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+    }
+    const int splits = (int)best;
+    const int64_t n_per_split = (c->n + splits - 1) / splits;
+    GP_TRY(gp_ensure_ws(c, (size_t)splits * rows_x_P * sizeof(double)));
+    dim3 grid(tiles, splits);
+    psi2_stats_kernel<Q><<<grid, PSI2_THREADS, smem, c->stream>>>(c->rec2, c->n, c->Z, P, c->pair_idx, c->pair_lk, n_per_split, c->ws);
+    GP_LAUNCH_CHECK(c);
+    psi2_reduce_kernel<<<(int)((rows_x_P + 255) / 256), 256, 0, c->stream>>>(c->ws, splits, rows_x_P, c->stats + c->L.off_s0);
+    GP_LAUNCH_CHECK(c);
+    return GPARML_OK;
+}
+
+int gp_launch_psi2_stats(gparml_ctx *c)
+{
+    switch (c->Q) {
+#define CASE_Q(q) case q: return launch_q<q>(c);
+        CASE_Q(1) CASE_Q(2) CASE_Q(3) CASE_Q(4) CASE_Q(5) CASE_Q(6) CASE_Q(7) CASE_Q(8)
+        CASE_Q(9) CASE_Q(10) CASE_Q(11) CASE_Q(12) CASE_Q(13) CASE_Q(14) CASE_Q(15) CASE_Q(16)
+#undef CASE_Q
+    }
+    gp_set_error("psi2_stats: unsupported Q=%d (1..%d)", c->Q, GP_MAX_Q);
+    return GPARML_ERR_ARG;
+}

@@ -1,0 +1,216 @@
+"""GPU parity tests (``-m gpu``): the CUDA path, called through the C ABI, against
+(a) the golden vectors generated from the live reference and (b) the C / numpy oracles on
+seeded inputs at the BASELINE shapes.  Bar: 1e-9 max-norm relative error in fp64
+(BASELINE.json north_star) on the 12 reduced statistics, F, the four global gradients and
+the per-point gradients, single- and multi-shard, step_size in {0, 1e-3}."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, check_against_golden, load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+
+
+def _gpu_evaluate(shards, Z, sf2, alpha, beta, step_size=0.0, fixed_embeddings=False, want_stats=True):
+    from gparml_b200 import _lib
+    from gparml_b200.engine import ShardContext, evaluate
+    M, Q = Z.shape
+    D = shards[0]["Y"].shape[1] if shards[0]["Y"].ndim == 2 else 1
+    N = sum(s["X_mu"].shape[0] for s in shards)
+    ctxs = []
+    try:
+        for s in shards:
+            c = ShardContext(M, Q, D, N, fixed_embeddings=fixed_embeddings)
+            c.upload_shard(s["Y"], s["X_mu"], s["X_S"])
+            if s.get("d") is not None:
+                c.upload(_lib.A_GRAD_D, s["d"])
+            ctxs.append(c)
+        F, grad = evaluate(ctxs, Z, sf2, alpha, beta, step_size=step_size)
+        root = ctxs[0]
+        out = {"global": {"F": F, "grad_Z": grad["Z"], "grad_sf2": grad["sf2"], "grad_alpha": grad["alpha"],
+                          "grad_beta": grad["beta"],
+                          "dF_dKmm": root.download(_lib.A_DF_DKMM, (M, M)),
+                          "dF_dsum_exp_K_miY": root.download(_lib.A_DF_DPSI1Y, (M, D)),
+                          "dF_dsum_exp_K_mi_K_im": root.download(_lib.A_DF_DPSI2, (M, M)),
+                          "Kmm": root.download(_lib.A_KMM, (M, M)),
+                          "Kmm_inv": root.download(_lib.A_KMM_INV, (M, M))},
+               "grad_latest": [] if fixed_embeddings else [c.grad_latest() for c in ctxs]}
+        if want_stats:
+            out["stats"] = root.stats_named()
+        return out
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_cuda_matches_reference_golden(name):
+    g = load_golden(name)
+    res = _gpu_evaluate(g["shards"], g["Z"], g["sf2"], g["alpha"], g["beta"], step_size=g["step_size"],
+                        fixed_embeddings=g["fixed_embeddings"])
+    errs = check_against_golden(res, g, TOL, "CUDA vs reference golden " + name)
+    print(name, "max rel err %.2e (cond Kmm %.1f)" % (max(errs.values()), float(g["glob_cond_Kmm"])))
+
+
+def _shards_of(p, parts):
+    from gparml_b200.synthetic import split_rows
+    out = []
+    for lo, hi in split_rows(p["N"], parts):
+        sh = dict(Y=p["Y"][lo:hi], X_mu=p["X_mu"][lo:hi], X_S=p["X_S"][lo:hi])
+        if "d" in p:
+            sh["d"] = p["d"][:, lo:hi]
+        out.append(sh)
+    return out
+
+
+# (config, N_parity, shards, step)  -- SURVEY.md 8d parity protocol, BASELINE shapes
+FULL_SHAPE_CASES = [
+    ("c1", 1000, 4, 1e-3),
+    ("c2", 8192, 1, 0.0),
+    ("c3", 8192, 1, 0.0),
+    ("c3", 4099, 8, 1e-3),      # ragged 8-shard split, prime N
+    ("c4", 384, 2, 0.0),
+]
+
+
+@pytest.mark.parametrize("cfg,n,parts,step", FULL_SHAPE_CASES)
+def test_cuda_matches_c_oracle_full_shapes(cfg, n, parts, step):
+    from gparml_b200.synthetic import CONFIGS, make_problem
+    from oracle import c_oracle
+    k = CONFIGS[cfg]
+    p = make_problem(n, k["M"], k["Q"], k["D"], seed=int(cfg[1]), fixed_embeddings=k["fixed_embeddings"],
+                     generic_hypers=True, with_direction=not k["fixed_embeddings"])
+    shards = _shards_of(p, parts)
+    ref = c_oracle.evaluate(shards, p["Z"], p["sf2"], p["alpha"], p["beta"], step_size=step,
+                            fixed_embeddings=k["fixed_embeddings"])
+    res = _gpu_evaluate(shards, p["Z"], p["sf2"], p["alpha"], p["beta"], step_size=step,
+                        fixed_embeddings=k["fixed_embeddings"])
+    errs = {}
+    for key, v in ref["stats"].items():
+        errs[key] = relerr(res["stats"][key], v)
+    for key in ("F", "grad_Z", "grad_alpha", "grad_sf2", "grad_beta", "dF_dKmm", "dF_dsum_exp_K_miY",
+                "dF_dsum_exp_K_mi_K_im"):
+        errs[key] = relerr(res["global"][key], ref["global"][key])
+    for i, (a, b) in enumerate(zip(res["grad_latest"], ref["grad_latest"])):
+        errs["grad_latest_%d" % i] = relerr(a, b)
+    print(cfg, n, parts, "log10 cond(Kmm) = %.2f" % np.log10(ref["global"]["cond_Kmm"]),
+          "max rel err %.2e at %s" % (max(errs.values()), max(errs, key=errs.get)))
+    bad = {k2: v for k2, v in errs.items() if not v <= TOL}
+    assert not bad, bad
+
+
+def test_statistics_are_additive_over_shards():
+    """Size-independent property: 1-shard and 5-shard evaluations agree (the sums are
+    exact up to fp64 reassociation)."""
+    from gparml_b200.synthetic import make_problem
+    p = make_problem(3001, 20, 3, 2, seed=7, generic_hypers=True)
+    a = _gpu_evaluate(_shards_of(p, 1), p["Z"], p["sf2"], p["alpha"], p["beta"])
+    b = _gpu_evaluate(_shards_of(p, 5), p["Z"], p["sf2"], p["alpha"], p["beta"])
+    for k in a["stats"]:
+        assert relerr(b["stats"][k], a["stats"][k]) < 1e-12, k
+    assert abs(a["global"]["F"] - b["global"]["F"]) < 1e-9 * abs(a["global"]["F"])
+    assert relerr(np.concatenate(b["grad_latest"], axis=1), a["grad_latest"][0]) < 1e-10
+
+
+def test_evaluation_is_deterministic():
+    from gparml_b200.synthetic import make_problem
+    p = make_problem(2000, 30, 4, 3, seed=8, generic_hypers=True)
+    a = _gpu_evaluate(_shards_of(p, 1), p["Z"], p["sf2"], p["alpha"], p["beta"])
+    b = _gpu_evaluate(_shards_of(p, 1), p["Z"], p["sf2"], p["alpha"], p["beta"])
+    assert a["global"]["F"] == b["global"]["F"]
+    assert np.array_equal(a["global"]["grad_Z"], b["global"]["grad_Z"])
+    assert np.array_equal(a["grad_latest"][0], b["grad_latest"][0])
+
+
+def test_finite_differences_through_cuda_path():
+    """The reference's own test strategy (test.py:62-93,150-201,270-296): analytic gradients
+    against finite differences of the bound -- here central differences through the CUDA path
+    on the fixture shape D=7, Q=2, N=5, M=10."""
+    g = load_golden("t5")
+    sh = g["shards"]
+
+    def F_of(**kw):
+        a = dict(Z=g["Z"], sf2=g["sf2"], alpha=g["alpha"], beta=g["beta"])
+        shards = sh
+        for k, v in kw.items():
+            if k in a:
+                a[k] = v
+            else:
+                shards = [dict(sh[0], **{k: v})]
+        return _gpu_evaluate(shards, a["Z"], a["sf2"], a["alpha"], a["beta"], want_stats=False)
+
+    base = F_of()
+    h = 1e-6
+    for (j, k) in [(0, 0), (7, 1)]:
+        Zp, Zm = g["Z"].copy(), g["Z"].copy(); Zp[j, k] += h; Zm[j, k] -= h
+        fd = (F_of(Z=Zp)["global"]["F"] - F_of(Z=Zm)["global"]["F"]) / (2 * h)
+        assert abs(fd - base["global"]["grad_Z"][j, k]) <= 2e-6 * max(1.0, abs(fd))
+    fd = (F_of(sf2=g["sf2"] + h)["global"]["F"] - F_of(sf2=g["sf2"] - h)["global"]["F"]) / (2 * h)
+    assert abs(fd - base["global"]["grad_sf2"]) <= 2e-6 * max(1.0, abs(fd))
+    fd = (F_of(beta=g["beta"] + h)["global"]["F"] - F_of(beta=g["beta"] - h)["global"]["F"]) / (2 * h)
+    assert abs(fd - base["global"]["grad_beta"]) <= 2e-6 * max(1.0, abs(fd))
+    ap, am = g["alpha"].copy(), g["alpha"].copy(); ap[1] += h; am[1] -= h
+    fd = (F_of(alpha=ap)["global"]["F"] - F_of(alpha=am)["global"]["F"]) / (2 * h)
+    assert abs(fd - base["global"]["grad_alpha"][1]) <= 2e-6 * max(1.0, abs(fd))
+    mp, mm = sh[0]["X_mu"].copy(), sh[0]["X_mu"].copy(); mp[2, 1] += h; mm[2, 1] -= h
+    fd = (F_of(X_mu=mp)["global"]["F"] - F_of(X_mu=mm)["global"]["F"]) / (2 * h)
+    assert abs(fd + base["grad_latest"][0][0, 2, 1]) <= 2e-6 * max(1.0, abs(fd))
+    sp, sm_ = sh[0]["X_S"].copy(), sh[0]["X_S"].copy(); sp[3, 0] += h; sm_[3, 0] -= h
+    fd = (F_of(X_S=sp)["global"]["F"] - F_of(X_S=sm_)["global"]["F"]) / (2 * h)
+    assert abs(fd + base["grad_latest"][0][1, 3, 0]) <= 2e-6 * max(1.0, abs(fd))
+
+
+def test_error_mapping_not_pd_and_range():
+    """Device-side numerical failure surfaces as the exception types the reference's
+    optimiser wrapper survives (scg_adapted.py:55)."""
+    from gparml_b200.engine import ShardContext
+    rng = np.random.default_rng(0)
+    M, Q, D, n = 6, 2, 2, 40
+    Z = rng.standard_normal((M, Q))
+    with ShardContext(M, Q, D, n) as c:
+        c.upload_shard(rng.standard_normal((n, D)), rng.standard_normal((n, Q)), rng.standard_normal((n, Q)) - 1.0)
+        c.set_globals(Z, 1.0, np.ones(Q), 1.0)
+        c.statistics()
+        F, _ = c.global_step()
+        assert np.isfinite(F)
+        # a negative-definite "Psi2" makes Kmm + beta*Psi2 indefinite -> failed Cholesky pivot
+        c.set_stats_named({"sum_exp_K_mi_K_im": -10.0 * np.eye(M)})
+        with pytest.raises(np.linalg.LinAlgError):
+            c.global_step()
+        bad = rng.standard_normal((n, Q)); bad[5, 1] = 40.0   # supporting_functions.py:154 assert
+        c.upload_shard(rng.standard_normal((n, D)), rng.standard_normal((n, Q)), bad)
+        c.set_globals(rng.standard_normal((M, Q)), 1.0, np.ones(Q), 1.0)
+        with pytest.raises(AssertionError):
+            c.statistics()
+
+
+def test_scg_local_ops_match_numpy():
+    from gparml_b200 import _lib
+    from gparml_b200.engine import ShardContext
+    from oracle import gparml_oracle as O
+    rng = np.random.default_rng(3)
+    n, Q = 777, 5
+    with ShardContext(4, Q, 2, n) as c:
+        mu0, s0 = rng.standard_normal((n, Q)), rng.standard_normal((n, Q))
+        c.upload_shard(rng.standard_normal((n, 2)), mu0, s0)
+        st = [dict(latest=rng.standard_normal((2, n, Q)), X_mu=mu0.copy(), X_S=s0.copy())]
+        c.upload(_lib.A_GRAD_LATEST, st[0]["latest"])
+        c.scg_set_grads(); O.scg_set_grads(st)
+        st[0]["latest"] = rng.standard_normal((2, n, Q)); c.upload(_lib.A_GRAD_LATEST, st[0]["latest"])
+        assert c.scg_get_mu() == pytest.approx(O.scg_get_mu(st), rel=1e-12)
+        assert c.scg_get_kappa() == pytest.approx(O.scg_get_kappa(st), rel=1e-12)
+        assert c.scg_get_theta() == pytest.approx(O.scg_get_theta(st), rel=1e-11)
+        assert c.scg_get_current_grad() == pytest.approx(O.scg_get_current_grad(st), rel=1e-12)
+        assert c.scg_get_max_d(0.37) == O.scg_get_max_d(st, 0.37)
+        c.scg_update_X(0.37); O.scg_update_X(st, 0.37)
+        assert np.array_equal(c.download(_lib.A_X_MU, (n, Q)), st[0]["X_mu"])
+        assert np.array_equal(c.download(_lib.A_X_S, (n, Q)), st[0]["X_S"])
+        c.scg_update_grad_old(); O.scg_update_grad_old(st)
+        c.scg_update_grad_new(); O.scg_update_grad_new(st)
+        assert c.scg_get_gamma() == pytest.approx(O.scg_get_gamma(st), rel=1e-12)
+        c.scg_update_d(0.81); O.scg_update_d(st, 0.81)
+        assert np.allclose(c.download(_lib.A_GRAD_D, (2, n, Q)), st[0]["d"], rtol=1e-15, atol=0)
+        c.scg_reset_d(); O.scg_reset_d(st)
+        assert np.array_equal(c.download(_lib.A_GRAD_D, (2, n, Q)), st[0]["d"])
