@@ -557,3 +557,70 @@ extern "C" int gparml_measure_dfma_peak(gparml_ctx *c, double *out)
     CHECK_CTX(c);
     return gp_measure_dfma(c, out);
 }
+
+// ---------------------------------------------------------------------------
+// partial_terms helper surface: Kmm-side derivative tensors and chain-rule contractions
+// ---------------------------------------------------------------------------
+int gp_launch_kmm_deriv(gparml_ctx *c, int which, double *dev_out);
+int gp_launch_grad_Z_contract(gparml_ctx *c, const double *A, const double *B, const double *C, const double *E, const double *G,
+                              const double *H, double *out);
+int gp_launch_grad_q_contract(gparml_ctx *c, int nq, const double *A, const double *B, const double *C, const double *E,
+                              const double *G, const double *H, double *out);
+
+extern "C" int gparml_kmm_derivative(gparml_ctx *c, int which, double *out)
+{
+    CHECK_CTX(c);
+    if (!c->have_globals || !out || which < 0 || which > 2) { gp_set_error("kmm_derivative: set_globals first / bad args"); return GPARML_ERR_ARG; }
+    GP_TRY(ensure_named_tmp(c));
+    const size_t total = which == 2 ? (size_t)c->M * c->M : (size_t)c->M * c->M * c->Q;
+    GP_TRY(gp_launch_kmm_deriv(c, which, c->named_tmp));
+    GP_TRY(d2h(c, out, c->named_tmp, total));
+    GP_CUDA(cudaStreamSynchronize(c->stream));
+    return GPARML_OK;
+}
+
+// grad_Z (which = 0, out (M,Q)), grad_alpha (which = 1, out (Q)) or the matrix part of
+// grad_sf2 (which = 2, out (1)) from six caller-owned host tensors in the reference's layouts.
+extern "C" int gparml_grad_contract(gparml_ctx *c, int which, const double *dF_dKmm, const double *dKmm_dx,
+                                    const double *dF_dPsi1Y, const double *dPsi1Y_dx, const double *dF_dPsi2,
+                                    const double *dPsi2_dx, double *out)
+{
+    CHECK_CTX(c);
+    if (!dF_dKmm || !dKmm_dx || !dF_dPsi1Y || !dPsi1Y_dx || !dF_dPsi2 || !dPsi2_dx || !out || which < 0 || which > 2) {
+        gp_set_error("grad_contract: null tensor or bad selector");
+        return GPARML_ERR_ARG;
+    }
+    const size_t MM = (size_t)c->M * c->M, MD = (size_t)c->M * c->D;
+    const size_t mult = which == 2 ? 1 : (size_t)c->Q;
+    const size_t need = 2 * MM + MD + mult * (2 * MM + MD) + (size_t)c->M * c->Q + 16;
+    GP_TRY(gp_ensure_ws(c, need * sizeof(double)));
+    double *A = c->ws, *G = A + MM, *C = G + MM, *B = C + MD, *H = B + mult * MM, *E = H + mult * MM, *o = E + mult * MD;
+    GP_CUDA(cudaMemcpyAsync(A, dF_dKmm, MM * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    GP_CUDA(cudaMemcpyAsync(G, dF_dPsi2, MM * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    GP_CUDA(cudaMemcpyAsync(C, dF_dPsi1Y, MD * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    GP_CUDA(cudaMemcpyAsync(B, dKmm_dx, mult * MM * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    GP_CUDA(cudaMemcpyAsync(H, dPsi2_dx, mult * MM * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    GP_CUDA(cudaMemcpyAsync(E, dPsi1Y_dx, mult * MD * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    size_t nout;
+    if (which == 0) { GP_TRY(gp_launch_grad_Z_contract(c, A, B, C, E, G, H, o)); nout = (size_t)c->M * c->Q; }
+    else { GP_TRY(gp_launch_grad_q_contract(c, (int)mult, A, B, C, E, G, H, o)); nout = mult; }
+    GP_TRY(d2h(c, out, o, nout));
+    GP_CUDA(cudaStreamSynchronize(c->stream));
+    return GPARML_OK;
+}
+
+// In-process reduce across devices: stats += packed buffer of a context on ANOTHER device
+// (peer copy into scratch, then the same fixed-order add).
+extern "C" int gparml_stats_add_peer(gparml_ctx *c, gparml_ctx *other, double scale)
+{
+    CHECK_CTX(c);
+    if (!other || other->L.count != c->L.count) { gp_set_error("stats_add_peer: incompatible contexts"); return GPARML_ERR_ARG; }
+    GP_CUDA(cudaSetDevice(other->device));
+    GP_CUDA(cudaStreamSynchronize(other->stream));
+    GP_CUDA(cudaSetDevice(c->device));
+    GP_TRY(gp_ensure_ws(c, (size_t)c->L.count * sizeof(double)));
+    GP_CUDA(cudaMemcpyPeerAsync(c->ws, c->device, other->stats, other->device, (size_t)c->L.count * sizeof(double), c->stream));
+    GP_TRY(gp_launch_stats_add(c, c->ws, scale));
+    c->have_global_step = false;
+    return GPARML_OK;
+}

@@ -255,3 +255,100 @@ int gp_measure_dfma(gparml_ctx *c, double *out)
     *out = best;
     return GPARML_OK;
 }
+
+// ---------------------------------------------------------------------------
+// Kmm-side derivative tensors (partial_terms.py:146-160, 247-254, 306-308)
+//   which 0: dKmm_dZ     (M, Q, M) = -alpha_q (z_aq - z_bq) Kmm[a,b]
+//   which 1: dKmm_dalpha (Q, M, M) = -1/2 Kmm[a,b] (z_aq - z_bq)^2
+//   which 2: dKmm_dsf2   (M, M)    = Kmm / sf2
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) kmm_deriv_kernel(const double *__restrict__ kmm, const double *__restrict__ Z,
+                                                        const GlobalsDev *__restrict__ glob, int M, int Q, int which,
+                                                        double *__restrict__ out)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (which == 0) {
+        if (idx >= (int64_t)M * Q * M) return;
+        const int b = (int)(idx % M), q = (int)((idx / M) % Q), a = (int)(idx / ((int64_t)M * Q));
+        out[idx] = -glob->alpha[q] * (Z[a * Q + q] - Z[b * Q + q]) * kmm[(size_t)a * M + b];
+    } else if (which == 1) {
+        if (idx >= (int64_t)Q * M * M) return;
+        const int b = (int)(idx % M), a = (int)((idx / M) % M), q = (int)(idx / ((int64_t)M * M));
+        const double dz = Z[a * Q + q] - Z[b * Q + q];
+        out[idx] = -0.5 * kmm[(size_t)a * M + b] * dz * dz;
+    } else {
+        if (idx >= (int64_t)M * M) return;
+        out[idx] = kmm[idx] / glob->sf2;
+    }
+}
+
+int gp_launch_kmm_deriv(gparml_ctx *c, int which, double *dev_out)
+{
+    const int64_t total = which == 2 ? (int64_t)c->M * c->M : (int64_t)c->M * c->M * c->Q;
+    kmm_deriv_kernel<<<(int)((total + 255) / 256), 256, 0, c->stream>>>(c->kmm, c->Z, c->d_glob, c->M, c->Q, which, dev_out);
+    GP_LAUNCH_CHECK(c);
+    return GPARML_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Chain-rule contractions with caller-supplied tensors (partial_terms.grad_Z :207-240,
+// grad_alpha :286-299, grad_sf2 :322-333).  One block per output element, fixed-order sums.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) grad_Z_contract_kernel(const double *__restrict__ A /*dF_dKmm (M,M)*/,
+                                                              const double *__restrict__ B /*dKmm_dZ (M,Q,M)*/,
+                                                              const double *__restrict__ C /*dF_dPsi1Y (M,D)*/,
+                                                              const double *__restrict__ E /*dPsi1Y_dZ (M,Q,D)*/,
+                                                              const double *__restrict__ G /*dF_dPsi2 (M,M)*/,
+                                                              const double *__restrict__ H /*dPsi2_dZ (M,Q,M)*/,
+                                                              int M, int Q, int D, double *__restrict__ out)
+{
+    __shared__ double sh[33];
+    const int j = blockIdx.x / Q, k = blockIdx.x % Q;
+    const double *Bjk = B + ((size_t)j * Q + k) * M, *Hjk = H + ((size_t)j * Q + k) * M, *Ejk = E + ((size_t)j * Q + k) * D;
+    double s = 0.0;
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        // row j and column j of an (M, M) mask; the doubly-hit [j, j] entry counts once (partial_terms.py:226-231)
+        const double a = (m == j) ? A[(size_t)j * M + j] : (A[(size_t)j * M + m] + A[(size_t)m * M + j]);
+        s = fma(a, Bjk[m], s);
+        s = fma(2.0 * G[(size_t)j * M + m], Hjk[m], s);
+    }
+    for (int d = threadIdx.x; d < D; d += blockDim.x) s = fma(C[(size_t)j * D + d], Ejk[d], s);
+    s = gp_block_sum(s, sh);
+    if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
+// out[q] = sum A*B[q] + sum C*E[q] + sum G*H[q]   (B, H: (Q,M,M); E: (Q,M,D)).  With Q = 1 and
+// scalars folded by the caller this also serves grad_sf2.
+__global__ void __launch_bounds__(256) grad_q_contract_kernel(const double *__restrict__ A, const double *__restrict__ B,
+                                                              const double *__restrict__ C, const double *__restrict__ E,
+                                                              const double *__restrict__ G, const double *__restrict__ H,
+                                                              int M, int D, double *__restrict__ out)
+{
+    __shared__ double sh[33];
+    const int q = blockIdx.x;
+    const size_t MM = (size_t)M * M, MD = (size_t)M * D;
+    double s = 0.0;
+    for (size_t i = threadIdx.x; i < MM; i += blockDim.x) {
+        s = fma(A[i], B[q * MM + i], s);
+        s = fma(G[i], H[q * MM + i], s);
+    }
+    for (size_t i = threadIdx.x; i < MD; i += blockDim.x) s = fma(C[i], E[q * MD + i], s);
+    s = gp_block_sum(s, sh);
+    if (threadIdx.x == 0) out[q] = s;
+}
+
+int gp_launch_grad_Z_contract(gparml_ctx *c, const double *A, const double *B, const double *C, const double *E, const double *G,
+                              const double *H, double *out)
+{
+    grad_Z_contract_kernel<<<c->M * c->Q, 128, 0, c->stream>>>(A, B, C, E, G, H, c->M, c->Q, c->D, out);
+    GP_LAUNCH_CHECK(c);
+    return GPARML_OK;
+}
+
+int gp_launch_grad_q_contract(gparml_ctx *c, int nq, const double *A, const double *B, const double *C, const double *E,
+                              const double *G, const double *H, double *out)
+{
+    grad_q_contract_kernel<<<nq, 256, 0, c->stream>>>(A, B, C, E, G, H, c->M, c->D, out);
+    GP_LAUNCH_CHECK(c);
+    return GPARML_OK;
+}

@@ -163,6 +163,40 @@ class ShardContext(object):
         other.synchronize()
         _lib.check(self._lib.gparml_stats_add(self._h, ctypes.c_void_p(other.stats_device_ptr()), float(scale)))
 
+    def stats_add_any(self, other, scale=1.0):
+        """stats_add that also works when ``other`` lives on a different GPU of this process."""
+        if other.device == self.device:
+            return self.stats_add(other, scale)
+        _lib.check(self._lib.gparml_stats_add_peer(self._h, other._h, float(scale)))
+
+    def stats_copy_from(self, other):
+        if other.device != self.device:
+            # zero-copy is impossible across devices: go through the peer add on a cleared buffer
+            self.upload(_lib.A_STATS, np.zeros(self.stats_count))
+            return self.stats_add_any(other, 1.0)
+        other.synchronize()
+        _lib.check(self._lib.gparml_stats_copy(self._h, ctypes.c_void_p(other.stats_device_ptr())))
+
+    def kmm_derivative(self, which):
+        shape = {0: (self.M, self.Q, self.M), 1: (self.Q, self.M, self.M), 2: (self.M, self.M)}[which]
+        out = np.empty(shape, dtype=np.float64)
+        _lib.check(self._lib.gparml_kmm_derivative(self._h, which, _lib.ptr(out)))
+        return out
+
+    def grad_contract(self, which, dF_dKmm, dKmm_dx, dF_dP1Y, dP1Y_dx, dF_dP2, dP2_dx):
+        M, Q, D = self.M, self.Q, self.D
+        lead = {0: (M, Q), 1: (Q, M), 2: (M,)}[which]
+        shp_k = {0: (M, Q, M), 1: (Q, M, M), 2: (M, M)}[which]
+        shp_1 = {0: (M, Q, D), 1: (Q, M, D), 2: (M, D)}[which]
+        a = _lib.as_f64(dF_dKmm, (M, M)); b = _lib.as_f64(dKmm_dx, shp_k)
+        c = _lib.as_f64(dF_dP1Y, (M, D)); e = _lib.as_f64(dP1Y_dx, shp_1)
+        g = _lib.as_f64(dF_dP2, (M, M)); h = _lib.as_f64(dP2_dx, shp_k)
+        out = np.empty({0: (M, Q), 1: (Q,), 2: (1,)}[which], dtype=np.float64)
+        del lead
+        _lib.check(self._lib.gparml_grad_contract(self._h, which, _lib.ptr(a), _lib.ptr(b), _lib.ptr(c), _lib.ptr(e),
+                                                  _lib.ptr(g), _lib.ptr(h), _lib.ptr(out)))
+        return out
+
     def stats_torch_view(self):
         """Zero-copy torch view (float64, cuda) of the packed device buffer, for
         ``torch.distributed.all_reduce`` over NCCL."""
@@ -277,18 +311,16 @@ def evaluate(contexts, Z, sf2, alpha, beta, step_size=0.0, reduce_fn=None):
         c.statistics()
     root = contexts[0]
     for c in contexts[1:]:
-        root.stats_add(c)
+        root.stats_add_any(c)
     if reduce_fn is not None:
         reduce_fn(root)
     F, grad = root.global_step()
     if not root.fixed_embeddings:
         if len(contexts) > 1:
-            root.synchronize()
-            packed_ptr = root.stats_device_ptr()
             for c in contexts[1:]:
                 # every shard needs the reduced sums and the partial derivatives
                 # (local_MapReduce.py:315-321,350-354): replicate the global step
-                _lib.check(c._lib.gparml_stats_copy(c._h, ctypes.c_void_p(packed_ptr)))
+                c.stats_copy_from(root)
                 c.global_step()
         for c in contexts:
             c.embedding_grads()

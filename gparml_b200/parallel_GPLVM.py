@@ -1,0 +1,225 @@
+"""Python-3 replay of the reference driver's evaluation protocol
+(``parallel_GPLVM.py:78-369``; the reference file is Python-2-only).  It is a *caller* of the
+hot path: option handling, the flat parameter vector with its softplus transforms, the
+per-evaluation sequence cache -> statistics_MR -> global statistics/derivatives ->
+embeddings_MR, timing dictionary and the final ``'f'`` evaluation are kept as in the
+reference so that the ``b200_MapReduce`` backend is exercised exactly the way
+``local_MapReduce`` is.  ``options['parallel']`` selects the backend ('b200' here).
+"""
+import os
+import pickle
+import time
+
+import numpy
+
+from . import transforms as sp
+from .scg_adapted import SCG_adapted
+
+options = {}
+map_reduce = None
+time_acc = {
+    'time_acc_statistics_map_reduce': [], 'time_acc_statistics_mapper': [], 'time_acc_statistics_reducer': [],
+    'time_acc_calculate_global_statistics': [], 'time_acc_embeddings_MR': [], 'time_acc_embeddings_MR_mapper': [],
+}
+
+DEFAULTS = dict(parallel='b200', iterations=5, M=2, Q=2, D=4, init='PCA', load=False, keep=False,
+                fixed_embeddings=False, fixed_beta=False, optimiser='SCG_adapted', drop_out_fraction=0,
+                local_no_pool=False, b200_write_files=True)
+
+
+def default_options(**kw):
+    o = dict(DEFAULTS)
+    o.update(kw)
+    for need in ('input', 'embeddings', 'statistics', 'tmp'):
+        if need not in o:
+            raise ValueError("option %r is required (parallel_GPLVM.py:479-496)" % need)
+        if not os.path.isdir(o[need]):
+            raise IOError("folder %s does not exist" % o[need])
+    return o
+
+
+def main(opt_param):
+    """parallel_GPLVM.py:78-131."""
+    global options, map_reduce
+    options = opt_param
+    if options['parallel'] == 'b200':
+        from . import b200_MapReduce
+        map_reduce = b200_MapReduce
+    else:
+        raise Exception("backend %r is not available here (b200 only)" % options['parallel'])
+    options = map_reduce.init(options)
+    options, global_statistics = init_statistics(map_reduce, options)
+    x0 = flatten_global_statistics(options, global_statistics)
+    x0 = numpy.array([sp.transform_back(b, x) for b, x in zip(options['flat_global_statistics_bounds'], x0)])
+    if options['optimiser'] != 'SCG_adapted':
+        raise Exception("only the SCG_adapted optimiser is replayed here")
+    x_opt = SCG_adapted(likelihood_and_gradient, x0, options['embeddings'], options['fixed_embeddings'],
+                        display=options.get('display', True), maxiters=options['iterations'], xtol=0, ftol=0, gtol=0)
+    flat_array = x_opt[0]
+    options['iteration'] = len(x_opt[1]) - 1
+    clean(options)
+    likelihood_and_gradient(flat_array, 'f')          # parallel_GPLVM.py:120: the checkpoint evaluation
+    map_reduce.flush(options)
+    with open(options['statistics'] + '/time_acc.obj', 'wb') as f:
+        pickle.dump(time_acc, f)
+    with open(options['statistics'] + '/nlml_acc.obj', 'wb') as f:
+        pickle.dump(x_opt[1], f)
+    with open(options['statistics'] + '/time_acc_SCG_adapted.obj', 'wb') as f:
+        pickle.dump(x_opt[4], f)
+    return x_opt
+
+
+def init_statistics(map_reduce, options):
+    """parallel_GPLVM.py:134-216 (Z from k-means of the first embeddings + 0.05 noise)."""
+    options['global_statistics_names'] = {
+        'Z': (options['M'], options['Q']), 'sf2': (1, 1), 'alpha': (1, options['Q']), 'beta': (1, 1)}
+    options['accumulated_statistics_names'] = [
+        'sum_YYT', 'sum_exp_K_mi_K_im', 'sum_exp_K_miY', 'sum_exp_K_ii', 'sum_KL',
+        'sum_d_exp_K_miY_d_Z', 'sum_d_exp_K_mi_K_im_d_Z', 'sum_d_exp_K_miY_d_alpha',
+        'sum_d_exp_K_mi_K_im_d_alpha', 'sum_d_exp_K_ii_d_sf2', 'sum_d_exp_K_miY_d_sf2',
+        'sum_d_exp_K_mi_K_im_d_sf2']
+    options['partial_derivatives_names'] = ['F', 'dF_dsum_exp_K_ii', 'dF_dKmm', 'dF_dsum_exp_K_miY',
+                                            'dF_dsum_exp_K_mi_K_im']
+    options['cache_names'] = ['Kmm', 'Kmm_inv']
+    if not options['load']:
+        names = sorted(os.listdir(options['input'] + '/'))
+        fid = 0
+        embeddings = map_reduce.load(options['embeddings'] + '/' + names[fid] + '.embedding.npy')
+        while embeddings.shape[0] < options['M']:
+            fid += 1
+            embeddings = numpy.concatenate(
+                (embeddings, map_reduce.load(options['embeddings'] + '/' + names[fid] + '.embedding.npy')))
+        if embeddings.shape[1] != options['Q']:
+            raise Exception('Given Q does not equal existing embedding data dimensions!')
+        import scipy.cluster.vq as cl
+        Z = cl.kmeans(embeddings, options['M'])[0]
+        missing = options['M'] - Z.shape[0]
+        if missing > 0:
+            Z = numpy.concatenate((Z, embeddings[:missing]))
+        Z = Z + numpy.random.randn(options['M'], options['Q']) * 0.05
+        global_statistics = {'Z': Z, 'sf2': numpy.array([[1.0]]), 'alpha': numpy.ones((1, options['Q'])),
+                             'beta': numpy.array([[1.0]])}
+    else:
+        global_statistics = {}
+        for key in options['global_statistics_names']:
+            global_statistics[key] = map_reduce.load(options['statistics'] + '/global_statistics_' + key + '_f.npy')
+    bounds = {'Z': [(None, None)] * (options['M'] * options['Q']), 'sf2': [(0, None)],
+              'alpha': [(0, None)] * options['Q'], 'beta': [(0, None)]}
+    flat = []
+    for key in options['global_statistics_names']:
+        flat = flat + bounds[key]
+    options['flat_global_statistics_bounds'] = flat
+    return options, global_statistics
+
+
+def likelihood_and_gradient(flat_array, iteration, step_size=0):
+    """parallel_GPLVM.py:222-279: returns (-F, -grad * transform_grad)."""
+    global options, map_reduce, time_acc
+    flat_t = numpy.array([sp.transform(b, x) for b, x in zip(options['flat_global_statistics_bounds'], flat_array)])
+    global_statistics = rebuild_global_statistics(options, flat_t)
+    options['i'] = iteration
+    options['step_size'] = step_size
+    clean(options)
+    write = options.get('b200_write_files', True)
+    if write:
+        for key in global_statistics:
+            map_reduce.save(options['statistics'] + '/global_statistics_' + key + '_' + str(options['i']) + '.npy',
+                            global_statistics[key])
+    t0 = time.time()
+    if write:
+        map_reduce.cache(options, global_statistics)
+        files, mapper_time, reducer_time = map_reduce.statistics_MR(options)
+        t1 = time.time()
+        partial_derivatives, accumulated, partial_terms = calculate_global_statistics(
+            options, global_statistics, files, map_reduce)
+        gradient = calculate_global_derivatives(options, partial_derivatives, accumulated, global_statistics, partial_terms)
+        partial_terms.close()
+        likelihood = partial_derivatives['F']
+        t2 = time.time()
+        embeddings_time = []
+        if not options['fixed_embeddings']:
+            embeddings_time = map_reduce.embeddings_MR(options)
+        t3 = time.time()
+    else:
+        likelihood, g = map_reduce.fast_evaluation(options, global_statistics)
+        gradient = {'Z': g['Z'], 'sf2': numpy.array([[g['sf2']]]), 'alpha': g['alpha'].reshape(1, -1),
+                    'beta': numpy.array([[g['beta']]])}
+        mapper_time, reducer_time, embeddings_time = [], [], []
+        t1 = t2 = t3 = time.time()
+    time_acc['time_acc_statistics_map_reduce'] += [t1 - t0]
+    time_acc['time_acc_statistics_mapper'] += [mapper_time]
+    time_acc['time_acc_statistics_reducer'] += [reducer_time]
+    time_acc['time_acc_calculate_global_statistics'] += [t2 - t1]
+    if not options['fixed_embeddings']:
+        time_acc['time_acc_embeddings_MR'] += [t3 - t2]
+        time_acc['time_acc_embeddings_MR_mapper'] += [embeddings_time]
+    gradient = flatten_global_statistics(options, gradient)
+    gradient = numpy.array([g * sp.transform_grad(b, x) for b, x, g in
+                            zip(options['flat_global_statistics_bounds'], flat_array, gradient)])
+    return -1 * likelihood, -1 * gradient
+
+
+def flatten_global_statistics(options, global_statistics):
+    """parallel_GPLVM.py:286-290, in the key order of global_statistics_names."""
+    return numpy.concatenate([numpy.asarray(global_statistics[k], dtype=float).flatten()
+                              for k in options['global_statistics_names']])
+
+
+def rebuild_global_statistics(options, flat_array):
+    """parallel_GPLVM.py:292-299."""
+    out, start = {}, 0
+    for key, shape in options['global_statistics_names'].items():
+        size = shape[0] * shape[1]
+        out[key] = flat_array[start:start + size].reshape(shape)
+        start += size
+    return out
+
+
+def calculate_global_statistics(options, global_statistics, accumulated_statistics_files, map_reduce):
+    """parallel_GPLVM.py:302-334."""
+    accumulated = {}
+    for statistic, file_name in accumulated_statistics_files:
+        accumulated[statistic] = map_reduce.load(file_name)
+    partial_terms = map_reduce.load_partial_terms(options, global_statistics)
+    map_reduce.load_cache(options, partial_terms)
+    partial_terms.set_local_statistics(accumulated['sum_YYT'], accumulated['sum_exp_K_mi_K_im'],
+                                       accumulated['sum_exp_K_miY'], accumulated['sum_exp_K_ii'], accumulated['sum_KL'])
+    partial_derivatives = {
+        'F': partial_terms.logmarglik(), 'dF_dsum_exp_K_ii': partial_terms.dF_dexp_K_ii(),
+        'dF_dsum_exp_K_miY': partial_terms.dF_dexp_K_miY(),
+        'dF_dsum_exp_K_mi_K_im': partial_terms.dF_dexp_K_mi_K_im(), 'dF_dKmm': partial_terms.dF_dKmm()}
+    for key in partial_derivatives:
+        map_reduce.save(options['statistics'] + '/partial_derivatives_' + key + '_' + str(options['i']) + '.npy',
+                        partial_derivatives[key])
+    return partial_derivatives, accumulated, partial_terms
+
+
+def calculate_global_derivatives(options, pd, acc, global_statistics, partial_terms):
+    """parallel_GPLVM.py:336-369."""
+    grad_Z = partial_terms.grad_Z(pd['dF_dKmm'], partial_terms.dKmm_dZ(), pd['dF_dsum_exp_K_miY'],
+                                  acc['sum_d_exp_K_miY_d_Z'], pd['dF_dsum_exp_K_mi_K_im'], acc['sum_d_exp_K_mi_K_im_d_Z'])
+    grad_alpha = partial_terms.grad_alpha(pd['dF_dKmm'], partial_terms.dKmm_dalpha(), pd['dF_dsum_exp_K_miY'],
+                                          acc['sum_d_exp_K_miY_d_alpha'], pd['dF_dsum_exp_K_mi_K_im'],
+                                          acc['sum_d_exp_K_mi_K_im_d_alpha'])
+    grad_sf2 = partial_terms.grad_sf2(pd['dF_dKmm'], partial_terms.dKmm_dsf2(), pd['dF_dsum_exp_K_ii'],
+                                      acc['sum_d_exp_K_ii_d_sf2'], pd['dF_dsum_exp_K_miY'], acc['sum_d_exp_K_miY_d_sf2'],
+                                      pd['dF_dsum_exp_K_mi_K_im'], acc['sum_d_exp_K_mi_K_im_d_sf2'])
+    gradient = {'Z': grad_Z, 'sf2': numpy.array([[grad_sf2]]), 'alpha': numpy.asarray(grad_alpha).reshape(1, -1)}
+    if not options['fixed_beta']:
+        gradient['beta'] = numpy.array([[partial_terms.grad_beta()]])
+    else:
+        gradient['beta'] = numpy.zeros((1, 1))
+    return gradient
+
+
+def clean(options):
+    """parallel_GPLVM.py:373-404."""
+    if options['keep'] or options['i'] == 'f':
+        return
+    groups = (('global_statistics_', options['global_statistics_names']),
+              ('accumulated_statistics_', options['accumulated_statistics_names']),
+              ('partial_derivatives_', options['partial_derivatives_names']), ('cache_', options['cache_names']))
+    for prefix, names in groups:
+        for key in names:
+            for it in (-1, options['i'] - 1, options['i']):
+                map_reduce.remove(options['statistics'] + '/' + prefix + key + '_' + str(it) + '.npy')

@@ -159,6 +159,24 @@ int gparml_update_global_statistics(gparml_ctx *ctx);
  * sign flip of local_MapReduce.py:357-360; result stays on device (GRAD_LATEST). */
 int gparml_embedding_grads(gparml_ctx *ctx);
 
+/* ---- partial_terms helper surface ------------------------------------------ */
+/* Kmm-side derivative tensors to caller-owned host memory:
+ *   which 0: dKmm_dZ     (M,Q,M)  partial_terms.py:146-160
+ *   which 1: dKmm_dalpha (Q,M,M)  partial_terms.py:247-254
+ *   which 2: dKmm_dsf2   (M,M)    partial_terms.py:306-308
+ * Needs Kmm (gparml_update_global_statistics or gparml_global_step). */
+int gparml_kmm_derivative(gparml_ctx *ctx, int which, double *out);
+/* Chain-rule contraction of six caller-supplied host tensors (reference layouts):
+ *   which 0: grad_Z     -> out (M,Q)   partial_terms.py:207-240
+ *   which 1: grad_alpha -> out (Q)     partial_terms.py:286-299
+ *   which 2: matrix part of grad_sf2 -> out (1)  partial_terms.py:322-333
+ *            (the caller adds dF_dexp_K_ii * dexp_K_ii_dsf2, a product of two scalars) */
+int gparml_grad_contract(gparml_ctx *ctx, int which, const double *dF_dKmm, const double *dKmm_dx,
+                         const double *dF_dPsi1Y, const double *dPsi1Y_dx, const double *dF_dPsi2,
+                         const double *dPsi2_dx, double *out);
+/* stats = (stats + packed buffer of a context on ANOTHER device) * scale (peer copy + add). */
+int gparml_stats_add_peer(gparml_ctx *ctx, gparml_ctx *other, double scale);
+
 /* ---- generic transfers ---------------------------------------------------- */
 int64_t gparml_array_count(const gparml_ctx *ctx, int array_id);
 int gparml_download(gparml_ctx *ctx, int array_id, double *dst, int64_t count);

@@ -1,0 +1,196 @@
+"""GPU tests of the drop-in boundary: the ``partial_terms`` mirror driven the way the
+reference's own tests drive the original (test.py), the ``b200_MapReduce`` module driven by
+the replayed ``parallel_GPLVM`` protocol, and the device-resident optimiser state."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _mirror_from_golden(name):
+    from gparml_b200.partial_terms import partial_terms
+    from oracle import gparml_oracle as O
+    g = load_golden(name)
+    sh = g["shards"][0]
+    N, D = sh["Y"].shape
+    M, Q = g["Z"].shape
+    pt = partial_terms(g["Z"].copy(), g["sf2"], g["alpha"].copy(), g["beta"], M, Q, N, D)
+    S = O.softplus(sh["X_S"])
+    pt.set_data(sh["Y"], sh["X_mu"], S, is_set_statistics=True)
+    return g, sh, S, pt
+
+
+def test_partial_terms_mirror_matches_reference_golden():
+    """Same call sequence as test.py:setUp + scg_adapted-example.py:140-211 on the fixture
+    D=7, Q=2, N=5, M=10."""
+    g, sh, S, pt = _mirror_from_golden("t5")
+    M, Q = g["Z"].shape
+    assert relerr(pt.Kmm, g["glob_Kmm"]) < 1e-12 and relerr(pt.Kmm_inv, g["glob_Kmm_inv"]) < 1e-9
+    assert relerr(pt.sum_exp_K_mi_K_im, g["stat_sum_exp_K_mi_K_im"]) < 1e-12
+    assert relerr(pt.exp_K_miY, g["stat_sum_exp_K_miY"]) < 1e-12
+    assert abs(pt.KL - float(g["stat_sum_KL"])) < 1e-12 * abs(float(g["stat_sum_KL"]))
+    assert abs(pt.logmarglik() - float(g["glob_F"])) < 1e-9 * abs(float(g["glob_F"]))
+    dF_dKmm, dF_d1, dF_d2, dF_d0 = pt.dF_dKmm(), pt.dF_dexp_K_miY(), pt.dF_dexp_K_mi_K_im(), pt.dF_dexp_K_ii()
+    assert relerr(dF_dKmm, g["glob_dF_dKmm"]) < 1e-9
+    assert relerr(dF_d1, g["glob_dF_dsum_exp_K_miY"]) < 1e-9
+    assert relerr(dF_d2, g["glob_dF_dsum_exp_K_mi_K_im"]) < 1e-9
+    gZ = pt.grad_Z(dF_dKmm, pt.dKmm_dZ(), dF_d1, pt.dexp_K_miY_dZ(), dF_d2, pt.dexp_K_mi_K_im_dZ())
+    ga = pt.grad_alpha(dF_dKmm, pt.dKmm_dalpha(), dF_d1, pt.dexp_K_miY_dalpha(), dF_d2, pt.dexp_K_mi_K_im_dalpha())
+    gs = pt.grad_sf2(dF_dKmm, pt.dKmm_dsf2(), dF_d0, pt.dexp_K_ii_dsf2(), dF_d1, pt.dexp_K_miY_dsf2(), dF_d2,
+                     pt.dexp_K_mi_K_im_dsf2())
+    assert relerr(gZ, g["glob_grad_Z"]) < 1e-9
+    assert relerr(ga, g["glob_grad_alpha"]) < 1e-9
+    assert relerr(gs, g["glob_grad_sf2"]) < 1e-9
+    assert relerr(pt.grad_beta(), g["glob_grad_beta"]) < 1e-9
+    from oracle import gparml_oracle as O
+    gl = -np.array([pt.grad_X_mu(), pt.grad_X_S() * O.softplus_grad(sh["X_S"])])
+    assert relerr(gl, g["grad_latest_0"]) < 1e-9
+    assert relerr(pt.exp_K_mi, O.psi1(g["Z"], g["sf2"], g["alpha"], sh["X_mu"], S)) < 1e-12
+    assert pt.hyp.sf == pytest.approx(g["sf2"] ** 0.5) and np.allclose(pt.hyp.ard, g["alpha"] ** -0.5)
+    pt.close()
+
+
+def test_partial_terms_mirror_finite_differences_like_reference_tests():
+    """test.py:62-93 (Z), :150-184 (sf via hyp.sf += d), :186-201 (beta), :270-296 (mu, S):
+    attribute pokes + set_data + update_global_statistics, forward differences, 1 % bar."""
+    g, sh, S, pt = _mirror_from_golden("t5")
+    M, Q = g["Z"].shape
+    F0 = pt.logmarglik()
+    dF_dKmm, dF_d1, dF_d2 = pt.dF_dKmm(), pt.dF_dexp_K_miY(), pt.dF_dexp_K_mi_K_im()
+    gZ = pt.grad_Z(dF_dKmm, pt.dKmm_dZ(), dF_d1, pt.dexp_K_miY_dZ(), dF_d2, pt.dexp_K_mi_K_im_dZ())
+    g_beta = pt.grad_beta()
+    g_mu, g_S = pt.grad_X_mu(), pt.grad_X_S()
+    h = 1e-6
+    Zp = g["Z"].copy(); Zp[4, 1] += h
+    pt.Z = Zp
+    pt.set_data(sh["Y"], sh["X_mu"], S, is_set_statistics=True)
+    pt.update_global_statistics()
+    assert abs((pt.logmarglik() - F0) / h - gZ[4, 1]) < 0.01 * abs(gZ[4, 1])
+    pt.Z = g["Z"].copy()
+    pt.beta += h
+    pt.set_data(sh["Y"], sh["X_mu"], S, is_set_statistics=True)
+    pt.update_global_statistics()
+    assert abs((pt.logmarglik() - F0) / h - g_beta) < 0.01 * abs(g_beta)
+    pt.beta -= h
+    mu = sh["X_mu"].copy(); mu[1, 0] += h
+    pt.set_data(sh["Y"], mu, S, is_set_statistics=True)
+    assert abs((pt.logmarglik() - F0) / h - g_mu[1, 0]) < 0.01 * abs(g_mu[1, 0])
+    S2 = S.copy(); S2[2, 1] += h
+    pt.set_data(sh["Y"], sh["X_mu"], S2, is_set_statistics=True)
+    assert abs((pt.logmarglik() - F0) / h - g_S[2, 1]) < 0.01 * abs(g_S[2, 1])
+    pt.close()
+
+
+def _write_problem(tmp_path, p, parts):
+    from gparml_b200.synthetic import split_rows
+    dirs = {}
+    for d in ("input", "embeddings", "statistics", "tmp"):
+        (tmp_path / d).mkdir()
+        dirs[d] = str(tmp_path / d)
+    for i, (lo, hi) in enumerate(split_rows(p["N"], parts)):
+        np.savetxt(os.path.join(dirs["input"], "easy_%d" % i), p["Y"][lo:hi], delimiter=",", fmt="%.17g")
+    return dirs
+
+
+def test_driver_protocol_c1_matches_oracle_scg(tmp_path):
+    """BASELINE config 1 (README minimal run): local MapReduce protocol, 5 SCG iterations,
+    M=2 Q=2 D=4, N=1k in 4 shards -- the replayed driver on the b200 backend against the same
+    driver on the oracle backend (objective trace and final parameters)."""
+    from gparml_b200 import b200_MapReduce, parallel_GPLVM as drv
+    from gparml_b200.scg_adapted import SCG_adapted
+    from gparml_b200.synthetic import make_problem
+    from oracle import c_oracle
+    from oracle_backend import OracleBackend
+    p = make_problem(1000, 2, 2, 4, seed=1)
+    dirs = _write_problem(tmp_path, p, 4)
+    np.random.seed(0)
+    opts = drv.default_options(M=2, Q=2, D=4, iterations=5, init="PCA", display=False, **dirs)
+    opts = b200_MapReduce.init(opts)
+    assert opts["N"] == 1000
+    opts, gs = drv.init_statistics(b200_MapReduce, opts)
+    x0 = drv.flatten_global_statistics(opts, gs)
+    x0 = np.array([drv.sp.transform_back(b, x) for b, x in zip(opts["flat_global_statistics_bounds"], x0)])
+    names = sorted(os.listdir(dirs["input"]))
+    shards = [dict(Y=np.genfromtxt(os.path.join(dirs["input"], n), delimiter=","),
+                   X_mu=np.load(os.path.join(dirs["embeddings"], n + ".embedding.npy")),
+                   X_S=np.load(os.path.join(dirs["embeddings"], n + ".variance.npy"))) for n in names]
+    drv.options, drv.map_reduce = opts, b200_MapReduce
+    try:
+        xg, flog_g, _, _, tacc = SCG_adapted(drv.likelihood_and_gradient, x0.copy(), opts["embeddings"], False,
+                                             display=False, maxiters=5, xtol=0, ftol=0, gtol=0)
+        # file protocol artefacts of the last evaluation exist where the reference writes them
+        assert os.path.exists(os.path.join(dirs["statistics"], "accumulated_statistics_sum_exp_K_mi_K_im_%d.npy" % opts["i"]))
+        assert os.path.exists(os.path.join(dirs["statistics"], "cache_Kmm_inv_%d.npy" % opts["i"]))
+        assert len(tacc["embeddings_get_grads_mu"]) > 0
+        be = OracleBackend(shards, 2, 2, evaluate=c_oracle.evaluate)
+        xo, flog_o, _, _, _ = SCG_adapted(be.f_and_gradf, x0.copy(), "unused", False, display=False, maxiters=5,
+                                          xtol=0, ftol=0, gtol=0, local_ops=be)
+        assert relerr(np.array(flog_g), np.array(flog_o)) < 1e-8
+        assert relerr(xg, xo) < 1e-6
+        assert flog_g[-1] < flog_g[0]
+        # device-resident embeddings after the run == oracle's files-in-memory
+        b200_MapReduce.flush(opts)
+        for n, s in zip(names, be.st):
+            assert relerr(np.load(os.path.join(dirs["embeddings"], n + ".embedding.npy")), s["X_mu"]) < 1e-6
+            assert relerr(np.load(os.path.join(dirs["embeddings"], n + ".grad_d.npy")), s["d"]) < 1e-5
+        # the file-less fast path gives the same evaluation
+        f1, g1 = drv.likelihood_and_gradient(xg, 7, 0)
+        opts["b200_write_files"] = False
+        f2, g2 = drv.likelihood_and_gradient(xg, 8, 0)
+        assert abs(f1 - f2) <= 1e-12 * abs(f1) and relerr(g2, g1) < 1e-10
+    finally:
+        b200_MapReduce.close()
+
+
+def test_main_runs_fixed_embeddings_sparse_gp(tmp_path):
+    """--fixed_embeddings (BASELINE config 2 shape, small N): the whole main() sequence incl. the
+    final 'f' checkpoint evaluation (parallel_GPLVM.py:120)."""
+    from gparml_b200 import b200_MapReduce, parallel_GPLVM as drv
+    from gparml_b200.synthetic import make_problem, split_rows
+    p = make_problem(600, 20, 4, 1, seed=2, fixed_embeddings=True)
+    dirs = _write_problem(tmp_path, p, 2)
+    for i, (lo, hi) in enumerate(split_rows(600, 2)):
+        np.save(os.path.join(dirs["embeddings"], "easy_%d.embedding.npy" % i), p["X_mu"][lo:hi])
+    np.random.seed(1)
+    opts = drv.default_options(M=20, Q=4, D=1, iterations=3, fixed_embeddings=True, display=False, **dirs)
+    try:
+        x_opt = drv.main(opts)
+        flog = x_opt[1]
+        assert len(flog) == 4 and flog[-1] <= flog[0]
+        assert os.path.exists(os.path.join(dirs["statistics"], "partial_derivatives_F_f.npy"))
+        assert os.path.exists(os.path.join(dirs["statistics"], "global_statistics_Z_f.npy"))
+        assert os.path.exists(os.path.join(dirs["statistics"], "nlml_acc.obj"))
+    finally:
+        b200_MapReduce.close()
+
+
+def test_dropout_rescales_like_reference(tmp_path):
+    """--drop_out_fraction (local_MapReduce.py:121-129,263-264): kept-shard sums scaled by total/kept."""
+    from gparml_b200 import b200_MapReduce, parallel_GPLVM as drv
+    from gparml_b200.synthetic import make_problem
+    p = make_problem(400, 5, 2, 3, seed=3)
+    dirs = _write_problem(tmp_path, p, 4)
+    np.random.seed(5)
+    opts = drv.default_options(M=5, Q=2, D=3, iterations=1, init="random", display=False, **dirs)
+    opts = b200_MapReduce.init(opts)
+    opts, gs = drv.init_statistics(b200_MapReduce, opts)
+    try:
+        opts["i"], opts["step_size"] = 0, 0
+        b200_MapReduce.cache(opts, gs)
+        files, _, _ = b200_MapReduce.statistics_MR(opts)
+        full = {k: np.load(f) for k, f in files}
+        opts["drop_out_fraction"] = 0.5
+        np.random.seed(11)
+        files, _, _ = b200_MapReduce.statistics_MR(opts)
+        kept = list(b200_MapReduce.non_dropped_out_nodes)
+        assert 1 <= len(kept) <= 4
+        part = {k: np.load(f) for k, f in files}
+        # N-proportional statistic: kept points * (4 / kept shards) (equal shard sizes here)
+        assert part["sum_d_exp_K_ii_d_sf2"] == pytest.approx(full["sum_d_exp_K_ii_d_sf2"])
+        assert part["sum_exp_K_mi_K_im"].shape == (5, 5)
+    finally:
+        b200_MapReduce.close()

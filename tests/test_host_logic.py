@@ -1,0 +1,102 @@
+"""CPU tests of the host-side logic around the hot path: the py3 SCG replay, the flat
+parameter transforms, and the world_size-2 (gloo) reduce plumbing of the N > 1 path."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+from gparml_b200 import transforms as T
+from gparml_b200.scg_adapted import SCG_adapted
+from gparml_b200.synthetic import make_problem, split_rows
+from oracle import gparml_oracle as O
+from oracle_backend import OracleBackend
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_transforms_match_oracle():
+    x = np.array([-3.0, 0.0, 2.0])
+    assert np.allclose([T.transform((0, None), v) for v in x], O.softplus(x))
+    assert np.allclose([T.transform_grad((0, None), v) for v in x], O.softplus_grad(x))
+    assert T.transform((None, None), -7.0) == -7.0 and T.transform_grad((None, None), 3.0) == 1
+    assert np.allclose(T.transformVar_back(T.transformVar(x)), x)
+    with pytest.raises(AssertionError):
+        T.transformVar(np.array([37.0]))
+
+
+def test_scg_minimises_quadratic_without_local_state():
+    A = np.diag(np.arange(1.0, 7.0))
+    b = np.arange(6.0)
+
+    def f(x, iteration, step_size=0):
+        return 0.5 * x @ A @ x - b @ x, A @ x - b
+    x, flog, nev, status, _ = SCG_adapted(f, np.zeros(6), "unused", fixed_embeddings=True, maxiters=40, display=False,
+                                          xtol=1e-12, ftol=1e-14, gtol=1e-14)
+    assert np.allclose(x, np.linalg.solve(A, b), atol=1e-5)
+    assert flog[-1] <= flog[0]
+
+
+def test_scg_with_oracle_backend_decreases_bound_and_moves_embeddings():
+    p = make_problem(60, 4, 2, 3, seed=21)
+    shards = [dict(Y=p["Y"][lo:hi], X_mu=p["X_mu"][lo:hi], X_S=p["X_S"][lo:hi]) for lo, hi in split_rows(60, 2)]
+    be = OracleBackend(shards, 4, 2)
+    x0 = np.concatenate([p["Z"].ravel(), O.softplus_inv(np.array([1.0, 1.0, 1.0, 1.0]))])
+    x, flog, nev, status, _ = SCG_adapted(be.f_and_gradf, x0, "unused", fixed_embeddings=False, maxiters=6,
+                                          display=False, xtol=0, ftol=0, gtol=0, local_ops=be)
+    assert flog[-1] < flog[0]
+    assert not np.allclose(be.st[0]["X_mu"], shards[0]["X_mu"])
+    assert status == "maxiter exceeded" and len(flog) == 7
+
+
+def test_safe_wrapper_maps_failures_to_inf():
+    from gparml_b200.scg_adapted import safe_f_and_grad_f
+
+    def bad(x, it, st):
+        raise np.linalg.LinAlgError("not PD")
+    f, g = safe_f_and_grad_f(bad, np.zeros(3))
+    assert f == np.inf and np.array_equal(g, np.ones(3))
+
+
+GLOO_WORKER = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, %(root)r)
+    import numpy as np, torch
+    from gparml_b200 import distributed as gd
+    from gparml_b200.synthetic import make_problem
+    from oracle import gparml_oracle as O
+    rank, world, _ = gd.init_process_group("gloo")
+    p = make_problem(41, 5, 2, 3, seed=4, generic_hypers=True)
+    lo, hi = gd.shard_range(41, world, rank)
+    S = O.softplus(p["X_S"])
+    st = O.shard_statistics(p["Y"][lo:hi], p["X_mu"][lo:hi], S[lo:hi], p["Z"], p["sf2"], p["alpha"])
+    packed = torch.from_numpy(np.concatenate([np.ravel(np.asarray(st[k], dtype=float)) for k in O.STAT_NAMES]))
+    gd.allreduce_sum_(packed)
+    full = O.shard_statistics(p["Y"], p["X_mu"], S, p["Z"], p["sf2"], p["alpha"])
+    ref = np.concatenate([np.ravel(np.asarray(full[k], dtype=float)) for k in O.STAT_NAMES])
+    err = float(np.max(np.abs(packed.numpy() - ref)) / np.max(np.abs(ref)))
+    assert err < 1e-13, err
+
+    class FakeCtx(object):          # one shard's partial inner products
+        def scg_get_mu(self): return 1.5 + rank
+        def scg_get_max_d(self, a): return a * (2.0 + rank)
+    ops = gd.DistributedLocalOps(FakeCtx())
+    assert ops.embeddings_get_grads_mu("x") == sum(1.5 + r for r in range(world))
+    assert ops.embeddings_get_grads_max_d("x", 0.5) == 0.5 * (2.0 + world - 1)
+    import torch.distributed as dist
+    dist.barrier(); dist.destroy_process_group()
+    print("rank %%d ok" %% rank)
+""")
+
+
+def test_world_size_2_gloo_reduce(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER % {"root": ROOT})
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.path.join(ROOT, "tests"))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
