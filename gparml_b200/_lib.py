@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgparml_b200.so")
+LIB_PATH = os.environ.get("GPARML_B200_LIB") or os.path.join(HERE, "libgparml_b200.so")   # env override: kernel-variant tuning only
 
 # return codes (include/gparml_b200.h)
 OK, ERR_CUDA, ERR_ARG, ERR_NOT_PD, ERR_STATE, ERR_NO_DEVICE, ERR_RANGE = 0, -1, -2, -3, -4, -5, -6

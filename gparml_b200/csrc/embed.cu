@@ -16,15 +16,25 @@
 // Mapping: the reduction runs over pairs for each point (the opposite direction to psi2_stats),
 // so one thread owns one point and keeps w (Q), mu - z_m/2 (Q), wd (Q) and the 2Q accumulators
 // in registers; Z/2 sits in shared memory and is read as broadcasts; (lk, Gs) per pair is a
-// warp-uniform 16-byte global load.  The grid is (point tiles) x (splits of the m range,
-// balanced by pair count); split partials are combined by embed_finish in a fixed order.
+// warp-uniform 16-byte global load issued one pair ahead.  The grid is (point tiles) x (splits
+// of the m range, balanced by pair count); split partials are combined by embed_finish in a
+// fixed order.
 //
-// Bound: FP64 pipe, 6Q + 21 FP64 instructions per (point, pair).
+// Bound: FP64 pipe, 6Q + 21 FP64 instructions per (point, pair) at exp = 18.
 #include <math.h>
 
 #include "common.cuh"
+#include "gp_exp.cuh"
 
+#ifndef EMB_THREADS
 #define EMB_THREADS 128
+#endif
+#ifndef EMB_MINB_LOWQ
+#define EMB_MINB_LOWQ 4        // resident CTAs per SM targeted for Q <= 10 (B200, Q=10: 3 -> 7.88 ms, 4 -> 7.51 ms at N=250k)
+#endif
+#ifndef EMB_UNROLL
+#define EMB_UNROLL 2           // pairs in flight per thread (7.51 -> 7.38 ms)
+#endif
 #define EMB_MAX_SPLITS 32
 
 struct EmbedParams {
@@ -36,15 +46,24 @@ struct EmbedParams {
     double *partial;     // [splits][n][2Q + 2]
 };
 
+#ifdef GP_USE_LIBM_EXP
+#define EMB_EXP(x) exp(x)
+#else
+#define EMB_EXP(x) gp_exp((x), exp_tab)
+#endif
+
 template <int Q>
-__global__ void __launch_bounds__(EMB_THREADS, (Q <= 10) ? 3 : ((Q <= 13) ? 2 : 1))
+__global__ void __launch_bounds__(EMB_THREADS, (Q <= 10) ? EMB_MINB_LOWQ : ((Q <= 13) ? 2 : 1))
 embed_grads_kernel(EmbedParams p)
 {
     constexpr int R = (3 * Q + 2) & ~1;
+    constexpr int EUNR = EMB_UNROLL;
     extern __shared__ __align__(16) double hz[];        // [M][Q] = Z / 2
+    __shared__ double exp_tab[GP_EXP_TAB];
     const int tid = threadIdx.x;
     const int M = p.M;
     for (int idx = tid; idx < M * Q; idx += EMB_THREADS) hz[idx] = 0.5 * p.Z[idx];
+    gp_exp_load_table(exp_tab);
     __syncthreads();
 
     int64_t i = (int64_t)blockIdx.x * EMB_THREADS + tid;
@@ -65,6 +84,8 @@ embed_grads_kernel(EmbedParams p)
 
     for (int m = m_lo; m < m_hi; ++m) {
         const double *hm = hz + m * Q;
+        const double2 *pg = p.pair_g + gp_pair_index(M, m, m);
+        double2 g = __ldg(pg);                           // first pair of the row, in flight during the Psi1 part
         // ---- Psi1 side (partial_terms.py:388-390, 421-423) -----------------------------
         {
             double e = lc1;
@@ -79,7 +100,7 @@ embed_grads_kernel(EmbedParams p)
             double b = 0.0;
             const double *g1 = p.G1 + (size_t)m * p.D;
             for (int d = 0; d < p.D; ++d) b = fma(y[d], g1[d], b);
-            const double h1 = 0.5 * b * exp(e);          // accumulators are scaled by 2 at the end
+            const double h1 = 0.5 * b * EMB_EXP(e);      // accumulators are scaled by 2 at the end
             acc_b += h1;
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
@@ -89,9 +110,9 @@ embed_grads_kernel(EmbedParams p)
             }
         }
         // ---- Psi2 side (partial_terms.py:393, 425-426), pairs (m, m' >= m) -------------
-        const double2 *pg = p.pair_g + gp_pair_index(M, m, m);
+#pragma unroll EUNR
         for (int b = m; b < M; ++b) {
-            const double2 g = __ldg(pg + (b - m));      // (lk, Gs), warp-uniform
+            const double2 gn = __ldg(pg + ((b + 1 < M) ? (b + 1 - m) : (b - m)));   // next pair, warp-uniform
             const double *hb = hz + b * Q;
             double e0 = g.x + lc2, e1 = 0.0;
 #pragma unroll
@@ -101,7 +122,7 @@ embed_grads_kernel(EmbedParams p)
                 if (q & 1) e1 = fma(-wd[q], d, e1);
                 else e0 = fma(-wd[q], d, e0);
             }
-            const double h = g.y * exp(e0 + e1);
+            const double h = g.y * EMB_EXP(e0 + e1);
             acc_h += h;
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
@@ -109,6 +130,7 @@ embed_grads_kernel(EmbedParams p)
                 acc_mu[q] += t;
                 acc_s[q] = fma(t, wd[q], acc_s[q]);
             }
+            g = gn;
         }
     }
     if (valid) {

@@ -7,107 +7,156 @@
 //
 // With a_nq = alpha_q / (alpha_q S_nq + 1), ad_q = a_nq (mu_nq - z_mq):
 //   Psi1[n,m]   = exp( lc1_n - 1/2 sum_q ad_q (mu_nq - z_mq) )
-//   row (m, 0)      : Psi1                       -> Psi1^T Y
-//   row (m, 1+q)    : Psi1 ad_q                  -> dPsi1Y/dZ[m,q,:]
-//   row (m, 1+Q+q)  : Psi1 (ad_q^2 + v1_nq)      -> -2 alpha_q^2 dPsi1Y/dalpha[q,m,:]
-// and every row is contracted with Y over the points: C[(m,j), d] = sum_n A[n,(m,j)] Y[n,d].
+//   row (0,   m) : Psi1                       -> Psi1^T Y
+//   row (1+q, m) : Psi1 ad_q                  -> dPsi1Y/dZ[m,q,:]
+//   row (1+Q+q,m): Psi1 (ad_q^2 + v1_nq)      -> -2 alpha_q^2 dPsi1Y/dalpha[q,m,:]
+// and every row is contracted with Y over the points: C[row, d] = sum_n A[n, row] Y[n, d].
 //
-// Two stages per point tile inside one CTA: (1) one thread per (point, inducing point)
-// evaluates Psi1 and its 1+2Q row entries into shared memory; (2) one thread per row keeps
-// DC output columns in registers and runs the small GEMM over the tile.  Q is a run-time
-// value here (row entries live in shared memory); DC (columns per thread) is the template.
-// <4 % of the evaluation's work; FP64-pipe bound in stage 2.
+// One CTA owns MB <= 32 inducing points and walks its slice of the points in tiles of 8
+// (one warp per point).  Stage 1: lane = inducing point, the warp's point record is read from
+// shared memory as broadcasts, Psi1 and the 1+2Q row entries go to shared memory laid out
+// [point][row] with row = j * MB + m (lane-consecutive, conflict free).  Stage 2: a small
+// register-blocked GEMM over the tile, each thread owning RB = 4 rows x DC columns, so that one
+// 8-byte A read and one broadcast Y read feed DC resp. RB FMAs (0.45 shared-memory wavefronts
+// per FP64 instruction; the first version with one row per thread was LSU-bound at 1.2).
+// Q is a run-time value (row entries live in shared memory); DC is the template parameter.
+// ~4 % of the evaluation's work; FP64-pipe bound.
 #include <math.h>
 
 #include "common.cuh"
+#include "gp_exp.cuh"
 
-#define PSI1_THREADS 256
+#define PSI1_THREADS 128
+#define PSI1_TN 8        // points per tile
+#define PSI1_RB 4        // rows per thread in the contraction: MB * (1 + 2Q) <= THREADS * RB
 
 struct Psi1Params {
     const double *rec1, *Y, *Z;
     int64_t n, n_per_split;
     int M, Q, D, R;
-    int MB, TN;          // inducing points / points per tile: TN * MB <= 256, MB * (1+2Q) <= 256
+    int MB;              // inducing points per CTA
     double *partial;     // [splits][M * (1+2Q)][D]
 };
 
+__device__ __forceinline__ void psi1_cp_async8(double *dst_smem, const double *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(gp_smem_u32(dst_smem)), "l"(src) : "memory");
+}
+
 template <int DC>
-__global__ void __launch_bounds__(PSI1_THREADS)
+__global__ void __launch_bounds__(PSI1_THREADS, (DC <= 10) ? 4 : 2)
 psi1_stats_kernel(Psi1Params p)
 {
     extern __shared__ __align__(16) double sm[];
-    const int Q = p.Q, J = 1 + 2 * Q, MB = p.MB, TN = p.TN, rows = MB * J;
-    double *A = sm;                          // [TN][rows]
-    double *Ys = A + (size_t)TN * rows;      // [TN][DC]
-    double *zs = Ys + (size_t)TN * DC;       // [MB][Q]
+    __shared__ double exp_tab[GP_EXP_TAB];
+    constexpr int DCP = (DC + 1) & ~1;                    // padded row of the Y tile (16-byte rows)
+    const int Q = p.Q, J = 1 + 2 * Q, MB = p.MB, R = p.R;
+    const int rows = MB * J;
+    const int rows_pad = (rows + 1) & ~1;
+    double *A = sm;                                      // [TN][rows_pad]
+    double *Ys = A + (size_t)PSI1_TN * rows_pad;         // [2][TN][DCP]   (double buffered)
+    double *recs = Ys + 2 * PSI1_TN * DCP;               // [2][TN][R]
+    double *zs = recs + 2 * PSI1_TN * R;                 // [Q][MB]
     const int tid = threadIdx.x;
     const int m0 = blockIdx.x * MB;
     const int d0 = blockIdx.z * DC;
     for (int idx = tid; idx < MB * Q; idx += PSI1_THREADS) {
-        const int m = m0 + idx / Q;
-        zs[idx] = (m < p.M) ? p.Z[(size_t)m * Q + idx % Q] : 0.0;
+        const int q = idx / MB, ml = idx % MB;
+        zs[idx] = (m0 + ml < p.M) ? p.Z[(size_t)(m0 + ml) * Q + q] : 0.0;
     }
-    const int n_l = tid / MB, m_l = tid % MB;
-    const bool s1 = tid < TN * MB;
-    const bool s2 = tid < rows;
+    for (int idx = tid; idx < 2 * PSI1_TN * DCP; idx += PSI1_THREADS) Ys[idx] = 0.0;   // columns >= D stay zero
+    gp_exp_load_table(exp_tab);
+    const int T2 = (rows + PSI1_RB - 1) / PSI1_RB;       // threads active in the contraction (<= THREADS)
+    const bool s2 = tid < T2;
     const int64_t n_lo = (int64_t)blockIdx.y * p.n_per_split;
     const int64_t n_hi = (n_lo + p.n_per_split < p.n) ? (n_lo + p.n_per_split) : p.n;
-    double acc[DC];
+    const int dcols = (p.D - d0 < DC) ? (p.D - d0) : DC; // valid output columns of this chunk
+    double acc[PSI1_RB][DC];
 #pragma unroll
-    for (int d = 0; d < DC; ++d) acc[d] = 0.0;
+    for (int k = 0; k < PSI1_RB; ++k)
+#pragma unroll
+        for (int d = 0; d < DC; ++d) acc[k][d] = 0.0;
     __syncthreads();
 
-    for (int64_t base = n_lo; base < n_hi; base += TN) {
-        for (int idx = tid; idx < TN * DC; idx += PSI1_THREADS) {
-            const int nn = idx / DC, dd = idx % DC;
-            const int64_t i = base + nn;
-            Ys[idx] = (i < n_hi && d0 + dd < p.D) ? p.Y[i * p.D + d0 + dd] : 0.0;
+    // asynchronous tile loader: records are contiguous, Y rows are strided by D
+    auto issue = [&](int64_t base, int buf) {
+        const int cnt = (int)((n_hi - base < PSI1_TN) ? (n_hi - base) : PSI1_TN);
+        double *rb = recs + buf * PSI1_TN * R, *yb = Ys + buf * PSI1_TN * DCP;
+        for (int idx = tid; idx < cnt * R; idx += PSI1_THREADS) psi1_cp_async8(rb + idx, p.rec1 + base * R + idx);
+        for (int idx = tid; idx < cnt * dcols; idx += PSI1_THREADS) {
+            const int nn = idx / dcols, dd = idx % dcols;
+            psi1_cp_async8(yb + nn * DCP + dd, p.Y + (base + nn) * p.D + d0 + dd);
         }
-        if (s1) {
-            const int64_t i = base + n_l;
-            double *ar = A + (size_t)n_l * rows + m_l * J;
-            if (i < n_hi && m0 + m_l < p.M) {
-                const double *rec = p.rec1 + i * p.R;
-                const double *z = zs + m_l * Q;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (n_lo < n_hi) issue(n_lo, 0);
+
+    int buf = 0;
+    for (int64_t base = n_lo; base < n_hi; base += PSI1_TN, buf ^= 1) {
+        const int cnt = (int)((n_hi - base < PSI1_TN) ? (n_hi - base) : PSI1_TN);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                  // tile data visible; previous contraction finished
+        const double *rb = recs + buf * PSI1_TN * R, *yb = Ys + buf * PSI1_TN * DCP;
+        // ---- stage 1: one (point, inducing point) item per thread and round ------------------
+        for (int item = tid; item < cnt * MB; item += PSI1_THREADS) {
+            const int nn = item / MB, ml = item % MB;
+            if (m0 + ml < p.M) {
+                const double *rec = rb + nn * R;
+                double *ar = A + (size_t)nn * rows_pad + ml;                    // row (j, ml) at ar[j * MB]
                 double e = rec[3 * Q];
                 for (int q = 0; q < Q; ++q) {
                     const double2 ma = *reinterpret_cast<const double2 *>(rec + 2 * q);   // (mu_q, a_q)
-                    const double d = ma.x - z[q];
+                    const double d = ma.x - zs[q * MB + ml];
                     const double ad = ma.y * d;
                     e = fma(-0.5 * ad, d, e);
-                    ar[1 + q] = ad;
+                    ar[(1 + q) * MB] = ad;
                 }
-                const double psi = exp(e);
+                const double psi = gp_exp(e, exp_tab);
                 ar[0] = psi;
                 for (int q = 0; q < Q; ++q) {
-                    const double ad = ar[1 + q];
-                    ar[1 + q] = psi * ad;
-                    ar[1 + Q + q] = psi * fma(ad, ad, rec[2 * Q + q]);
+                    const double ad = ar[(1 + q) * MB];
+                    ar[(1 + q) * MB] = psi * ad;
+                    ar[(1 + Q + q) * MB] = psi * fma(ad, ad, rec[2 * Q + q]);
                 }
-            } else {
-                for (int j = 0; j < J; ++j) ar[j] = 0.0;
             }
         }
         __syncthreads();
+        if (base + PSI1_TN < n_hi) issue(base + PSI1_TN, buf ^ 1);   // overlaps the contraction
+        // ---- stage 2: RB x DC register tile per thread --------------------------------------
         if (s2) {
-            const int cnt = (int)((n_hi - base < TN) ? (n_hi - base) : TN);
+#pragma unroll 2
             for (int nn = 0; nn < cnt; ++nn) {
-                const double a = A[(size_t)nn * rows + tid];
-                const double *y = Ys + nn * DC;
+                const double *an = A + (size_t)nn * rows_pad + tid;
+                double a[PSI1_RB];
 #pragma unroll
-                for (int d = 0; d < DC; ++d) acc[d] = fma(a, y[d], acc[d]);
+                for (int k = 0; k < PSI1_RB; ++k) a[k] = (tid + k * T2 < rows) ? an[k * T2] : 0.0;
+                const double2 *y2 = reinterpret_cast<const double2 *>(yb + nn * DCP);
+#pragma unroll
+                for (int d2 = 0; d2 < DCP / 2; ++d2) {
+                    const double2 yy = y2[d2];                                   // broadcast
+#pragma unroll
+                    for (int k = 0; k < PSI1_RB; ++k) {
+                        acc[k][2 * d2] = fma(a[k], yy.x, acc[k][2 * d2]);
+                        if (2 * d2 + 1 < DC) acc[k][2 * d2 + 1] = fma(a[k], yy.y, acc[k][2 * d2 + 1]);
+                    }
+                }
             }
         }
-        __syncthreads();
     }
 
     if (s2) {
-        const int m = m0 + tid / J, j = tid % J;
-        if (m < p.M) {
-            double *out = p.partial + ((size_t)blockIdx.y * p.M * J + (size_t)m * J + j) * p.D;
 #pragma unroll
-            for (int d = 0; d < DC; ++d)
-                if (d0 + d < p.D) out[d0 + d] = acc[d];
+        for (int k = 0; k < PSI1_RB; ++k) {
+            const int r = tid + k * T2;
+            if (r < rows) {
+                const int j = r / MB, m = m0 + r % MB;
+                if (m < p.M) {
+                    double *out = p.partial + ((size_t)blockIdx.y * p.M * J + (size_t)m * J + j) * p.D;
+#pragma unroll
+                    for (int d = 0; d < DC; ++d)
+                        if (d0 + d < p.D) out[d0 + d] = acc[k][d];
+                }
+            }
         }
     }
 }
@@ -142,7 +191,9 @@ template <int DC>
 static int launch_dc(gparml_ctx *c, Psi1Params &p, int dchunks)
 {
     const int J = 1 + 2 * c->Q;
-    const size_t smem = ((size_t)p.TN * p.MB * J + (size_t)p.TN * DC + (size_t)p.MB * c->Q) * sizeof(double);
+    const int rows_pad = (p.MB * J + 1) & ~1;
+    constexpr int DCP = (DC + 1) & ~1;
+    const size_t smem = ((size_t)PSI1_TN * rows_pad + 2 * (size_t)PSI1_TN * DCP + 2 * (size_t)PSI1_TN * p.R + (size_t)p.MB * c->Q) * sizeof(double);
     GP_CUDA(cudaFuncSetAttribute(psi1_stats_kernel<DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
     GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, psi1_stats_kernel<DC>, PSI1_THREADS, smem));
@@ -150,7 +201,7 @@ static int launch_dc(gparml_ctx *c, Psi1Params &p, int dchunks)
     const int mblocks = (c->M + p.MB - 1) / p.MB;
     const int64_t per_split_rows = (int64_t)c->M * J * c->D;
     const int64_t slots = (int64_t)c->sm_count * occ;
-    int64_t max_splits = (c->n + 8 * p.TN - 1) / (8 * p.TN);
+    int64_t max_splits = (c->n + 32 * PSI1_TN - 1) / (32 * PSI1_TN);
     const int64_t ws_cap = ((int64_t)128 << 20) / (per_split_rows * (int64_t)sizeof(double));
     if (max_splits > ws_cap) max_splits = ws_cap;
     if (max_splits > 65535) max_splits = 65535;
@@ -182,13 +233,11 @@ int gp_launch_psi1_stats(gparml_ctx *c)
     Psi1Params p;
     p.rec1 = c->rec1; p.Y = c->Y; p.Z = c->Z;
     p.n = c->n; p.M = c->M; p.Q = c->Q; p.D = c->D; p.R = gp_rec_len(c->Q);
-    const int J = 1 + 2 * c->Q;
-    int MB = PSI1_THREADS / J;
-    if (MB > c->M) MB = c->M;
-    if (MB < 1) MB = 1;
-    int TN = PSI1_THREADS / MB;
-    if (TN > 64) TN = 64;
-    p.MB = MB; p.TN = TN;
+    // balanced blocks of inducing points with MB * (1 + 2Q) rows <= THREADS * RB
+    int mb_max = PSI1_THREADS * PSI1_RB / (1 + 2 * c->Q);
+    if (mb_max < 1) mb_max = 1;
+    const int nblk = (c->M + mb_max - 1) / mb_max;
+    p.MB = (c->M + nblk - 1) / nblk;
     const int dchunks = (c->D + 15) / 16;
     const int per = (c->D + dchunks - 1) / dchunks;     // columns per chunk
     if (per <= 1) return launch_dc<1>(c, p, dchunks);

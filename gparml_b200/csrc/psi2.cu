@@ -28,37 +28,75 @@
 
 #include "common.cuh"
 
+#include "gp_exp.cuh"
+
+#ifndef PSI2_THREADS
 #define PSI2_THREADS 256
+#endif
+#ifndef PSI2_MINB
+#define PSI2_MINB 2      // resident CTAs per SM the register budget is tuned for
+#endif
+#ifndef PSI2_UNROLL
+#define PSI2_UNROLL 2    // points in flight per thread
+#endif
+#ifndef PSI2_TN
 #define PSI2_TN 64       // points per stage
+#endif
+#ifndef PSI2_STAGES
 #define PSI2_STAGES 2
+#endif
+#define PSI2_STR2(x) #x
+#define PSI2_STR(x) PSI2_STR2(x)
+
+// Pairs per thread (register blocking: each shared-memory read feeds PP pairs) and the number
+// of resident CTAs the register budget is tuned for.  Measured on B200 at Q=10 (tools/tune.py,
+// N=250k): PP=1/2 CTAs 6.56 ms, PP=2/1 CTA 6.26 ms (LSU wavefronts 74 % -> 43 %, FP64 pipe
+// 76 % -> 80 %).  Above Q=10 two pairs no longer fit the 255-register budget.
+#ifdef PSI2_PAIRS
+template <int Q> struct Psi2Cfg { static constexpr int PP = PSI2_PAIRS; static constexpr int MINB = PSI2_MINB; };
+#else
+template <int Q> struct Psi2Cfg {
+    static constexpr int PP = (Q <= 10) ? 2 : 1;
+    static constexpr int MINB = (Q <= 10) ? ((Q <= 3) ? 3 : ((Q <= 6) ? 2 : 1)) : 2;
+};
+#endif
 
 template <int Q>
-__global__ void __launch_bounds__(PSI2_THREADS, 2)
+__global__ void __launch_bounds__(PSI2_THREADS, Psi2Cfg<Q>::MINB)
 psi2_stats_kernel(const double *__restrict__ rec2, int64_t n, const double *__restrict__ Z, int64_t P,
                   const int2 *__restrict__ pair_idx, const double *__restrict__ pair_lk, int64_t n_per_split,
                   double *__restrict__ partial)
 {
     constexpr int R = (3 * Q + 2) & ~1;
     constexpr int NT2 = (Q + 2) / 2;          // double2 loads covering v_0..v_{Q-1} and lc2
+    constexpr int UNR = PSI2_UNROLL;
+    constexpr int PP = Psi2Cfg<Q>::PP;
     extern __shared__ __align__(16) double tile[];       // [STAGES][TN][R]
     __shared__ __align__(8) uint64_t bar[PSI2_STAGES];
+    __shared__ double exp_tab[GP_EXP_TAB];
 
     const int tid = threadIdx.x;
-    const int64_t p = (int64_t)blockIdx.x * PSI2_THREADS + tid;
-    const bool valid = p < P;
-    const int2 ab = valid ? pair_idx[p] : make_int2(0, 0);
-    const double lk = valid ? pair_lk[p] : 0.0;
-    double zb[Q], acc[1 + 2 * Q];
+    int64_t p[PP];
+    bool valid[PP];
+    double lk[PP], zb[PP][Q], acc[PP][1 + 2 * Q];
 #pragma unroll
-    for (int q = 0; q < Q; ++q) zb[q] = 0.5 * (Z[ab.x * Q + q] + Z[ab.y * Q + q]);
+    for (int u = 0; u < PP; ++u) {
+        p[u] = ((int64_t)blockIdx.x * PP + u) * PSI2_THREADS + tid;
+        valid[u] = p[u] < P;
+        const int2 ab = valid[u] ? pair_idx[p[u]] : make_int2(0, 0);
+        lk[u] = valid[u] ? pair_lk[p[u]] : 0.0;
 #pragma unroll
-    for (int j = 0; j < 1 + 2 * Q; ++j) acc[j] = 0.0;
+        for (int q = 0; q < Q; ++q) zb[u][q] = 0.5 * (Z[ab.x * Q + q] + Z[ab.y * Q + q]);
+#pragma unroll
+        for (int j = 0; j < 1 + 2 * Q; ++j) acc[u][j] = 0.0;
+    }
 
     const int64_t n_lo = (int64_t)blockIdx.y * n_per_split;
     const int64_t n_hi = (n_lo + n_per_split < n) ? (n_lo + n_per_split) : n;
     const int64_t span = n_hi > n_lo ? n_hi - n_lo : 0;
     const int ntiles = (int)((span + PSI2_TN - 1) / PSI2_TN);
 
+    gp_exp_load_table(exp_tab);
     if (tid == 0) {
         for (int s = 0; s < PSI2_STAGES; ++s) gp_mbar_init(&bar[s], 1);
         gp_fence_mbar_init();
@@ -81,33 +119,49 @@ psi2_stats_kernel(const double *__restrict__ rec2, int64_t n, const double *__re
         const int cnt = (int)((n_hi - base < PSI2_TN) ? (n_hi - base) : PSI2_TN);
         gp_mbar_wait(&bar[s], parity);
         const double *tb = tile + (size_t)s * PSI2_TN * R;
-#pragma unroll 2
+#pragma unroll UNR
         for (int i = 0; i < cnt; ++i) {
             const double2 *r = reinterpret_cast<const double2 *>(tb + i * R);
-            double tv[2 * NT2];
+            double wd[PP][Q], e0[PP], e1[PP], psi[PP];
+            const double lc2 = tb[i * R + 3 * Q];
+#pragma unroll
+            for (int u = 0; u < PP; ++u) { e0[u] = lk[u] + lc2; e1[u] = 0.0; }
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const double2 mw = r[q];           // (mu_q, w_q), broadcast; feeds all PP pairs
+#pragma unroll
+                for (int u = 0; u < PP; ++u) {
+                    const double d = mw.x - zb[u][q];
+                    wd[u][q] = mw.y * d;
+                    if (q & 1) e1[u] = fma(-wd[u][q], d, e1[u]);
+                    else e0[u] = fma(-wd[u][q], d, e0[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < PP; ++u) {
+#ifdef GP_USE_LIBM_EXP
+                psi[u] = exp(e0[u] + e1[u]);
+#else
+                psi[u] = gp_exp(e0[u] + e1[u], exp_tab);
+#endif
+                acc[u][0] += psi[u];
+            }
 #pragma unroll
             for (int k = 0; k < NT2; ++k) {
-                const double2 t2 = r[Q + k];
-                tv[2 * k] = t2.x;
-                tv[2 * k + 1] = t2.y;
-            }
-            double wd[Q];
-            double e0 = lk + tv[Q], e1 = 0.0;      // tv[Q] = lc2
+                const double2 v2 = r[Q + k];       // (v_2k, v_2k+1); the last slot holds lc2 / padding
 #pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                const double2 mw = r[q];           // (mu_q, w_q), broadcast
-                const double d = mw.x - zb[q];
-                wd[q] = mw.y * d;
-                if (q & 1) e1 = fma(-wd[q], d, e1);
-                else e0 = fma(-wd[q], d, e0);
-            }
-            const double psi = exp(e0 + e1);
-            acc[0] += psi;
+                for (int h = 0; h < 2; ++h) {
+                    const int q = 2 * k + h;
+                    if (q < Q) {
+                        const double v = h ? v2.y : v2.x;
 #pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                acc[1 + q] = fma(psi, wd[q], acc[1 + q]);
-                const double g = fma(wd[q], wd[q], tv[q]);
-                acc[1 + Q + q] = fma(psi, g, acc[1 + Q + q]);
+                        for (int u = 0; u < PP; ++u) {
+                            acc[u][1 + q] = fma(psi[u], wd[u][q], acc[u][1 + q]);
+                            const double g = fma(wd[u][q], wd[u][q], v);
+                            acc[u][1 + Q + q] = fma(psi[u], g, acc[u][1 + Q + q]);
+                        }
+                    }
+                }
             }
         }
         __syncthreads();      // every thread is done reading stage s
@@ -120,10 +174,13 @@ psi2_stats_kernel(const double *__restrict__ rec2, int64_t n, const double *__re
         }
     }
 
-    if (valid) {
-        double *out = partial + (size_t)blockIdx.y * (1 + 2 * Q) * P + p;
 #pragma unroll
-        for (int j = 0; j < 1 + 2 * Q; ++j) out[(size_t)j * P] = acc[j];
+    for (int u = 0; u < PP; ++u) {
+        if (valid[u]) {
+            double *out = partial + (size_t)blockIdx.y * (1 + 2 * Q) * P + p[u];
+#pragma unroll
+            for (int j = 0; j < 1 + 2 * Q; ++j) out[(size_t)j * P] = acc[u][j];
+        }
     }
 }
 
@@ -143,16 +200,12 @@ static int launch_q(gparml_ctx *c)
 {
     constexpr int R = (3 * Q + 2) & ~1;
     const size_t smem = (size_t)PSI2_STAGES * PSI2_TN * R * sizeof(double);
-    static bool configured = false;
-    static int occ = 2;
-    if (!configured) {
-        GP_CUDA(cudaFuncSetAttribute(psi2_stats_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, psi2_stats_kernel<Q>, PSI2_THREADS, smem));
-        if (occ < 1) occ = 1;
-        configured = true;
-    }
+    int occ = 2;
+    GP_CUDA(cudaFuncSetAttribute(psi2_stats_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, psi2_stats_kernel<Q>, PSI2_THREADS, smem));
+    if (occ < 1) occ = 1;
     const int64_t P = c->L.P;
-    const int tiles = (int)((P + PSI2_THREADS - 1) / PSI2_THREADS);
+    const int tiles = (int)((P + PSI2_THREADS * Psi2Cfg<Q>::PP - 1) / (PSI2_THREADS * Psi2Cfg<Q>::PP));
     const int64_t slots = (int64_t)c->sm_count * occ;
     // number of n-splits: whole waves of resident CTAs, >= 4 point tiles per split, bounded workspace
     const int64_t rows_x_P = (int64_t)(1 + 2 * Q) * P;
