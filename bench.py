@@ -182,12 +182,12 @@ class ClockSampler(object):
 
     def __init__(self, uuid):
         self.uuid = uuid
-        self.lines = []
+        self.lines = []          # (host receive time, csv line)
         self.proc = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -197,9 +197,10 @@ class ClockSampler(object):
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples received in the wall-clock window [t0, t1] (the timed regions)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -209,7 +210,10 @@ class ClockSampler(object):
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for ln in self.lines:
+        rows = [(t, ln) for t, ln in self.lines if (t0 is None or t >= t0) and (t1 is None or t <= t1 + 0.15)]
+        if not rows:
+            rows = self.lines[-2:]
+        for _, ln in rows:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8 or (self.uuid and self.uuid not in f[0]):
                 continue
@@ -322,20 +326,20 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), out, phases
 
-    for _ in range(args.warmup):
-        evaluation()
-    ctx.enable_timing(True)
     uuid = ""
     try:
         uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
     except Exception:
         pass
     sampler = ClockSampler(uuid) if rank == 0 else None
-    launches0 = ctx.launch_count
     if sampler:
-        sampler.start()
+        sampler.start()          # started before the warm-up so that it is sampling when the timed region begins
+    for _ in range(args.warmup):
+        evaluation()
+    ctx.enable_timing(True)
+    launches0 = ctx.launch_count
+    t_load0 = time.time()
     ms_total, (F, g), phases = timed(evaluation, args.steps, collect_phases=True)
-    clocks = sampler.stop() if sampler else None
     launches = ctx.launch_count - launches0
     ctx.enable_timing(False)
     ms_per_step = ms_total / args.steps
@@ -353,6 +357,8 @@ def main():
         e2e = {"value": 1e3 / (ms_e2e / args.steps), "unit": UNIT, "h2d_bytes_per_step": int(tot[0].item()),
                "d2h_bytes_per_step": int(tot[1].item()),
                "api": "upload_shard(Y, X_mu, X_S) from pinned host memory + evaluation + grad_latest back to pinned host, every step"}
+
+    clocks = sampler.stop(t_load0, time.time()) if sampler else None   # samples during the two timed loops
 
     # roofline of the dominant kernel (psi2_stats) on this rank, live CUDA-event durations
     P = M * (M + 1) // 2

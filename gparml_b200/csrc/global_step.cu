@@ -11,20 +11,26 @@
 //   partial_terms.py:340-360              grad_beta
 //   parallel_GPLVM.py:302-369             the glue that sequences them
 //
-// The reference uses explicit LU inverses and slogdet; here both symmetric positive definite
-// matrices are Cholesky-factorised in place, the triangular factor is inverted in place and
-// the inverse is formed as L^-T L^-1 (differences are O(cond * eps)).  A failed
-// pivot reports GPARML_ERR_NOT_PD (the caller raises LinAlgError, which the reference's
+// The reference uses explicit LU inverses and slogdet.  Here both symmetric positive definite
+// matrices are inverted in place with the symmetric sweep operator (M rank-1 steps; after
+// sweeping every pivot the matrix holds -A^-1 and the pivots are the Schur-complement
+// diagonals, so log det = sum log d_k and a non-positive pivot means "not positive definite").
+// One barrier pair per pivot and M^2 / 1024 updates per thread: the kernel is latency-bound by
+// design and was 10x slower with Cholesky + triangular inverse + L^T L (3-5 barriers per
+// column, warp-serial inner products).  Differences to LU are O(cond * eps).  A
+// failed pivot reports GPARML_ERR_NOT_PD (the caller raises LinAlgError, which the reference's
 // optimiser wrapper turns into f = inf, scg_adapted.py:55).
 //
 // Two M x M work matrices (X, W) live in shared memory when 2 M^2 doubles fit (M <= 118);
-// larger M runs the same code on L2-resident global scratch.  Latency-bound by design: it is
-// replicated on every GPU after the all-reduce, so no second broadcast is needed.
+// larger M runs the same code on L2-resident global scratch.  The kernel is replicated on
+// every GPU after the all-reduce, so no second broadcast is needed.
 #include <math.h>
 
 #include "common.cuh"
 
 #define GS_THREADS 1024
+#define GS_TI 2          // register tile of the two M x M x M products: 2 x 5 outputs per thread
+#define GS_TJ 5
 
 struct GsParams {
     int M, Q, D;
@@ -36,7 +42,7 @@ struct GsParams {
     const double *Z;
     const GlobalsDev *glob;
     const double *pair_lk;
-    double *kmm, *kmm_inv, *a_inv, *g_k, *g_1, *g_2, *c_mat;
+    double *kmm, *kmm_inv, *a_inv, *g_k, *g_1, *g_2, *c_mat, *psi2_full;
     double *X, *W;            // global scratch (used when !use_smem)
     double2 *pair_g;
     double *out;              // [0] F, [1 .. 1+MQ+Q+2) grad (Z, sf2, alpha, beta), then [logdetK, logdetA, trKP, tr1]
@@ -48,59 +54,134 @@ __device__ __forceinline__ int64_t pidx(int M, int i, int j)
     return (i <= j) ? gp_pair_index(M, i, j) : gp_pair_index(M, j, i);
 }
 
-// In-place lower Cholesky of the lower triangle of A (ld = M).  *fail set on a bad pivot.
-__device__ void gs_chol(double *A, int M, int *fail)
+// In-place symmetric sweep of every pivot: A <- -A^-1, returns sum log(pivot) (valid in every
+// thread).  Memory-resident version for M > 128: every step streams the whole matrix through
+// the CTA (shared-memory / L2 bandwidth bound).  tmp >= M doubles, piv >= M doubles.
+__device__ bool gs_sweep_invert_mem(double *A, int M, double *tmp, double *piv, double *red, double *logdet)
 {
     const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
     for (int k = 0; k < M; ++k) {
-        if (tid == 0) {
-            double d = A[(size_t)k * M + k];
-            if (!(d > 0.0) || !isfinite(d)) { *fail = 1; d = 1.0; }
-            A[(size_t)k * M + k] = sqrt(d);
-        }
+        for (int i = tid; i < M; i += GS_THREADS) tmp[i] = A[(size_t)i * M + k];
         __syncthreads();
-        const double dk = A[(size_t)k * M + k];
-        for (int i = k + 1 + tid; i < M; i += GS_THREADS) A[(size_t)i * M + k] /= dk;
-        __syncthreads();
-        for (int i = k + 1 + ty; i < M; i += GS_THREADS / 32) {
-            const double aik = A[(size_t)i * M + k];
-            for (int j = k + 1 + tx; j <= i; j += 32) A[(size_t)i * M + j] -= aik * A[(size_t)j * M + k];
-        }
-        __syncthreads();
-    }
-}
-
-// In-place inverse of a lower-triangular matrix (column sweep from the last column; the
-// original sub-diagonal column is staged in tmp).  tmp holds >= M doubles.
-__device__ void gs_trtri(double *A, int M, double *tmp)
-{
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int j = M - 1; j >= 0; --j) {
-        for (int k = j + 1 + tid; k < M; k += GS_THREADS) tmp[k] = A[(size_t)k * M + j];
-        if (tid == 0) A[(size_t)j * M + j] = 1.0 / A[(size_t)j * M + j];
-        __syncthreads();
-        const double ajj = A[(size_t)j * M + j];
-        for (int i = j + 1 + wid; i < M; i += GS_THREADS / 32) {
-            double s = 0.0;
-            for (int k = j + 1 + lane; k <= i; k += 32) s = fma(A[(size_t)i * M + k], tmp[k], s);
-            s = gp_warp_sum(s);
-            if (lane == 0) A[(size_t)i * M + j] = -ajj * s;
+        const double d = tmp[k];
+        if (!(d > 0.0) || !isfinite(d)) return false;          // uniform: every thread reads the same pivot
+        const double pinv = 1.0 / d;
+        if (tid == 0) piv[k] = d;
+        for (int i = ty; i < M; i += GS_THREADS / 32) {
+            const double ti = tmp[i] * pinv;
+            double *row = A + (size_t)i * M;
+            if (i == k) {
+                for (int j = tx; j < M; j += 32) row[j] = (j == k) ? -pinv : tmp[j] * pinv;
+            } else {
+                for (int j = tx; j < M; j += 32) row[j] = (j == k) ? ti : fma(-ti, tmp[j], row[j]);
+            }
         }
         __syncthreads();
     }
+    double v = 0.0;
+    for (int i = tid; i < M; i += GS_THREADS) v += log(piv[i]);
+    *logdet = gp_block_sum(v, red);
+    return true;
 }
 
-// out = Linv^T Linv (full symmetric), Linv lower-triangular
-__device__ void gs_ltl(const double *Li, int M, double *out)
+// Register-resident version for M <= 128: thread (ty, tx) owns the elements (ty + 32 a, tx + 32 b),
+// a, b < 4, for the whole sweep; only the pivot column travels through shared memory (double
+// buffered, one barrier per pivot).  Per pivot: 8 shared-memory reads and 16 FMAs per thread
+// instead of 3 shared-memory accesses per element.
+__device__ bool gs_sweep_invert_reg(double *A, int M, double *tmp2 /* 2 x 128 */, double *piv, double *red, double *logdet)
 {
     const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-    for (int i = ty; i < M; i += GS_THREADS / 32) {
-        for (int j = tx; j <= i; j += 32) {
-            double s = 0.0;
-            for (int k = i; k < M; ++k) s = fma(Li[(size_t)k * M + i], Li[(size_t)k * M + j], s);
-            out[(size_t)i * M + j] = s;
-            out[(size_t)j * M + i] = s;
+    double e[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int i = ty + 32 * a, j = tx + 32 * b;
+            e[a][b] = (i < M && j < M) ? A[(size_t)i * M + j] : 0.0;
         }
+    for (int k = 0; k < M; ++k) {
+        double *tmp = tmp2 + (k & 1) * 128;
+        // owners of column k publish it: elements (i, k) live in threads with tx == k % 32, slot b == k / 32
+        if (tx == (k & 31)) {
+            const int kb = k >> 5;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const double v = (kb == 0) ? e[a][0] : ((kb == 1) ? e[a][1] : ((kb == 2) ? e[a][2] : e[a][3]));
+                tmp[ty + 32 * a] = v;
+            }
+        }
+        __syncthreads();
+        const double d = tmp[k];
+        if (!(d > 0.0) || !isfinite(d)) return false;          // uniform
+        // one division per warp instead of one per thread: the single SM's FP64 pipe is the limit here
+        double pinv = 0.0;
+        if (tx == 0) pinv = 1.0 / d;
+        pinv = __shfl_sync(0xffffffffu, pinv, 0);
+        if (tid == 0) piv[k] = d;
+        double tj[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) tj[b] = tmp[tx + 32 * b];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int i = ty + 32 * a;                          // warp-uniform
+            if (i == k) {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) e[a][b] = (tx + 32 * b == k) ? -pinv : tj[b] * pinv;
+            } else {
+                const double ti = tmp[i] * pinv;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) e[a][b] = (tx + 32 * b == k) ? ti : fma(-ti, tj[b], e[a][b]);
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int i = ty + 32 * a, j = tx + 32 * b;
+            if (i < M && j < M) A[(size_t)i * M + j] = e[a][b];
+        }
+    double v = 0.0;
+    for (int i = tid; i < M; i += GS_THREADS) v += log(piv[i]);
+    *logdet = gp_block_sum(v, red);      // includes the barriers that publish A
+    return true;
+}
+
+__device__ __forceinline__ bool gs_sweep_invert(double *A, int M, double *tmp, double *piv, double *red, double *logdet)
+{
+    return (M <= 128) ? gs_sweep_invert_reg(A, M, tmp, piv, red, logdet) : gs_sweep_invert_mem(A, M, tmp, piv, red, logdet);
+}
+
+// C[i][j] = sum_k A[i][k] B[k][j] for a GS_TI x GS_TJ register tile per thread; `emit` consumes
+// each finished element.  A and B are M x M, row-major.
+template <typename Emit>
+__device__ __forceinline__ void gs_matmul(const double *__restrict__ A, const double *__restrict__ B, int M, Emit emit)
+{
+    const int tiles_j = (M + GS_TJ - 1) / GS_TJ, tiles_i = (M + GS_TI - 1) / GS_TI;
+    for (int t = threadIdx.x; t < tiles_i * tiles_j; t += GS_THREADS) {
+        const int i0 = (t / tiles_j) * GS_TI, j0 = (t % tiles_j) * GS_TJ;
+        double acc[GS_TI][GS_TJ];
+#pragma unroll
+        for (int a = 0; a < GS_TI; ++a)
+#pragma unroll
+            for (int b = 0; b < GS_TJ; ++b) acc[a][b] = 0.0;
+        for (int k = 0; k < M; ++k) {
+            double av[GS_TI], bv[GS_TJ];
+#pragma unroll
+            for (int a = 0; a < GS_TI; ++a) av[a] = (i0 + a < M) ? A[(size_t)(i0 + a) * M + k] : 0.0;
+#pragma unroll
+            for (int b = 0; b < GS_TJ; ++b) bv[b] = (j0 + b < M) ? B[(size_t)k * M + j0 + b] : 0.0;
+#pragma unroll
+            for (int a = 0; a < GS_TI; ++a)
+#pragma unroll
+                for (int b = 0; b < GS_TJ; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+        }
+#pragma unroll
+        for (int a = 0; a < GS_TI; ++a)
+#pragma unroll
+            for (int b = 0; b < GS_TJ; ++b)
+                if (i0 + a < M && j0 + b < M) emit(i0 + a, j0 + b, acc[a][b]);
     }
 }
 
@@ -108,20 +189,22 @@ __global__ void __launch_bounds__(GS_THREADS, 1) global_step_kernel(GsParams p)
 {
     extern __shared__ __align__(16) double sm[];
     __shared__ double red[33];
-    __shared__ int fail;
+    __shared__ double qred[32 * GP_MAX_Q];
+    __shared__ double ia2[GP_MAX_Q];
     const int M = p.M, Q = p.Q, D = p.D;
-    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const size_t MM = (size_t)M * M;
     double *X = p.use_smem ? sm : p.X;
     double *W = p.use_smem ? sm + MM : p.W;
-    double *tmp = p.use_smem ? sm + 2 * MM : sm;          // M doubles
+    double *tmp = p.use_smem ? sm + 2 * MM : sm;          // max(M, 256) doubles: pivot column (double buffered when M <= 128)
+    double *piv = tmp + (M > 256 ? M : 256);              // M doubles: the pivots
     const GlobalsDev g = *p.glob;
     const double sf2 = g.sf2, beta = g.beta;
     const double *S0 = p.stats + p.off_s0;
     const double *P1Y = p.stats + p.off_p1y;
-    if (tid == 0) fail = 0;
+    double *P2 = p.psi2_full;
 
-    // ---- Kmm (kernels.py:108-111 with V = 2 ard^2 = 2 / alpha) -------------------------------
+    // ---- Kmm (kernels.py:108-111 with V = 2 ard^2 = 2 / alpha) and the full Psi2 -------------
     for (size_t idx = tid; idx < MM; idx += GS_THREADS) {
         const int i = (int)(idx / M), j = (int)(idx % M);
         double s = 0.0;
@@ -132,61 +215,47 @@ __global__ void __launch_bounds__(GS_THREADS, 1) global_step_kernel(GsParams p)
         const double k = sf2 * exp(-0.5 * s);
         X[idx] = k;
         p.kmm[idx] = k;
+        if (!p.kmm_only) P2[idx] = S0[pidx(M, i, j)];
     }
     __syncthreads();
-    gs_chol(X, M, &fail);
-    if (fail) {
+    double ldK = 0.0, ldA = 0.0;
+    if (!gs_sweep_invert(X, M, tmp, piv, red, &ldK)) {
         if (tid == 0) atomicOr(p.status, 1);
         return;
     }
-    double v = 0.0;
-    for (int i = tid; i < M; i += GS_THREADS) v += log(X[(size_t)i * M + i]);
-    const double ldK = 2.0 * gp_block_sum(v, red);
-    gs_trtri(X, M, tmp);
-    gs_ltl(X, M, W);
-    __syncthreads();
-    for (size_t idx = tid; idx < MM; idx += GS_THREADS) p.kmm_inv[idx] = W[idx];
+    for (size_t idx = tid; idx < MM; idx += GS_THREADS) {
+        const double v = -X[idx];
+        W[idx] = v;                        // Kmm^-1
+        p.kmm_inv[idx] = v;
+    }
     if (p.kmm_only) return;
+    __syncthreads();
 
     // ---- A = Kmm + beta Psi2, A^-1 (partial_terms.py:60) ---------------------------------------
-    for (size_t idx = tid; idx < MM; idx += GS_THREADS) {
-        const int i = (int)(idx / M), j = (int)(idx % M);
-        X[idx] = p.kmm[idx] + beta * S0[pidx(M, i, j)];
-    }
+    for (size_t idx = tid; idx < MM; idx += GS_THREADS) X[idx] = fma(beta, P2[idx], p.kmm[idx]);
     __syncthreads();
-    gs_chol(X, M, &fail);
-    if (fail) {
+    if (!gs_sweep_invert(X, M, tmp, piv, red, &ldA)) {
         if (tid == 0) atomicOr(p.status, 2);
         return;
     }
-    v = 0.0;
-    for (int i = tid; i < M; i += GS_THREADS) v += log(X[(size_t)i * M + i]);
-    const double ldA = 2.0 * gp_block_sum(v, red);
-    gs_trtri(X, M, tmp);
-    gs_ltl(X, M, p.a_inv);
+    for (size_t idx = tid; idx < MM; idx += GS_THREADS) p.a_inv[idx] = -X[idx];
     __syncthreads();
 
     // ---- C = A^-1 Psi1Y, G1 = beta^2 C (partial_terms.py:115-121) -----------------------------
     for (int idx = tid; idx < M * D; idx += GS_THREADS) {
         const int i = idx / D, d = idx % D;
         double s = 0.0;
-        for (int k = 0; k < M; ++k) s = fma(p.a_inv[(size_t)i * M + k], P1Y[(size_t)k * D + d], s);
+        for (int k = 0; k < M; ++k) s = fma(-X[(size_t)i * M + k], P1Y[(size_t)k * D + d], s);
         p.c_mat[idx] = s;
         p.g_1[idx] = beta * beta * s;
     }
     __syncthreads();
-    v = 0.0;
+    double v = 0.0;
     for (int idx = tid; idx < M * D; idx += GS_THREADS) v = fma(P1Y[idx], p.c_mat[idx], v);
     const double tr1 = gp_block_sum(v, red);               // tr(Psi1Y^T A^-1 Psi1Y)
 
-    // ---- U = Psi2 Kmm^-1 -> X ---------------------------------------------------------------------
-    for (int i = ty; i < M; i += GS_THREADS / 32) {
-        for (int j = tx; j < M; j += 32) {
-            double s = 0.0;
-            for (int k = 0; k < M; ++k) s = fma(S0[pidx(M, i, k)], W[(size_t)k * M + j], s);
-            X[(size_t)i * M + j] = s;
-        }
-    }
+    // ---- U = Psi2 Kmm^-1 -> X  (X no longer needed: A^-1 lives in p.a_inv) ---------------------
+    gs_matmul(P2, W, M, [&](int i, int j, double val) { X[(size_t)i * M + j] = val; });
     __syncthreads();
     v = 0.0;
     for (int i = tid; i < M; i += GS_THREADS) v += X[(size_t)i * M + i];
@@ -195,28 +264,30 @@ __global__ void __launch_bounds__(GS_THREADS, 1) global_step_kernel(GsParams p)
     // ---- dF/dKmm, dF/dPsi2 (partial_terms.py:102-131) and the scalar contractions ------------
     double s_ap = 0.0, s_cpc = 0.0, s_kk = 0.0, s_22 = 0.0;
     const double hD = 0.5 * (double)D;
-    for (int i = ty; i < M; i += GS_THREADS / 32) {
-        for (int j = tx; j < M; j += 32) {
-            const size_t idx = (size_t)i * M + j;
-            double t = 0.0;
-            for (int k = 0; k < M; ++k) t = fma(W[(size_t)i * M + k], X[(size_t)k * M + j], t);   // Kinv Psi2 Kinv
-            double e = 0.0;
-            for (int d = 0; d < D; ++d) e = fma(p.c_mat[i * D + d], p.c_mat[j * D + d], e);     // (C C^T)[i,j]
-            const double ai = p.a_inv[idx], wi = W[idx], ps = S0[pidx(M, i, j)];
-            const double gk = hD * wi - hD * ai - hD * beta * t - 0.5 * beta * beta * e;
-            const double g2 = hD * beta * (wi - ai) - 0.5 * beta * beta * beta * e;
-            p.g_k[idx] = gk;
-            p.g_2[idx] = g2;
-            s_ap = fma(ai, ps, s_ap);
-            s_cpc = fma(ps, e, s_cpc);
-            s_kk = fma(gk, p.kmm[idx], s_kk);
-            s_22 = fma(g2, ps, s_22);
-        }
-    }
+    gs_matmul(W, X, M, [&](int i, int j, double t) {       // t = (Kinv Psi2 Kinv)[i,j]
+        const size_t idx = (size_t)i * M + j;
+        double e = 0.0;
+        for (int d = 0; d < D; ++d) e = fma(p.c_mat[i * D + d], p.c_mat[j * D + d], e);     // (C C^T)[i,j]
+        const double ai = p.a_inv[idx], wi = W[idx], ps = P2[idx];
+        const double gk = hD * wi - hD * ai - hD * beta * t - 0.5 * beta * beta * e;
+        const double g2 = hD * beta * (wi - ai) - 0.5 * beta * beta * beta * e;
+        p.g_k[idx] = gk;
+        p.g_2[idx] = g2;
+        s_ap = fma(ai, ps, s_ap);
+        s_cpc = fma(ps, e, s_cpc);
+        s_kk = fma(gk, p.kmm[idx], s_kk);
+        s_22 = fma(g2, ps, s_22);
+    });
     s_ap = gp_block_sum(s_ap, red);      // tr(A^-1 Psi2)
     s_cpc = gp_block_sum(s_cpc, red);    // tr(C^T Psi2 C)
     s_kk = gp_block_sum(s_kk, red);      // <dF/dKmm, Kmm>
     s_22 = gp_block_sum(s_22, red);      // <dF/dPsi2, Psi2>
+    __syncthreads();
+    // the work matrices are free now: keep dF/dKmm in X and dF/dPsi2 in W for the contractions
+    for (size_t idx = tid; idx < MM; idx += GS_THREADS) {
+        X[idx] = p.g_k[idx];
+        W[idx] = p.g_2[idx];
+    }
     __syncthreads();
 
     const int nz = M * Q;
@@ -239,22 +310,46 @@ __global__ void __launch_bounds__(GS_THREADS, 1) global_step_kernel(GsParams p)
         extra[0] = ldK; extra[1] = ldA; extra[2] = trKP; extra[3] = tr1;
     }
 
-    // ---- grad_alpha (partial_terms.py:247-254, 286-299) ----------------------------------------
-    for (int q = 0; q < Q; ++q) {
-        const double al = g.alpha[q];
-        const double *TAq = p.stats + p.off_ta + (int64_t)q * p.P;
-        const double *D1Aq = p.stats + p.off_d1a + (int64_t)q * M * D;
-        double s = 0.0;
+    // ---- grad_alpha (partial_terms.py:247-254, 286-299): one pass, Q partial sums per thread ----
+    {
+        double sq[GP_MAX_Q];
+#pragma unroll
+        for (int q = 0; q < GP_MAX_Q; ++q) sq[q] = 0.0;
+        if (tid < Q) ia2[tid] = 1.0 / (g.alpha[tid] * g.alpha[tid]);
+        __syncthreads();
         for (size_t idx = tid; idx < MM; idx += GS_THREADS) {
             const int i = (int)(idx / M), j = (int)(idx % M);
-            const double dz = p.Z[i * Q + q] - p.Z[j * Q + q];
             const int64_t pp = pidx(M, i, j);
-            s = fma(p.g_k[idx], -0.5 * p.kmm[idx] * dz * dz, s);
-            s = fma(p.g_2[idx], -0.25 * dz * dz * S0[pp] - TAq[pp] / (al * al), s);
+            const double gk = X[idx], g2 = W[idx], km = p.kmm[idx], ps = P2[idx];
+#pragma unroll
+            for (int q = 0; q < GP_MAX_Q; ++q) {
+                if (q < Q) {
+                    const double dz = p.Z[i * Q + q] - p.Z[j * Q + q];
+                    const double ta = p.stats[p.off_ta + (int64_t)q * p.P + pp];
+                    sq[q] = fma(gk, -0.5 * km * dz * dz, sq[q]);
+                    sq[q] = fma(g2, -0.25 * dz * dz * ps - ta * ia2[q], sq[q]);
+                }
+            }
         }
-        for (int idx = tid; idx < M * D; idx += GS_THREADS) s = fma(p.g_1[idx], D1Aq[idx], s);
-        s = gp_block_sum(s, red);
-        if (tid == 0) grad[nz + 1 + q] = s;
+        for (int idx = tid; idx < M * D; idx += GS_THREADS) {
+            const double g1 = p.g_1[idx];
+#pragma unroll
+            for (int q = 0; q < GP_MAX_Q; ++q)
+                if (q < Q) sq[q] = fma(g1, p.stats[p.off_d1a + (int64_t)q * M * D + idx], sq[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < GP_MAX_Q; ++q) {
+            if (q < Q) {
+                const double w = gp_warp_sum(sq[q]);
+                if (lane == 0) qred[wid * GP_MAX_Q + q] = w;
+            }
+        }
+        __syncthreads();
+        if (tid < Q) {
+            double s = 0.0;
+            for (int w = 0; w < GS_THREADS / 32; ++w) s += qred[w * GP_MAX_Q + tid];
+            grad[nz + 1 + tid] = s;
+        }
     }
 
     // ---- grad_Z (partial_terms.py:146-160, 207-240) --------------------------------------------
@@ -266,9 +361,8 @@ __global__ void __launch_bounds__(GS_THREADS, 1) global_step_kernel(GsParams p)
         for (int m = 0; m < M; ++m) {
             const double dz = zjk - p.Z[m * Q + k];
             const size_t jm = (size_t)j * M + m, mj = (size_t)m * M + j;
-            const int64_t pp = pidx(M, j, m);
-            s = fma(p.g_k[jm] + p.g_k[mj], -al * dz * p.kmm[jm], s);
-            s = fma(2.0 * p.g_2[jm], -0.5 * al * dz * S0[pp] + TZk[pp], s);
+            s = fma(X[jm] + X[mj], -al * dz * p.kmm[jm], s);
+            s = fma(2.0 * W[jm], -0.5 * al * dz * P2[jm] + TZk[pidx(M, j, m)], s);
         }
         const double *D1Z = p.stats + p.off_d1z + (int64_t)idx * D;
         for (int d = 0; d < D; ++d) s = fma(p.g_1[j * D + d], D1Z[d], s);
@@ -280,7 +374,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1) global_step_kernel(GsParams p)
         const int i = (int)(idx / M), j = (int)(idx % M);
         if (j < i) continue;
         const int64_t pp = gp_pair_index(M, i, j);
-        const double gs = (i == j) ? p.g_2[idx] : (p.g_2[idx] + p.g_2[(size_t)j * M + i]);
+        const double gs = (i == j) ? W[idx] : (W[idx] + W[(size_t)j * M + i]);
         p.pair_g[pp] = make_double2(p.pair_lk[pp], gs);
     }
 }
@@ -293,15 +387,17 @@ int gp_launch_global_step(gparml_ctx *c, bool kmm_only)
     p.fixed_beta = (c->flags & GPARML_FLAG_FIXED_BETA) ? 1 : 0;
     p.kmm_only = kmm_only ? 1 : 0;
     const size_t MM = (size_t)c->M * c->M;
-    const size_t smem_full = (2 * MM + c->M) * sizeof(double);
-    p.use_smem = smem_full <= (size_t)220 * 1024 ? 1 : 0;
-    const size_t smem = p.use_smem ? smem_full : (size_t)c->M * sizeof(double);
+    const size_t vec = (size_t)(c->M > 256 ? c->M : 256) + c->M;      // pivot column buffers + pivots
+    const size_t smem_full = (2 * MM + vec) * sizeof(double);
+    p.use_smem = smem_full <= (size_t)216 * 1024 ? 1 : 0;
+    const size_t smem = p.use_smem ? smem_full : vec * sizeof(double);
     p.stats = c->stats;
     p.off_p1y = c->L.off_p1y; p.off_d1z = c->L.off_d1z; p.off_d1a = c->L.off_d1a;
     p.off_s0 = c->L.off_s0; p.off_tz = c->L.off_tz; p.off_ta = c->L.off_ta;
     p.Z = c->Z; p.glob = c->d_glob; p.pair_lk = c->pair_lk;
     p.kmm = c->kmm; p.kmm_inv = c->kmm_inv; p.a_inv = c->a_inv;
     p.g_k = c->g_k; p.g_1 = c->g_1; p.g_2 = c->g_2; p.c_mat = c->c_mat;
+    p.psi2_full = c->psi2_full;
     p.X = c->scratch_x; p.W = c->scratch_w;
     p.pair_g = c->pair_g;
     p.out = c->glob_out;

@@ -43,14 +43,20 @@ __device__ __forceinline__ void psi1_cp_async8(double *dst_smem, const double *s
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(gp_smem_u32(dst_smem)), "l"(src) : "memory");
 }
 
-template <int DC>
-__global__ void __launch_bounds__(PSI1_THREADS, (DC <= 10) ? 4 : 2)
+__device__ __forceinline__ void psi1_cp_async16(double *dst_smem, const double *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(gp_smem_u32(dst_smem)), "l"(src) : "memory");
+}
+
+template <int Q, int DC>
+__global__ void __launch_bounds__(PSI1_THREADS, 4)
 psi1_stats_kernel(Psi1Params p)
 {
     extern __shared__ __align__(16) double sm[];
     __shared__ double exp_tab[GP_EXP_TAB];
     constexpr int DCP = (DC + 1) & ~1;                    // padded row of the Y tile (16-byte rows)
-    const int Q = p.Q, J = 1 + 2 * Q, MB = p.MB, R = p.R;
+    constexpr int J = 1 + 2 * Q, R = (3 * Q + 2) & ~1, NV2 = (Q + 1) / 2;
+    const int MB = p.MB;
     const int rows = MB * J;
     const int rows_pad = (rows + 1) & ~1;
     double *A = sm;                                      // [TN][rows_pad]
@@ -82,10 +88,15 @@ psi1_stats_kernel(Psi1Params p)
     auto issue = [&](int64_t base, int buf) {
         const int cnt = (int)((n_hi - base < PSI1_TN) ? (n_hi - base) : PSI1_TN);
         double *rb = recs + buf * PSI1_TN * R, *yb = Ys + buf * PSI1_TN * DCP;
-        for (int idx = tid; idx < cnt * R; idx += PSI1_THREADS) psi1_cp_async8(rb + idx, p.rec1 + base * R + idx);
-        for (int idx = tid; idx < cnt * dcols; idx += PSI1_THREADS) {
-            const int nn = idx / dcols, dd = idx % dcols;
-            psi1_cp_async8(yb + nn * DCP + dd, p.Y + (base + nn) * p.D + d0 + dd);
+        for (int idx = tid; idx < cnt * (R / 2); idx += PSI1_THREADS) psi1_cp_async16(rb + 2 * idx, p.rec1 + base * R + 2 * idx);
+        if (p.D == DCP && ((cnt * DCP) & 1) == 0) {
+            // single chunk and unpadded rows: the Y tile is one contiguous, 16-byte aligned block
+            for (int idx = tid; idx < cnt * (DCP / 2); idx += PSI1_THREADS) psi1_cp_async16(yb + 2 * idx, p.Y + base * p.D + 2 * idx);
+        } else {
+            for (int idx = tid; idx < cnt * DCP; idx += PSI1_THREADS) {
+                const int nn = idx / DCP, dd = idx % DCP;               // compile-time divisor
+                if (dd < dcols) psi1_cp_async8(yb + idx, p.Y + (base + nn) * p.D + d0 + dd);
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -101,22 +112,30 @@ psi1_stats_kernel(Psi1Params p)
         for (int item = tid; item < cnt * MB; item += PSI1_THREADS) {
             const int nn = item / MB, ml = item % MB;
             if (m0 + ml < p.M) {
-                const double *rec = rb + nn * R;
+                const double2 *rec = reinterpret_cast<const double2 *>(rb + nn * R);
                 double *ar = A + (size_t)nn * rows_pad + ml;                    // row (j, ml) at ar[j * MB]
-                double e = rec[3 * Q];
+                double ad[Q];
+                double e = rb[nn * R + 3 * Q];
+#pragma unroll
                 for (int q = 0; q < Q; ++q) {
-                    const double2 ma = *reinterpret_cast<const double2 *>(rec + 2 * q);   // (mu_q, a_q)
+                    const double2 ma = rec[q];                                  // (mu_q, a_q)
                     const double d = ma.x - zs[q * MB + ml];
-                    const double ad = ma.y * d;
-                    e = fma(-0.5 * ad, d, e);
-                    ar[(1 + q) * MB] = ad;
+                    ad[q] = ma.y * d;
+                    e = fma(-0.5 * ad[q], d, e);
                 }
                 const double psi = gp_exp(e, exp_tab);
                 ar[0] = psi;
-                for (int q = 0; q < Q; ++q) {
-                    const double ad = ar[(1 + q) * MB];
-                    ar[(1 + q) * MB] = psi * ad;
-                    ar[(1 + Q + q) * MB] = psi * fma(ad, ad, rec[2 * Q + q]);
+#pragma unroll
+                for (int k = 0; k < NV2; ++k) {
+                    const double2 v2 = rec[Q + k];                              // (v1_2k, v1_2k+1)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int q = 2 * k + h;
+                        if (q < Q) {
+                            ar[(1 + q) * MB] = psi * ad[q];
+                            ar[(1 + Q + q) * MB] = psi * fma(ad[q], ad[q], h ? v2.y : v2.x);
+                        }
+                    }
                 }
             }
         }
@@ -187,16 +206,16 @@ __global__ void __launch_bounds__(256) psi1_reduce_kernel(const double *__restri
     }
 }
 
-template <int DC>
-static int launch_dc(gparml_ctx *c, Psi1Params &p, int dchunks)
+template <int Q, int DC>
+static int launch_qdc(gparml_ctx *c, Psi1Params &p, int dchunks)
 {
     const int J = 1 + 2 * c->Q;
     const int rows_pad = (p.MB * J + 1) & ~1;
     constexpr int DCP = (DC + 1) & ~1;
     const size_t smem = ((size_t)PSI1_TN * rows_pad + 2 * (size_t)PSI1_TN * DCP + 2 * (size_t)PSI1_TN * p.R + (size_t)p.MB * c->Q) * sizeof(double);
-    GP_CUDA(cudaFuncSetAttribute(psi1_stats_kernel<DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GP_CUDA(cudaFuncSetAttribute(psi1_stats_kernel<Q, DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
-    GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, psi1_stats_kernel<DC>, PSI1_THREADS, smem));
+    GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, psi1_stats_kernel<Q, DC>, PSI1_THREADS, smem));
     if (occ < 1) occ = 1;
     const int mblocks = (c->M + p.MB - 1) / p.MB;
     const int64_t per_split_rows = (int64_t)c->M * J * c->D;
@@ -220,7 +239,7 @@ static int launch_dc(gparml_ctx *c, Psi1Params &p, int dchunks)
     GP_TRY(gp_ensure_ws(c, (size_t)splits * per_split_rows * sizeof(double)));
     p.partial = c->ws;
     dim3 grid(mblocks, splits, dchunks);
-    psi1_stats_kernel<DC><<<grid, PSI1_THREADS, smem, c->stream>>>(p);
+    psi1_stats_kernel<Q, DC><<<grid, PSI1_THREADS, smem, c->stream>>>(p);
     GP_LAUNCH_CHECK(c);
     psi1_reduce_kernel<<<(int)((per_split_rows + 255) / 256), 256, 0, c->stream>>>(
         c->ws, splits, c->M, c->Q, c->D, c->d_glob, c->stats, c->L.off_p1y, c->L.off_d1z, c->L.off_d1a);
@@ -238,17 +257,23 @@ int gp_launch_psi1_stats(gparml_ctx *c)
     if (mb_max < 1) mb_max = 1;
     const int nblk = (c->M + mb_max - 1) / mb_max;
     p.MB = (c->M + nblk - 1) / nblk;
-    const int dchunks = (c->D + 15) / 16;
-    const int per = (c->D + dchunks - 1) / dchunks;     // columns per chunk
-    if (per <= 1) return launch_dc<1>(c, p, dchunks);
-    if (per <= 2) return launch_dc<2>(c, p, dchunks);
-    if (per <= 4) return launch_dc<4>(c, p, dchunks);
-    if (per <= 6) return launch_dc<6>(c, p, dchunks);
-    if (per <= 8) return launch_dc<8>(c, p, dchunks);
-    if (per <= 10) return launch_dc<10>(c, p, dchunks);
-    if (per <= 12) return launch_dc<12>(c, p, dchunks);
-    if (per <= 14) return launch_dc<14>(c, p, dchunks);
-    return launch_dc<16>(c, p, dchunks);
+    // output columns per CTA: chunks of at most 10, rounded up to an instantiated width
+    const int dchunks = (c->D + 9) / 10;
+    const int per = (c->D + dchunks - 1) / dchunks;
+    switch (c->Q) {
+#define CASE_Q(q)                                                   \
+    case q:                                                         \
+        if (per <= 1) return launch_qdc<q, 1>(c, p, dchunks);       \
+        if (per <= 2) return launch_qdc<q, 2>(c, p, dchunks);       \
+        if (per <= 4) return launch_qdc<q, 4>(c, p, dchunks);       \
+        if (per <= 8) return launch_qdc<q, 8>(c, p, dchunks);       \
+        return launch_qdc<q, 10>(c, p, dchunks);
+        CASE_Q(1) CASE_Q(2) CASE_Q(3) CASE_Q(4) CASE_Q(5) CASE_Q(6) CASE_Q(7) CASE_Q(8)
+        CASE_Q(9) CASE_Q(10) CASE_Q(11) CASE_Q(12) CASE_Q(13) CASE_Q(14) CASE_Q(15) CASE_Q(16)
+#undef CASE_Q
+    }
+    gp_set_error("psi1_stats: unsupported Q=%d (1..%d)", c->Q, GP_MAX_Q);
+    return GPARML_ERR_ARG;
 }
 
 // ---------------------------------------------------------------------------
