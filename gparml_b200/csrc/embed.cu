@@ -13,14 +13,23 @@
 //   g_mu[n,q] = -mu_nq - sum_m B Psi1 ad_q - 2 sum_p Gs Psi2_n wd_q
 //   g_S[n,q]  = -1/2 (1 - 1/S_nq) + 1/2 sum_m B Psi1 (ad_q^2 - a_nq) + sum_p Gs Psi2_n (2 wd_q^2 - w_nq)
 //
-// Mapping: the reduction runs over pairs for each point (the opposite direction to psi2_stats),
-// so one thread owns one point and keeps w (Q), mu - z_m/2 (Q), wd (Q) and the 2Q accumulators
-// in registers; Z/2 sits in shared memory and is read as broadcasts; (lk, Gs) per pair is a
-// warp-uniform 16-byte global load issued one pair ahead.  The grid is (point tiles) x (splits
-// of the m range, balanced by pair count); split partials are combined by embed_finish in a
-// fixed order.
+// Psi2 part (embed_psi2_kernel, >97 % of the work).  The reduction runs over pairs for each
+// point (the opposite direction to psi2_stats), so one thread owns one point.  Because the
+// accumulators belong to a point, the per-point factor sqrt(w_nq) can be pulled out of the
+// pair loop: with sw = sqrt(w), u_q = sw_q (mu_q - zbar_q) = fma(-sw_q, z_m'q / 2, sw_q (mu_q - z_mq / 2))
+//   Psi2_n = exp(lk + lc2 - sum_q u_q^2),   h = Gs Psi2_n,
+//   AM_q = sum_p h u_q,  AS_q = sum_p h u_q^2,  AH = sum_p h
+//   sum_p Gs Psi2_n wd_q = sw_q AM_q,   sum_p Gs Psi2_n wd_q^2 = w_q AS_q
+// i.e. 2 FMAs per latent dimension for the exponent instead of sub + mul + FMA: 5Q + 12 FP64
+// instructions per (point, pair) instead of 6Q + 12.  Registers per thread: sw, sw (mu - z_m/2),
+// u, AM, AS (5Q doubles); Z/2 sits in shared memory and is read as broadcasts; (lk, Gs) per
+// pair is a warp-uniform 16-byte global load issued one pair ahead.  Grid = (point tiles) x
+// (splits of the m range, balanced by pair count); split partials are combined in a fixed
+// order by embed_finish.
 //
-// Bound: FP64 pipe, 6Q + 21 FP64 instructions per (point, pair) at exp = 18.
+// Psi1 part (embed_psi1_kernel): thread per point, loop over the M inducing points.
+//
+// Bound: FP64 pipe.
 #include <math.h>
 
 #include "common.cuh"
@@ -43,7 +52,8 @@ struct EmbedParams {
     int64_t n;
     int M, D;
     int m_bounds[EMB_MAX_SPLITS + 1];
-    double *partial;     // [splits][n][2Q + 2]
+    double *partial;     // [splits][n][2Q + 1]  (AM, AS, AH)
+    double *psi1_part;   // [n][2Q + 1]          (sum_m h1 ad, sum_m h1 ad^2, sum_m h1),  h1 = B Psi1
 };
 
 #ifdef GP_USE_LIBM_EXP
@@ -54,7 +64,7 @@ struct EmbedParams {
 
 template <int Q>
 __global__ void __launch_bounds__(EMB_THREADS, (Q <= 10) ? EMB_MINB_LOWQ : ((Q <= 13) ? 2 : 1))
-embed_grads_kernel(EmbedParams p)
+embed_psi2_kernel(EmbedParams p)
 {
     constexpr int R = (3 * Q + 2) & ~1;
     constexpr int EUNR = EMB_UNROLL;
@@ -69,85 +79,119 @@ embed_grads_kernel(EmbedParams p)
     int64_t i = (int64_t)blockIdx.x * EMB_THREADS + tid;
     const bool valid = i < p.n;
     if (!valid) i = p.n - 1;                             // compute on a real record, never store
-    const double *r1 = p.rec1 + i * R, *r2 = p.rec2 + i * R;
-    const double *y = p.Y + i * p.D;
-    const double lc1 = r1[3 * Q], lc2 = r2[3 * Q];
-    double w[Q], dm[Q], wd[Q], acc_mu[Q], acc_s[Q];
-    double acc_h = 0.0, acc_b = 0.0;
+    const double2 *r2 = reinterpret_cast<const double2 *>(p.rec2 + i * R);
+    const double lc2 = p.rec2[i * R + 3 * Q];
+    double sw[Q], sdm[Q], u[Q], am[Q], as[Q];
+    double ah = 0.0;
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
-        w[q] = r2[2 * q + 1];
-        acc_mu[q] = 0.0;
-        acc_s[q] = 0.0;
+        sw[q] = sqrt(r2[q].y);
+        am[q] = 0.0;
+        as[q] = 0.0;
     }
     const int m_lo = p.m_bounds[blockIdx.y], m_hi = p.m_bounds[blockIdx.y + 1];
 
     for (int m = m_lo; m < m_hi; ++m) {
         const double *hm = hz + m * Q;
         const double2 *pg = p.pair_g + gp_pair_index(M, m, m);
-        double2 g = __ldg(pg);                           // first pair of the row, in flight during the Psi1 part
-        // ---- Psi1 side (partial_terms.py:388-390, 421-423) -----------------------------
-        {
-            double e = lc1;
+        double2 g = __ldg(pg);                           // first pair of the row
 #pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                const double2 ma = *reinterpret_cast<const double2 *>(r1 + 2 * q);   // (mu_q, a_q)
-                dm[q] = ma.x - hm[q];
-                const double d = dm[q] - hm[q];                                       // mu - z_m
-                wd[q] = ma.y * d;                                                     // ad_q
-                e = fma(-0.5 * wd[q], d, e);
-            }
-            double b = 0.0;
-            const double *g1 = p.G1 + (size_t)m * p.D;
-            for (int d = 0; d < p.D; ++d) b = fma(y[d], g1[d], b);
-            const double h1 = 0.5 * b * EMB_EXP(e);      // accumulators are scaled by 2 at the end
-            acc_b += h1;
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                const double t = h1 * wd[q];
-                acc_mu[q] += t;
-                acc_s[q] = fma(0.5 * t, wd[q], acc_s[q]);
-            }
-        }
-        // ---- Psi2 side (partial_terms.py:393, 425-426), pairs (m, m' >= m) -------------
+        for (int q = 0; q < Q; ++q) sdm[q] = sw[q] * (r2[q].x - hm[q]);      // sw (mu - z_m / 2); mu re-read from L1
 #pragma unroll EUNR
         for (int b = m; b < M; ++b) {
             const double2 gn = __ldg(pg + ((b + 1 < M) ? (b + 1 - m) : (b - m)));   // next pair, warp-uniform
             const double *hb = hz + b * Q;
-            double e0 = g.x + lc2, e1 = 0.0;
+            double e0 = g.x, e1 = lc2;
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
-                const double d = dm[q] - hb[q];          // mu - zbar
-                wd[q] = w[q] * d;
-                if (q & 1) e1 = fma(-wd[q], d, e1);
-                else e0 = fma(-wd[q], d, e0);
+                u[q] = fma(-sw[q], hb[q], sdm[q]);       // sw (mu - zbar)
+                if (q & 1) e1 = fma(-u[q], u[q], e1);
+                else e0 = fma(-u[q], u[q], e0);
             }
             const double h = g.y * EMB_EXP(e0 + e1);
-            acc_h += h;
+            ah += h;
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
-                const double t = h * wd[q];
-                acc_mu[q] += t;
-                acc_s[q] = fma(t, wd[q], acc_s[q]);
+                const double t = h * u[q];
+                am[q] += t;
+                as[q] = fma(t, u[q], as[q]);
             }
             g = gn;
         }
     }
     if (valid) {
-        double *out = p.partial + ((size_t)blockIdx.y * p.n + i) * (2 * Q + 2);
+        double *out = p.partial + ((size_t)blockIdx.y * p.n + i) * (2 * Q + 1);
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
-            out[q] = acc_mu[q];
-            out[Q + q] = acc_s[q];
+            out[q] = am[q];
+            out[Q + q] = as[q];
         }
-        out[2 * Q] = acc_h;
-        out[2 * Q + 1] = acc_b;
+        out[2 * Q] = ah;
     }
 }
 
-// Combine the split partials, add the KL terms (partial_terms.py:385,418), apply the softplus
-// chain and the sign flip (local_MapReduce.py:357-360).
-__global__ void __launch_bounds__(256) embed_finish_kernel(const double *__restrict__ partial, int splits, int64_t n, int Q, int R,
+// Psi1 side (partial_terms.py:388-390, 421-423): h1 = B[n,m] Psi1[n,m];
+//   out[q] = sum_m h1 ad_q,  out[Q+q] = sum_m h1 ad_q^2,  out[2Q] = sum_m h1
+template <int Q>
+__global__ void __launch_bounds__(128) embed_psi1_kernel(EmbedParams p)
+{
+    constexpr int R = (3 * Q + 2) & ~1;
+    extern __shared__ __align__(16) double zs[];         // [M][Q] = Z
+    __shared__ double exp_tab[GP_EXP_TAB];
+    const int tid = threadIdx.x;
+    const int M = p.M;
+    for (int idx = tid; idx < M * Q; idx += 128) zs[idx] = p.Z[idx];
+    gp_exp_load_table(exp_tab);
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * 128 + tid;
+    if (i >= p.n) return;
+    const double2 *r1 = reinterpret_cast<const double2 *>(p.rec1 + i * R);
+    const double lc1 = p.rec1[i * R + 3 * Q];
+    const double *y = p.Y + i * p.D;
+    double mu[Q], a[Q], ad[Q], s1[Q], s2[Q];
+    double s0 = 0.0;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const double2 ma = r1[q];
+        mu[q] = ma.x;
+        a[q] = ma.y;
+        s1[q] = 0.0;
+        s2[q] = 0.0;
+    }
+    for (int m = 0; m < M; ++m) {
+        const double *z = zs + m * Q;
+        double e = lc1;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const double d = mu[q] - z[q];
+            ad[q] = a[q] * d;
+            e = fma(-0.5 * ad[q], d, e);
+        }
+        double b = 0.0;
+        const double *g1 = p.G1 + (size_t)m * p.D;
+        for (int d = 0; d < p.D; ++d) b = fma(y[d], g1[d], b);
+        const double h1 = b * EMB_EXP(e);
+        s0 += h1;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const double t = h1 * ad[q];
+            s1[q] += t;
+            s2[q] = fma(t, ad[q], s2[q]);
+        }
+    }
+    double *out = p.psi1_part + (size_t)i * (2 * Q + 1);
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        out[q] = s1[q];
+        out[Q + q] = s2[q];
+    }
+    out[2 * Q] = s0;
+}
+
+// Combine the split partials and the Psi1 part, add the KL terms (partial_terms.py:385,418),
+// apply the softplus chain and the sign flip (local_MapReduce.py:357-360).
+__global__ void __launch_bounds__(256) embed_finish_kernel(const double *__restrict__ partial, int splits,
+                                                           const double *__restrict__ psi1_part, int64_t n, int Q, int R,
                                                            const double *__restrict__ rec1, const double *__restrict__ rec2,
                                                            const double *__restrict__ s_pos, const double *__restrict__ s_sig,
                                                            double *__restrict__ gx_mu, double *__restrict__ gx_s,
@@ -157,19 +201,19 @@ __global__ void __launch_bounds__(256) embed_finish_kernel(const double *__restr
     if (idx >= n * Q) return;
     const int64_t i = idx / Q;
     const int q = (int)(idx % Q);
-    const int W = 2 * Q + 2;
-    double amu = 0.0, as = 0.0, ah = 0.0, ab = 0.0;
+    const int W = 2 * Q + 1;
+    double am = 0.0, as = 0.0, ah = 0.0;
     for (int s = 0; s < splits; ++s) {
         const double *pr = partial + ((size_t)s * n + i) * W;
-        amu += pr[q];
+        am += pr[q];
         as += pr[Q + q];
         ah += pr[2 * Q];
-        ab += pr[2 * Q + 1];
     }
+    const double *p1 = psi1_part + (size_t)i * W;
     const double mu = rec2[i * R + 2 * q], w = rec2[i * R + 2 * q + 1], a = rec1[i * R + 2 * q + 1];
     const double S = s_pos[idx];
-    const double gmu = -mu - 2.0 * amu;
-    const double gs = -0.5 * (1.0 - 1.0 / S) + 2.0 * as - w * ah - a * ab;
+    const double gmu = -mu - p1[q] - 2.0 * sqrt(w) * am;
+    const double gs = -0.5 * (1.0 - 1.0 / S) + 0.5 * (p1[Q + q] - a * p1[2 * Q]) + w * (2.0 * as - ah);
     gx_mu[idx] = gmu;
     gx_s[idx] = gs;
     grad_latest[idx] = -gmu;
@@ -180,9 +224,10 @@ template <int Q>
 static int launch_q(gparml_ctx *c)
 {
     const size_t smem = (size_t)c->M * Q * sizeof(double);
-    GP_CUDA(cudaFuncSetAttribute(embed_grads_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GP_CUDA(cudaFuncSetAttribute(embed_psi2_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GP_CUDA(cudaFuncSetAttribute(embed_psi1_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
-    GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, embed_grads_kernel<Q>, EMB_THREADS, smem));
+    GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, embed_psi2_kernel<Q>, EMB_THREADS, smem));
     if (occ < 1) occ = 1;
     const int64_t ntiles = (c->n + EMB_THREADS - 1) / EMB_THREADS;
     const int64_t slots = (int64_t)c->sm_count * occ;
@@ -212,14 +257,19 @@ static int launch_q(gparml_ctx *c)
         p.m_bounds[s] = m;
     }
     p.m_bounds[splits] = c->M;
-    GP_TRY(gp_ensure_ws(c, (size_t)splits * c->n * (2 * Q + 2) * sizeof(double)));
+    const size_t W = 2 * Q + 1;
+    GP_TRY(gp_ensure_ws(c, (size_t)(splits + 1) * c->n * W * sizeof(double)));
     p.partial = c->ws;
+    p.psi1_part = c->ws + (size_t)splits * c->n * W;
+    embed_psi1_kernel<Q><<<(unsigned)((c->n + 127) / 128), 128, smem, c->stream>>>(p);
+    GP_LAUNCH_CHECK(c);
     dim3 grid((unsigned)ntiles, splits);
-    embed_grads_kernel<Q><<<grid, EMB_THREADS, smem, c->stream>>>(p);
+    embed_psi2_kernel<Q><<<grid, EMB_THREADS, smem, c->stream>>>(p);
     GP_LAUNCH_CHECK(c);
     const int64_t total = c->n * Q;
-    embed_finish_kernel<<<(int)((total + 255) / 256), 256, 0, c->stream>>>(c->ws, splits, c->n, Q, gp_rec_len(Q), c->rec1, c->rec2,
-                                                                           c->s_pos, c->s_sig, c->gx_mu, c->gx_s, c->grad_latest);
+    embed_finish_kernel<<<(int)((total + 255) / 256), 256, 0, c->stream>>>(c->ws, splits, p.psi1_part, c->n, Q, gp_rec_len(Q), c->rec1,
+                                                                           c->rec2, c->s_pos, c->s_sig, c->gx_mu, c->gx_s,
+                                                                           c->grad_latest);
     GP_LAUNCH_CHECK(c);
     return GPARML_OK;
 }

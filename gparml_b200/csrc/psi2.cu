@@ -125,7 +125,7 @@ psi2_stats_kernel(const double *__restrict__ rec2, int64_t n, const double *__re
             double wd[PP][Q], e0[PP], e1[PP], psi[PP];
             const double lc2 = tb[i * R + 3 * Q];
 #pragma unroll
-            for (int u = 0; u < PP; ++u) { e0[u] = lk[u] + lc2; e1[u] = 0.0; }
+            for (int u = 0; u < PP; ++u) { e0[u] = lk[u]; e1[u] = lc2; }   // the two partial sums start at lk and lc2
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
                 const double2 mw = r[q];           // (mu_q, w_q), broadcast; feeds all PP pairs
