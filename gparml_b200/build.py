@@ -13,8 +13,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libgparml_b200.so")
-SOURCES = ["capi.cu", "prep.cu", "psi1.cu", "psi2.cu", "embed.cu", "global_step.cu", "misc.cu"]
-HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(os.path.dirname(HERE), "include", "gparml_b200.h")]
+SOURCES = ["capi.cu", "prep.cu", "psi1.cu", "psi2.cu", "embed.cu", "global_step.cu", "global_step_large.cu", "misc.cu"]
+HEADERS = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cuh")] + [
+    os.path.join(os.path.dirname(HERE), "include", "gparml_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]

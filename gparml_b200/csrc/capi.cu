@@ -119,7 +119,7 @@ extern "C" int gparml_destroy(gparml_ctx *c)
     void *ptrs[] = {c->Y, c->x_mu, c->x_s, c->grad_d, c->grad_latest, c->grad_new, c->grad_old, c->rec1, c->rec2, c->s_pos, c->s_sig,
                     c->gx_mu, c->gx_s, c->psi1, c->Z, c->d_glob, c->pair_idx, c->pair_lk, c->pair_g, c->stats, c->ws, c->red_ws,
                     c->d_status, c->kmm, c->kmm_inv, c->a_inv, c->g_k, c->g_1, c->g_2, c->scratch_x, c->scratch_w, c->c_mat,
-                    c->glob_out, c->named_tmp, c->psi2_full};
+                    c->glob_out, c->named_tmp, c->psi2_full, c->gsl_ws};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);

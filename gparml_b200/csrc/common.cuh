@@ -138,6 +138,7 @@ struct gparml_ctx {
     double *scratch_x = nullptr, *scratch_w = nullptr;   // (M, M) each, used when M*M does not fit shared memory
     double *c_mat = nullptr;    // (M, D)
     double *psi2_full = nullptr;  // (M, M) expanded Psi2 for the global step
+    double *gsl_ws = nullptr;     // workspace of the large-M (multi-kernel) global step, allocated on first use
     double *glob_out = nullptr; // [0]=F, [1..] grad (M*Q + Q + 2), then scalars
     double *named_tmp = nullptr;  // expansion buffer
     size_t named_tmp_count = 0;

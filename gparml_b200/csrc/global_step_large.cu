@@ -1,0 +1,333 @@
+// K4 for large M (two M x M work matrices no longer fit one SM's shared memory, M > 116):
+// the same master step as global_step.cu spread over the whole GPU as a short sequence of
+// kernels on L2-resident matrices (M = 500: 2 MB each).
+//
+//   build        Kmm, full Psi2                                   elementwise, multi-CTA
+//   block sweep  A <- -A^-1 in blocks of NB = 32 pivots:           M / NB steps of
+//                  pivot   invert the NB x NB pivot block (1 CTA, register-resident sweep)
+//                  panel   T = A[:, K] Pinv, keep the old panel    (M rows in parallel)
+//                  update  A[i,j] -= T[i,:] . Old[j,:]  (rank-NB)  64 x 64 tiles, all SMs
+//   gemm         U = Psi2 Kinv,  T2 = Kinv U,  C = A^-1 Psi1Y      tiled DGEMM, all SMs
+//   assemble     dF/dKmm, dF/dPsi2, scalar contractions            elementwise + partial sums
+//   tail         bound, hyper-parameter gradients, pair table      one CTA (gs_common.cuh)
+//
+// Same arithmetic as the single-CTA kernel (block sweep == sequential sweep of the same
+// pivots), same error behaviour (non-positive pivot -> GPARML_ERR_NOT_PD).
+// Reference lines replaced: see global_step.cu.
+#include "gs_common.cuh"
+
+#define GSL_NB 32
+#define GSL_TILE 64
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gsl_build_kernel(GsParams p, double *__restrict__ X)
+{
+    const int M = p.M, Q = p.Q;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)M * M) return;
+    const int i = (int)(idx / M), j = (int)(idx % M);
+    double s = 0.0;
+    for (int q = 0; q < Q; ++q) {
+        const double dz = p.Z[i * Q + q] - p.Z[j * Q + q];
+        s = fma(p.glob->alpha[q] * dz, dz, s);
+    }
+    const double k = p.glob->sf2 * exp(-0.5 * s);
+    X[idx] = k;
+    p.kmm[idx] = k;
+    if (!p.kmm_only) p.psi2_full[idx] = p.stats[p.off_s0 + pidx(M, i, j)];
+}
+
+// X = Kmm + beta Psi2
+__global__ void __launch_bounds__(256) gsl_form_a_kernel(GsParams p, double *__restrict__ X)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)p.M * p.M) return;
+    X[idx] = fma(p.glob->beta, p.psi2_full[idx], p.kmm[idx]);
+}
+
+// dst = -src (and optionally a second copy)
+__global__ void __launch_bounds__(256) gsl_negate_kernel(const double *__restrict__ src, size_t count, double *__restrict__ dst,
+                                                         double *__restrict__ dst2)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count) return;
+    const double v = -src[idx];
+    dst[idx] = v;
+    if (dst2) dst2[idx] = v;
+}
+
+// pivot block: Pinv = (A[k0:k0+nb, k0:k0+nb])^-1 by a register-resident sweep; pivots -> piv[]
+__global__ void __launch_bounds__(1024) gsl_pivot_kernel(const double *__restrict__ A, int M, int k0, int nb,
+                                                         double *__restrict__ pinv_out, double *__restrict__ piv, int *status,
+                                                         int fail_bit)
+{
+    __shared__ double col[2][GSL_NB];
+    const int r = threadIdx.x >> 5, c = threadIdx.x & 31;
+    double e = (r < nb && c < nb) ? A[(size_t)(k0 + r) * M + k0 + c] : 0.0;
+    for (int k = 0; k < nb; ++k) {
+        double *cb = col[k & 1];
+        if (c == k) cb[r] = e;
+        __syncthreads();
+        const double d = cb[k];
+        if (!(d > 0.0) || !isfinite(d)) {
+            if (threadIdx.x == 0) atomicOr(status, fail_bit);
+            return;                                   // uniform
+        }
+        const double pi = 1.0 / d;
+        if (threadIdx.x == 0) piv[k0 + k] = d;
+        const double cr = cb[r], cc = cb[c];
+        if (r == k) e = (c == k) ? -pi : cc * pi;
+        else e = (c == k) ? cr * pi : fma(-cr * pi, cc, e);
+    }
+    if (r < nb && c < nb) pinv_out[r * GSL_NB + c] = -e;
+}
+
+// panel: Old[i][c] = A[i][k0 + c],  T[i][c] = sum_c' Old[i][c'] Pinv[c'][c]
+__global__ void __launch_bounds__(128) gsl_panel_kernel(const double *__restrict__ A, int M, int k0, int nb,
+                                                        const double *__restrict__ pinv, double *__restrict__ T,
+                                                        double *__restrict__ Old, const int *status)
+{
+    __shared__ double ps[GSL_NB * GSL_NB];
+    if (*status) return;
+    for (int idx = threadIdx.x; idx < GSL_NB * GSL_NB; idx += 128) ps[idx] = pinv[idx];
+    __syncthreads();
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= M) return;
+    double a[GSL_NB];
+#pragma unroll
+    for (int c = 0; c < GSL_NB; ++c) a[c] = (c < nb) ? A[(size_t)i * M + k0 + c] : 0.0;
+#pragma unroll
+    for (int c = 0; c < GSL_NB; ++c) Old[(size_t)i * GSL_NB + c] = a[c];
+    for (int c = 0; c < nb; ++c) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < GSL_NB; ++k) s = fma(a[k], ps[k * GSL_NB + c], s);
+        T[(size_t)i * GSL_NB + c] = s;
+    }
+    for (int c = nb; c < GSL_NB; ++c) T[(size_t)i * GSL_NB + c] = 0.0;
+}
+
+// rank-NB update of the whole matrix, 64 x 64 tile per CTA, 4 x 4 outputs per thread
+__global__ void __launch_bounds__(256) gsl_update_kernel(double *__restrict__ A, int M, int k0, int nb,
+                                                         const double *__restrict__ pinv, const double *__restrict__ T,
+                                                         const double *__restrict__ Old, const int *status)
+{
+    __shared__ __align__(16) double Ts[GSL_NB][GSL_TILE];      // [c][i]
+    __shared__ __align__(16) double Os[GSL_NB][GSL_TILE];      // [c][j]
+    if (*status) return;
+    const int i0 = blockIdx.y * GSL_TILE, j0 = blockIdx.x * GSL_TILE;
+    for (int idx = threadIdx.x; idx < GSL_TILE * GSL_NB; idx += 256) {
+        const int r = idx / GSL_NB, c = idx % GSL_NB;
+        Ts[c][r] = (i0 + r < M) ? T[(size_t)(i0 + r) * GSL_NB + c] : 0.0;
+        Os[c][r] = (j0 + r < M) ? Old[(size_t)(j0 + r) * GSL_NB + c] : 0.0;
+    }
+    __syncthreads();
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+#pragma unroll 8
+    for (int c = 0; c < GSL_NB; ++c) {
+        const double2 t01 = *reinterpret_cast<const double2 *>(&Ts[c][ty * 4]), t23 = *reinterpret_cast<const double2 *>(&Ts[c][ty * 4 + 2]);
+        const double2 o01 = *reinterpret_cast<const double2 *>(&Os[c][tx * 4]), o23 = *reinterpret_cast<const double2 *>(&Os[c][tx * 4 + 2]);
+        const double tv[4] = {t01.x, t01.y, t23.x, t23.y}, ov[4] = {o01.x, o01.y, o23.x, o23.y};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = fma(tv[a], ov[b], acc[a][b]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int i = i0 + ty * 4 + a;
+        if (i >= M) continue;
+        const bool ik = i >= k0 && i < k0 + nb;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int j = j0 + tx * 4 + b;
+            if (j >= M) continue;
+            const bool jk = j >= k0 && j < k0 + nb;
+            double v;
+            if (ik && jk) v = -pinv[(i - k0) * GSL_NB + (j - k0)];
+            else if (jk) v = Ts[j - k0][ty * 4 + a];                      // T[i][j - k0]
+            else if (ik) v = T[(size_t)j * GSL_NB + (i - k0)];            // symmetric counterpart
+            else v = A[(size_t)i * M + j] - acc[a][b];
+            A[(size_t)i * M + j] = v;
+        }
+    }
+}
+
+// C (M x N, ldc) = alpha * A (M x K, lda) * B (K x N, ldb); 64 x 64 x 16 tiles, 4 x 4 per thread
+__global__ void __launch_bounds__(256) gsl_gemm_kernel(const double *__restrict__ A, int lda, const double *__restrict__ B, int ldb,
+                                                       double *__restrict__ C, int ldc, int M, int N, int K, double alpha,
+                                                       const int *status)
+{
+    __shared__ __align__(16) double As[16][GSL_TILE];          // [k][i]
+    __shared__ __align__(16) double Bs[16][GSL_TILE];          // [k][j]
+    if (*status) return;
+    const int i0 = blockIdx.y * GSL_TILE, j0 = blockIdx.x * GSL_TILE;
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    for (int kk = 0; kk < K; kk += 16) {
+        for (int idx = threadIdx.x; idx < GSL_TILE * 16; idx += 256) {
+            const int r = idx / 16, k = idx % 16;                  // A tile: rows i0 + r, cols kk + k
+            As[k][r] = (i0 + r < M && kk + k < K) ? A[(size_t)(i0 + r) * lda + kk + k] : 0.0;
+            const int k2 = idx / GSL_TILE, c = idx % GSL_TILE;     // B tile: rows kk + k2, cols j0 + c
+            Bs[k2][c] = (kk + k2 < K && j0 + c < N) ? B[(size_t)(kk + k2) * ldb + j0 + c] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const double2 a01 = *reinterpret_cast<const double2 *>(&As[k][ty * 4]), a23 = *reinterpret_cast<const double2 *>(&As[k][ty * 4 + 2]);
+            const double2 b01 = *reinterpret_cast<const double2 *>(&Bs[k][tx * 4]), b23 = *reinterpret_cast<const double2 *>(&Bs[k][tx * 4 + 2]);
+            const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int i = i0 + ty * 4 + a, j = j0 + tx * 4 + b;
+            if (i < M && j < N) C[(size_t)i * ldc + j] = alpha * acc[a][b];
+        }
+}
+
+// dF/dKmm, dF/dPsi2 (partial_terms.py:102-131), G1 = beta^2 C, and per-CTA partial sums of
+// the scalar contractions: part[b] = (tr(A^-1 Psi2), tr(C^T Psi2 C), <GK,Kmm>, <G2,Psi2>, tr(Kinv Psi2), <Psi1Y, C>)
+__global__ void __launch_bounds__(256) gsl_assemble_kernel(GsParams p, const double *__restrict__ Kinv, const double *__restrict__ U,
+                                                           const double *__restrict__ T2, double *__restrict__ part)
+{
+    __shared__ double sh[33];
+    const int M = p.M, D = p.D;
+    const size_t MM = (size_t)M * M;
+    const double beta = p.glob->beta, hD = 0.5 * (double)D;
+    double s[6] = {0, 0, 0, 0, 0, 0};
+    if (*p.status == 0) {
+        for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < MM; idx += (size_t)gridDim.x * blockDim.x) {
+            const int i = (int)(idx / M), j = (int)(idx % M);
+            double e = 0.0;
+            for (int d = 0; d < D; ++d) e = fma(p.c_mat[i * D + d], p.c_mat[j * D + d], e);
+            const double ai = p.a_inv[idx], wi = Kinv[idx], ps = p.psi2_full[idx], t = T2[idx];
+            const double gk = hD * wi - hD * ai - hD * beta * t - 0.5 * beta * beta * e;
+            const double g2 = hD * beta * (wi - ai) - 0.5 * beta * beta * beta * e;
+            p.g_k[idx] = gk;
+            p.g_2[idx] = g2;
+            s[0] = fma(ai, ps, s[0]);
+            s[1] = fma(ps, e, s[1]);
+            s[2] = fma(gk, p.kmm[idx], s[2]);
+            s[3] = fma(g2, ps, s[3]);
+            if (i == j) s[4] += U[idx];
+        }
+        const double *P1Y = p.stats + p.off_p1y;
+        for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (size_t)M * D; idx += (size_t)gridDim.x * blockDim.x) {
+            const double c = p.c_mat[idx];
+            p.g_1[idx] = beta * beta * c;
+            s[5] = fma(P1Y[idx], c, s[5]);
+        }
+    }
+    for (int k = 0; k < 6; ++k) {
+        const double v = gp_block_sum(s[k], sh);
+        if (threadIdx.x == 0) part[(size_t)blockIdx.x * 6 + k] = v;
+    }
+}
+
+// one CTA: finish the scalars (fixed-order sums) and run the shared tail
+__global__ void __launch_bounds__(GS_THREADS, 1) gsl_tail_kernel(GsParams p, const double *__restrict__ part, int nparts,
+                                                                 const double *__restrict__ pivK, const double *__restrict__ pivA)
+{
+    __shared__ double red[33];
+    __shared__ double qred[32 * GP_MAX_Q];
+    __shared__ double ia2[GP_MAX_Q];
+    if (*p.status) return;
+    const int tid = threadIdx.x, M = p.M;
+    double s[6];
+    for (int k = 0; k < 6; ++k) {
+        double v = 0.0;
+        for (int b = tid; b < nparts; b += GS_THREADS) v += part[(size_t)b * 6 + k];
+        s[k] = gp_block_sum(v, red);
+    }
+    double v = 0.0, w = 0.0;
+    for (int i = tid; i < M; i += GS_THREADS) { v += log(pivK[i]); w += log(pivA[i]); }
+    const double ldK = gp_block_sum(v, red), ldA = gp_block_sum(w, red);
+    __syncthreads();
+    gs_tail(p, p.g_k, p.g_2, p.psi2_full, ldK, ldA, s[5], s[4], s[0], s[1], s[2], s[3], qred, ia2);
+}
+
+// ---------------------------------------------------------------------------------------------
+static int block_sweep(gparml_ctx *c, double *X, double *pinv, double *T, double *Old, double *piv, int fail_bit)
+{
+    const int M = c->M;
+    const int tiles = (M + GSL_TILE - 1) / GSL_TILE;
+    for (int k0 = 0; k0 < M; k0 += GSL_NB) {
+        const int nb = (M - k0 < GSL_NB) ? (M - k0) : GSL_NB;
+        gsl_pivot_kernel<<<1, 1024, 0, c->stream>>>(X, M, k0, nb, pinv, piv, c->d_status, fail_bit);
+        GP_LAUNCH_CHECK(c);
+        gsl_panel_kernel<<<(M + 127) / 128, 128, 0, c->stream>>>(X, M, k0, nb, pinv, T, Old, c->d_status);
+        GP_LAUNCH_CHECK(c);
+        gsl_update_kernel<<<dim3(tiles, tiles), 256, 0, c->stream>>>(X, M, k0, nb, pinv, T, Old, c->d_status);
+        GP_LAUNCH_CHECK(c);
+    }
+    return GPARML_OK;
+}
+
+static int gemm(gparml_ctx *c, const double *A, int lda, const double *B, int ldb, double *C, int ldc, int M, int N, int K, double alpha)
+{
+    dim3 grid((N + GSL_TILE - 1) / GSL_TILE, (M + GSL_TILE - 1) / GSL_TILE);
+    gsl_gemm_kernel<<<grid, 256, 0, c->stream>>>(A, lda, B, ldb, C, ldc, M, N, K, alpha, c->d_status);
+    GP_LAUNCH_CHECK(c);
+    return GPARML_OK;
+}
+
+int gp_launch_global_step_large(gparml_ctx *c, GsParams &p)
+{
+    const int M = c->M, D = c->D;
+    const size_t MM = (size_t)M * M;
+    const int eb = (int)((MM + 255) / 256);
+    // scratch layout inside the context's large-M workspace
+    double *X = c->scratch_x, *W = c->scratch_w;                  // X: matrix being inverted / U;  W: Kmm^-1
+    double *T2 = c->gsl_ws;                                       // (M, M)  Kinv Psi2 Kinv
+    double *pinv = T2 + MM;                                       // (NB, NB)
+    double *T = pinv + GSL_NB * GSL_NB;                           // (M, NB)
+    double *Old = T + (size_t)M * GSL_NB;                         // (M, NB)
+    double *pivK = Old + (size_t)M * GSL_NB;                      // (M)
+    double *pivA = pivK + M;                                      // (M)
+    double *part = pivA + M;                                      // (nparts, 6)
+    const int nparts = c->sm_count * 2;
+
+    gsl_build_kernel<<<eb, 256, 0, c->stream>>>(p, X);
+    GP_LAUNCH_CHECK(c);
+    GP_TRY(block_sweep(c, X, pinv, T, Old, pivK, 1));
+    gsl_negate_kernel<<<eb, 256, 0, c->stream>>>(X, MM, W, c->kmm_inv);
+    GP_LAUNCH_CHECK(c);
+    if (p.kmm_only) return GPARML_OK;
+
+    gsl_form_a_kernel<<<eb, 256, 0, c->stream>>>(p, X);
+    GP_LAUNCH_CHECK(c);
+    GP_TRY(block_sweep(c, X, pinv, T, Old, pivA, 2));
+    gsl_negate_kernel<<<eb, 256, 0, c->stream>>>(X, MM, c->a_inv, nullptr);
+    GP_LAUNCH_CHECK(c);
+
+    GP_TRY(gemm(c, c->a_inv, M, c->stats + c->L.off_p1y, D, c->c_mat, D, M, D, M, 1.0));      // C = A^-1 Psi1Y
+    GP_TRY(gemm(c, c->psi2_full, M, W, M, X, M, M, M, M, 1.0));                                 // U = Psi2 Kinv
+    GP_TRY(gemm(c, W, M, X, M, T2, M, M, M, M, 1.0));                                           // T2 = Kinv U
+    gsl_assemble_kernel<<<nparts, 256, 0, c->stream>>>(p, W, X, T2, part);
+    GP_LAUNCH_CHECK(c);
+    gsl_tail_kernel<<<1, GS_THREADS, 0, c->stream>>>(p, part, nparts, pivK, pivA);
+    GP_LAUNCH_CHECK(c);
+    return GPARML_OK;
+}
+
+size_t gp_global_step_large_ws_doubles(int M, int sm_count)
+{
+    return (size_t)M * M + GSL_NB * GSL_NB + 2 * (size_t)M * GSL_NB + 2 * (size_t)M + (size_t)sm_count * 2 * 6 + 64;
+}

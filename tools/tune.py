@@ -19,7 +19,7 @@ CSRC = os.path.join(ROOT, "gparml_b200", "csrc")
 VDIR = os.path.join(ROOT, "gparml_b200", "variants")
 NVCC = "/usr/local/cuda/bin/nvcc"
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
-ALL = ["capi.cu", "prep.cu", "psi1.cu", "psi2.cu", "embed.cu", "global_step.cu", "misc.cu"]
+ALL = ["capi.cu", "prep.cu", "psi1.cu", "psi2.cu", "embed.cu", "global_step.cu", "global_step_large.cu", "misc.cu"]
 
 # name -> {source: [defines]}
 VARIANTS = {
