@@ -214,3 +214,24 @@ def test_scg_local_ops_match_numpy():
         assert np.allclose(c.download(_lib.A_GRAD_D, (2, n, Q)), st[0]["d"], rtol=1e-15, atol=0)
         c.scg_reset_d(); O.scg_reset_d(st)
         assert np.array_equal(c.download(_lib.A_GRAD_D, (2, n, Q)), st[0]["d"])
+
+
+@pytest.mark.parametrize("Q,D,M", [(1, 1, 5), (3, 3, 17), (7, 13, 40), (12, 2, 33), (16, 5, 20), (5, 21, 130)])
+def test_template_paths_odd_shapes(Q, D, M):
+    """Every template path: odd/even Q (record padding), Q > 10 (one pair per thread), Q = 16,
+    D that needs several column chunks, M > 116 (multi-kernel master step), ragged 3-shard split."""
+    from gparml_b200.synthetic import make_problem
+    from oracle import c_oracle
+    n = 700 + 13 * Q
+    p = make_problem(n, M, Q, D, seed=100 + Q, generic_hypers=True, with_direction=True)
+    shards = _shards_of(p, 3)
+    ref = c_oracle.evaluate(shards, p["Z"], p["sf2"], p["alpha"], p["beta"], step_size=1e-3)
+    res = _gpu_evaluate(shards, p["Z"], p["sf2"], p["alpha"], p["beta"], step_size=1e-3)
+    errs = {k: relerr(res["stats"][k], v) for k, v in ref["stats"].items()}
+    for key in ("F", "grad_Z", "grad_alpha", "grad_sf2", "grad_beta", "dF_dKmm", "dF_dsum_exp_K_miY", "dF_dsum_exp_K_mi_K_im"):
+        errs[key] = relerr(res["global"][key], ref["global"][key])
+    for i, (a, b) in enumerate(zip(res["grad_latest"], ref["grad_latest"])):
+        errs["grad_latest_%d" % i] = relerr(a, b)
+    print(Q, D, M, "log10 cond %.2f" % np.log10(ref["global"]["cond_Kmm"]), "max rel err %.2e at %s" % (max(errs.values()), max(errs, key=errs.get)))
+    bad = {k2: v for k2, v in errs.items() if not v <= TOL}
+    assert not bad, bad
