@@ -43,6 +43,7 @@ PROTOTYPES = {
     "gparml_create": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _i64, ctypes.c_int]),
     "gparml_destroy": (ctypes.c_int, [_vp]),
     "gparml_set_stream": (ctypes.c_int, [_vp, _vp]),
+    "gparml_use_own_stream": (ctypes.c_int, [_vp]),
     "gparml_synchronize": (ctypes.c_int, [_vp]),
     "gparml_set_n_total": (ctypes.c_int, [_vp, _i64]),
     "gparml_upload_shard": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, ctypes.c_int]),

@@ -131,7 +131,15 @@ extern "C" int gparml_set_stream(gparml_ctx *c, void *s)
 {
     CHECK_CTX(c);
     GP_CUDA(cudaStreamSynchronize(c->stream));
-    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    c->stream = (cudaStream_t)s;          // taken literally: NULL is the legacy default stream
+    return GPARML_OK;
+}
+
+extern "C" int gparml_use_own_stream(gparml_ctx *c)
+{
+    CHECK_CTX(c);
+    GP_CUDA(cudaStreamSynchronize(c->stream));
+    c->stream = c->own_stream;
     return GPARML_OK;
 }
 

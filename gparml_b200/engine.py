@@ -65,7 +65,11 @@ class ShardContext(object):
 
     # -- plumbing -----------------------------------------------------------------
     def set_stream(self, cuda_stream_ptr):
-        _lib.check(self._lib.gparml_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr or 0)))
+        """Order the context's work on the given cudaStream_t (0 = CUDA's legacy default stream)."""
+        _lib.check(self._lib.gparml_set_stream(self._h, ctypes.c_void_p(int(cuda_stream_ptr or 0))))
+
+    def use_own_stream(self):
+        _lib.check(self._lib.gparml_use_own_stream(self._h))
 
     def use_torch_stream(self):
         """Order this context's work on torch's current stream (needed when the packed

@@ -101,7 +101,12 @@ const char *gparml_last_error(void);                 /* message of the last fail
  * n_total is the global number of points N (options['N'], local_MapReduce.py:46). */
 int gparml_create(gparml_ctx **out, int device, int M, int Q, int D, int64_t n_total, int flags);
 int gparml_destroy(gparml_ctx *ctx);
-int gparml_set_stream(gparml_ctx *ctx, void *cuda_stream);   /* cudaStream_t; NULL = the context's own */
+/* Order all work of the context on the caller's stream (cudaStream_t passed as void*).  The
+ * handle is taken literally: NULL is CUDA's legacy default stream 0 (what torch uses unless a
+ * stream context is active), NOT "the context's own stream" -- use gparml_use_own_stream()
+ * to go back to the private non-blocking stream the context was created with. */
+int gparml_set_stream(gparml_ctx *ctx, void *cuda_stream);
+int gparml_use_own_stream(gparml_ctx *ctx);
 int gparml_synchronize(gparml_ctx *ctx);
 int gparml_set_n_total(gparml_ctx *ctx, int64_t n_total);
 
