@@ -381,6 +381,29 @@ def main():
                                    "launch_ms": med["embed_grads"], "algorithmic_ops_per_launch": w_emb}
     total_ops = algorithmic_ops(N, M, Q, D, fixed)
     roofline["whole_evaluation_frac"] = (2.0 * total_ops / world / (ms_per_step * 1e-3) / 1e12) / peak
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture of the same workload
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")))
+        ent = tr.get(args.config, {}).get("psi2_stats_kernel")
+        if ent and int(ent["n_local"]) == n_loc:
+            roofline["traffic"] = ent["dram_bytes"]
+            roofline["traffic_source"] = ent.get("source")
+    except Exception:
+        pass
+    # the HBM-bound streaming kernel (prep_points): algorithmic bytes against the measured copy bandwidth
+    hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        hbm_peak, hbm_src = float(mp["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        pass
+    R = (3 * Q + 2) & ~1
+    prep_bytes = n_loc * 8 * ((2 * Q if fixed else 4 * Q) + 2 * R + 2 * Q)
+    if med.get("prep_points", 0) > 0:
+        gbs = prep_bytes / (med["prep_points"] * 1e-3) / 1e9
+        roofline["prep_points_hbm"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                       "peak_source": hbm_src, "algorithmic_bytes_per_launch": prep_bytes,
+                                       "launch_ms": med["prep_points"]}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
