@@ -119,7 +119,7 @@ extern "C" int gparml_destroy(gparml_ctx *c)
     void *ptrs[] = {c->Y, c->x_mu, c->x_s, c->grad_d, c->grad_latest, c->grad_new, c->grad_old, c->rec1, c->rec2, c->s_pos, c->s_sig,
                     c->gx_mu, c->gx_s, c->psi1, c->Z, c->d_glob, c->pair_idx, c->pair_lk, c->pair_g, c->stats, c->ws, c->red_ws,
                     c->d_status, c->kmm, c->kmm_inv, c->a_inv, c->g_k, c->g_1, c->g_2, c->scratch_x, c->scratch_w, c->c_mat,
-                    c->glob_out, c->named_tmp, c->psi2_full, c->gsl_ws};
+                    c->glob_out, c->named_tmp, c->psi2_full, c->gsl_ws, c->rec2f};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -175,6 +175,7 @@ static int ensure_shard_capacity(gparml_ctx *c, int64_t n)
     GP_TRY(dev_alloc(&c->grad_old, 2 * nq));
     GP_TRY(dev_alloc(&c->rec1, (size_t)n * R));
     GP_TRY(dev_alloc(&c->rec2, (size_t)n * R));
+    if (c->flags & GPARML_FLAG_FP32_MAP) GP_TRY(dev_alloc(&c->rec2f, (size_t)n * gp_rec_len_f32(c->Q)));
     GP_TRY(dev_alloc(&c->s_pos, nq));
     GP_TRY(dev_alloc(&c->s_sig, nq));
     GP_TRY(dev_alloc(&c->gx_mu, nq));
@@ -220,6 +221,13 @@ extern "C" int gparml_set_globals(gparml_ctx *c, const double *Z, double sf2, co
     for (int q = 0; q < c->Q; ++q) {
         if (!(alpha[q] >= 0.0)) { gp_set_error("set_globals: alpha[%d] negative (kernel_exp.py:30 assert)", q); return GPARML_ERR_ARG; }
         c->h_glob.alpha[q] = alpha[q];
+    }
+    if (c->flags & GPARML_FLAG_FP32_MAP) {          // centre of the inducing inputs (fp32 maps subtract it)
+        for (int q = 0; q < c->Q; ++q) {
+            double s = 0.0;
+            for (int m = 0; m < c->M; ++m) s += Z[(size_t)m * c->Q + q];
+            c->h_glob.center[q] = s / c->M;
+        }
     }
     // pageable host memory: the async copies below stage synchronously, so Z/alpha may be reused by the caller on return
     GP_CUDA(cudaMemcpyAsync(c->Z, Z, (size_t)c->M * c->Q * sizeof(double), cudaMemcpyHostToDevice, c->stream));

@@ -43,6 +43,8 @@ void gp_set_error(const char *fmt, ...);
 //   padded to an even number of doubles so every record is 16-byte aligned.
 // ---------------------------------------------------------------------------
 __host__ __device__ inline int gp_rec_len(int Q) { return (3 * Q + 2) & ~1; }
+// fp32 record: same fields as floats, padded to a multiple of 4 (16-byte records)
+__host__ __device__ inline int gp_rec_len_f32(int Q) { return (3 * Q + 4) & ~3; }
 
 // packed partial-sum buffer (see DESIGN.md "packed statistics")
 struct StatLayout {
@@ -83,6 +85,7 @@ struct GlobalsDev {
     double sf2, beta;
     double log_sf2;
     double alpha[GP_MAX_Q];
+    double center[GP_MAX_Q];   // column means of Z: the fp32 maps work on mu - center, z - center
 };
 
 // ---------------------------------------------------------------------------
@@ -109,6 +112,7 @@ struct gparml_ctx {
     double *x_s = nullptr;      // (n, Q) uploaded domain
     double *grad_d = nullptr, *grad_latest = nullptr, *grad_new = nullptr, *grad_old = nullptr;  // (2, n, Q)
     double *rec1 = nullptr, *rec2 = nullptr;   // (n, R)
+    float *rec2f = nullptr;     // (n, RF) fp32 copy of the Psi2 records (GPARML_FLAG_FP32_MAP only)
     double *s_pos = nullptr;    // (n, Q) positive variance of this evaluation
     double *s_sig = nullptr;    // (n, Q) d softplus / d raw (sigmoid) of this evaluation, 1 if positive domain
     double *gx_mu = nullptr, *gx_s = nullptr;  // (n, Q) positive-domain gradients

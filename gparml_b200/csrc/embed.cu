@@ -220,6 +220,8 @@ __global__ void __launch_bounds__(256) embed_finish_kernel(const double *__restr
     grad_latest[n * Q + idx] = -(gs * s_sig[idx]);
 }
 
+int gp_launch_embed_psi2_f32(gparml_ctx *c, const int *m_bounds, int splits, double *partial);
+
 template <int Q>
 static int launch_q(gparml_ctx *c)
 {
@@ -263,9 +265,13 @@ static int launch_q(gparml_ctx *c)
     p.psi1_part = c->ws + (size_t)splits * c->n * W;
     embed_psi1_kernel<Q><<<(unsigned)((c->n + 127) / 128), 128, smem, c->stream>>>(p);
     GP_LAUNCH_CHECK(c);
-    dim3 grid((unsigned)ntiles, splits);
-    embed_psi2_kernel<Q><<<grid, EMB_THREADS, smem, c->stream>>>(p);
-    GP_LAUNCH_CHECK(c);
+    if (c->flags & GPARML_FLAG_FP32_MAP) {               // opt-in fp32 evaluation of the Psi2 part
+        GP_TRY(gp_launch_embed_psi2_f32(c, p.m_bounds, splits, p.partial));
+    } else {
+        dim3 grid((unsigned)ntiles, splits);
+        embed_psi2_kernel<Q><<<grid, EMB_THREADS, smem, c->stream>>>(p);
+        GP_LAUNCH_CHECK(c);
+    }
     const int64_t total = c->n * Q;
     embed_finish_kernel<<<(int)((total + 255) / 256), 256, 0, c->stream>>>(c->ws, splits, p.psi1_part, c->n, Q, gp_rec_len(Q), c->rec1,
                                                                            c->rec2, c->s_pos, c->s_sig, c->gx_mu, c->gx_s,

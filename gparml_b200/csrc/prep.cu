@@ -66,6 +66,8 @@ struct PrepParams {
     int mode;  // 0 = unconstrained variance (softplus), 1 = positive as given, 2 = fixed embeddings (S as given, KL = 0)
     const GlobalsDev *glob;
     double *rec1, *rec2, *s_pos, *s_sig;
+    float *rec2f;           // optional fp32 copy of the Psi2 records (centred means), RF floats per point
+    int RF;
     double *kl_partials;    // [gridDim.x][2]: (kl sum, number of exactly-zero variances)
     int *status;
 };
@@ -86,6 +88,8 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_points_kernel(PrepParams p)
     __shared__ GlobalsDev g;
     const int Q = p.Q, R = p.R, tid = threadIdx.x;
     double *r1t = psm, *r2t = r1t + PREP_TP * R, *d1s = r2t + PREP_TP * R, *d2s = d1s + PREP_TP * Q;
+    float *rft = reinterpret_cast<float *>(d2s + PREP_TP * Q);     // [TP][RF], only with rec2f
+    const int RF = p.RF;
     if (tid == 0) g = *p.glob;
     __syncthreads();
     double kl = 0.0, zeros = 0.0;
@@ -115,6 +119,10 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_points_kernel(PrepParams p)
             double *r1 = r1t + pt * R, *r2 = r2t + pt * R;
             r1[2 * q] = mu;  r1[2 * q + 1] = a;  r1[2 * Q + q] = al * S * a;
             r2[2 * q] = mu;  r2[2 * q + 1] = w;  r2[2 * Q + q] = al * S * w;
+            if (p.rec2f) {
+                float *rf = rft + pt * RF;
+                rf[2 * q] = (float)(mu - g.center[q]);  rf[2 * q + 1] = (float)w;  rf[2 * Q + q] = (float)(al * S * w);
+            }
             d1s[e] = den1;
             d2s[e] = den2;
             p.s_pos[gi] = S;
@@ -131,8 +139,17 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_points_kernel(PrepParams p)
             r1t[pt * R + 3 * Q] = g.log_sf2 - 0.5 * log(prod1);
             r2t[pt * R + 3 * Q] = 2.0 * g.log_sf2 - 0.5 * log(prod2);
             if (3 * Q + 1 < R) { r1t[pt * R + 3 * Q + 1] = 0.0; r2t[pt * R + 3 * Q + 1] = 0.0; }
+            if (p.rec2f) {
+                rft[pt * RF + 3 * Q] = (float)r2t[pt * R + 3 * Q];
+                for (int k = 3 * Q + 1; k < RF; ++k) rft[pt * RF + k] = 0.f;
+            }
         }
         __syncthreads();
+        if (p.rec2f) {
+            float4 *of = reinterpret_cast<float4 *>(p.rec2f + base * RF);
+            const float4 *inf = reinterpret_cast<const float4 *>(rft);
+            for (int e = tid; e < cnt * (RF / 4); e += PREP_THREADS) of[e] = inf[e];
+        }
         double2 *o1 = reinterpret_cast<double2 *>(p.rec1 + base * R), *o2 = reinterpret_cast<double2 *>(p.rec2 + base * R);
         const double2 *i1 = reinterpret_cast<const double2 *>(r1t), *i2 = reinterpret_cast<const double2 *>(r2t);
         for (int e = tid; e < cnt * (R / 2); e += PREP_THREADS) { o1[e] = i1[e]; o2[e] = i2[e]; }
@@ -188,10 +205,13 @@ int gp_launch_prep(gparml_ctx *c)
     p.s_pos = c->s_pos;
     p.s_sig = c->s_sig;
     p.status = c->d_status;
+    p.rec2f = (c->flags & GPARML_FLAG_FP32_MAP) ? c->rec2f : nullptr;
+    p.RF = gp_rec_len_f32(c->Q);
     int blocks = (int)((c->n + PREP_TP - 1) / PREP_TP);
     if (blocks > c->sm_count * 8) blocks = c->sm_count * 8;
     if (blocks < 1) blocks = 1;
-    const size_t smem = ((size_t)2 * PREP_TP * p.R + (size_t)2 * PREP_TP * p.Q) * sizeof(double);
+    const size_t smem = ((size_t)2 * PREP_TP * p.R + (size_t)2 * PREP_TP * p.Q) * sizeof(double) +
+                        (p.rec2f ? (size_t)PREP_TP * p.RF * sizeof(float) : 0);
     GP_CUDA(cudaFuncSetAttribute(prep_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GP_TRY(gp_ensure_ws(c, (size_t)blocks * 2 * sizeof(double)));
     p.kl_partials = c->ws;

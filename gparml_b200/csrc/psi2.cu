@@ -234,8 +234,11 @@ static int launch_q(gparml_ctx *c)
     return GPARML_OK;
 }
 
+int gp_launch_psi2_stats_f32(gparml_ctx *c);
+
 int gp_launch_psi2_stats(gparml_ctx *c)
 {
+    if (c->flags & GPARML_FLAG_FP32_MAP) return gp_launch_psi2_stats_f32(c);      // opt-in fp32 evaluation
     switch (c->Q) {
 #define CASE_Q(q) case q: return launch_q<q>(c);
         CASE_Q(1) CASE_Q(2) CASE_Q(3) CASE_Q(4) CASE_Q(5) CASE_Q(6) CASE_Q(7) CASE_Q(8)

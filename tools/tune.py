@@ -19,7 +19,7 @@ CSRC = os.path.join(ROOT, "gparml_b200", "csrc")
 VDIR = os.path.join(ROOT, "gparml_b200", "variants")
 NVCC = "/usr/local/cuda/bin/nvcc"
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
-ALL = ["capi.cu", "prep.cu", "psi1.cu", "psi2.cu", "embed.cu", "global_step.cu", "global_step_large.cu", "misc.cu"]
+ALL = ["capi.cu", "prep.cu", "psi1.cu", "psi2.cu", "psi2_f32.cu", "embed.cu", "global_step.cu", "global_step_large.cu", "misc.cu"]
 
 # name -> {source: [defines]}
 VARIANTS = {
@@ -83,7 +83,7 @@ def one(lib, n):
     from gparml_b200.synthetic import CONFIGS, make_problem
     k = CONFIGS["c3"]
     p = make_problem(n, k["M"], k["Q"], k["D"], seed=3, with_direction=True)
-    c = ShardContext(k["M"], k["Q"], k["D"], n)
+    c = ShardContext(k["M"], k["Q"], k["D"], n, fp32_map=os.environ.get("GPARML_TUNE_FP32") == "1")
     c.upload_shard(p["Y"], p["X_mu"], p["X_S"])
     c.enable_timing(True)
     acc = {}
