@@ -303,10 +303,17 @@ def main():
         return F, g
 
     def evaluation_e2e():
+        # host buffers in, host buffers out: the Y upload overlaps prep_points + psi2_stats and the
+        # gradient download overlaps embed_grads (chunked) inside the library
         ctx.upload_shard_ptrs(Yp.data_ptr(), MUp.data_ptr(), Sp.data_ptr(), n_loc)
-        F, g = evaluation()
+        ctx.set_globals(Z, sf2, alpha, beta)
+        ctx.set_step(step_size)
+        ctx.statistics()
+        if world > 1:
+            dist.all_reduce(stats_view, op=dist.ReduceOp.SUM)
+        F, g = ctx.global_step()
         if not fixed:
-            ctx.download_into_ptr(_lib.A_GRAD_LATEST, GLp.data_ptr(), 2 * n_loc * Q)
+            ctx.embedding_grads_into(GLp.data_ptr(), chunks=4)
         return F, g
 
     def timed(fn, steps, collect_phases=False):

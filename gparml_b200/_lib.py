@@ -60,6 +60,7 @@ PROTOTYPES = {
     "gparml_global_step": (ctypes.c_int, [_vp, _vp, _vp]),
     "gparml_update_global_statistics": (ctypes.c_int, [_vp]),
     "gparml_embedding_grads": (ctypes.c_int, [_vp]),
+    "gparml_embedding_grads_download": (ctypes.c_int, [_vp, _vp, ctypes.c_int]),
     "gparml_kmm_derivative": (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
     "gparml_grad_contract": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gparml_stats_add_peer": (ctypes.c_int, [_vp, _vp, ctypes.c_double]),

@@ -88,6 +88,11 @@ extern "C" int gparml_create(gparml_ctx **out, int device, int M, int Q, int D, 
     auto fail = [&](int code) { gparml_destroy(c); return code; };
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { gp_set_error("stream create failed"); return fail(GPARML_ERR_CUDA); }
     c->stream = c->own_stream;
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_y, cudaEventDisableTiming) != cudaSuccess) { gp_set_error("copy stream create failed"); return fail(GPARML_ERR_CUDA); }
+    for (int i = 0; i < 8; ++i)
+        if (cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming) != cudaSuccess) { gp_set_error("event create failed"); return fail(GPARML_ERR_CUDA); }
     const size_t MM = (size_t)M * M;
 #define A_(ptr, count) if ((r = dev_alloc(&(ptr), (count))) != GPARML_OK) return fail(r)
     A_(c->Z, (size_t)M * Q);
@@ -97,6 +102,7 @@ extern "C" int gparml_create(gparml_ctx **out, int device, int M, int Q, int D, 
     A_(c->pair_g, (size_t)c->L.P);
     A_(c->stats, (size_t)c->L.count);
     A_(c->red_ws, 4096);
+    A_(c->d_yyt, 1100);
     A_(c->d_status, 1);
     A_(c->kmm, MM); A_(c->kmm_inv, MM); A_(c->a_inv, MM);
     A_(c->g_k, MM); A_(c->g_2, MM); A_(c->g_1, (size_t)M * D); A_(c->c_mat, (size_t)M * D);
@@ -119,9 +125,14 @@ extern "C" int gparml_destroy(gparml_ctx *c)
     void *ptrs[] = {c->Y, c->x_mu, c->x_s, c->grad_d, c->grad_latest, c->grad_new, c->grad_old, c->rec1, c->rec2, c->s_pos, c->s_sig,
                     c->gx_mu, c->gx_s, c->psi1, c->Z, c->d_glob, c->pair_idx, c->pair_lk, c->pair_g, c->stats, c->ws, c->red_ws,
                     c->d_status, c->kmm, c->kmm_inv, c->a_inv, c->g_k, c->g_1, c->g_2, c->scratch_x, c->scratch_w, c->c_mat,
-                    c->glob_out, c->named_tmp, c->psi2_full, c->gsl_ws, c->rec2f};
+                    c->glob_out, c->named_tmp, c->psi2_full, c->gsl_ws, c->rec2f, c->d_yyt};
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 8; ++i) if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
+    if (c->ev_main) cudaEventDestroy(c->ev_main);
+    if (c->ev_y) cudaEventDestroy(c->ev_y);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return GPARML_OK;
@@ -192,10 +203,15 @@ extern "C" int gparml_upload_shard(gparml_ctx *c, const double *Y, const double 
     if (domain != GPARML_VARIANCE_UNCONSTRAINED && domain != GPARML_VARIANCE_POSITIVE) { gp_set_error("upload_shard: bad variance domain %d", domain); return GPARML_ERR_ARG; }
     GP_TRY(ensure_shard_capacity(c, n));
     const size_t nq = (size_t)n * c->Q;
+    // Y is needed only by psi1_stats / the Psi1 part of embed_grads: it travels on the copy stream
+    // (ordered behind everything already queued on the main stream, which may still read the old Y)
+    // and overlaps prep_points + psi2_stats; X_mu / X_S go first on the main stream.
+    GP_CUDA(cudaEventRecord(c->ev_main, c->stream));
+    GP_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
     if (n > 0) {
-        GP_CUDA(cudaMemcpyAsync(c->Y, Y, (size_t)n * c->D * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         GP_CUDA(cudaMemcpyAsync(c->x_mu, X_mu, nq * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         GP_CUDA(cudaMemcpyAsync(c->x_s, X_S, nq * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        GP_CUDA(cudaMemcpyAsync(c->Y, Y, (size_t)n * c->D * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
     }
     if (n != c->n) {
         c->have_dir = false;
@@ -205,7 +221,17 @@ extern "C" int gparml_upload_shard(gparml_ctx *c, const double *Y, const double 
     c->variance_domain = domain;
     c->have_shard = true;
     c->have_prep = c->have_stats = c->have_global_step = false;
-    GP_TRY(gp_launch_yyt(c, &c->yyt));
+    GP_TRY(gp_launch_yyt(c, c->copy_stream));
+    GP_CUDA(cudaEventRecord(c->ev_y, c->copy_stream));
+    // pageable host arrays: the async copies above are staged before they return, so the caller may
+    // reuse its buffers; pinned arrays must stay valid until the next synchronising call.
+    return GPARML_OK;
+}
+
+// make the main stream wait for the Y upload (and its sum of squares)
+static int wait_y(gparml_ctx *c)
+{
+    GP_CUDA(cudaStreamWaitEvent(c->stream, c->ev_y, 0));
     return GPARML_OK;
 }
 
@@ -285,9 +311,11 @@ extern "C" int gparml_statistics(gparml_ctx *c)
     GP_TRY(gp_launch_prep(c));          // always: it also rewrites the header of the packed buffer
     c->have_prep = true;
     GP_TRY(record(c, 1));
-    GP_TRY(gp_launch_psi1_stats(c));
+    GP_TRY(gp_launch_psi2_stats(c));    // needs only X: runs while Y may still be arriving on the copy stream
     GP_TRY(record(c, 2));
-    GP_TRY(gp_launch_psi2_stats(c));
+    GP_TRY(wait_y(c));
+    GP_TRY(gp_launch_set_yyt(c));
+    GP_TRY(gp_launch_psi1_stats(c));
     GP_TRY(record(c, 3));
     c->have_stats = true;
     c->have_global_step = false;
@@ -353,9 +381,40 @@ extern "C" int gparml_embedding_grads(gparml_ctx *c)
     if (c->flags & GPARML_FLAG_FIXED_EMBEDDINGS) { gp_set_error("embedding_grads: context has fixed embeddings"); return GPARML_ERR_STATE; }
     if (!c->have_global_step) { gp_set_error("embedding_grads: global_step first"); return GPARML_ERR_STATE; }
     GP_TRY(prep_if_needed(c));
+    GP_TRY(wait_y(c));
     GP_TRY(record(c, 6));
     GP_TRY(gp_launch_embed_grads(c));
     GP_TRY(record(c, 7));
+    return GPARML_OK;
+}
+
+// embedding_grads + download of GRAD_LATEST in one call, in `chunks` point ranges: the
+// device-to-host copy of range k (copy stream) overlaps the kernels of range k + 1.
+extern "C" int gparml_embedding_grads_download(gparml_ctx *c, double *host_grad_latest, int chunks)
+{
+    CHECK_CTX(c);
+    if (c->flags & GPARML_FLAG_FIXED_EMBEDDINGS) { gp_set_error("embedding_grads: context has fixed embeddings"); return GPARML_ERR_STATE; }
+    if (!c->have_global_step) { gp_set_error("embedding_grads: global_step first"); return GPARML_ERR_STATE; }
+    if (!host_grad_latest) { gp_set_error("embedding_grads_download: null destination"); return GPARML_ERR_ARG; }
+    if (chunks < 1) chunks = 1;
+    if (chunks > 8) chunks = 8;
+    GP_TRY(prep_if_needed(c));
+    GP_TRY(wait_y(c));
+    GP_TRY(record(c, 6));
+    const int64_t n = c->n, Q = c->Q;
+    for (int k = 0; k < chunks; ++k) {
+        const int64_t lo = n * k / chunks, hi = n * (k + 1) / chunks;
+        if (hi <= lo) continue;
+        GP_TRY(gp_launch_embed_grads_range(c, lo, hi));
+        GP_CUDA(cudaEventRecord(c->ev_chunk[k], c->stream));
+        GP_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_chunk[k], 0));
+        const size_t bytes = (size_t)(hi - lo) * Q * sizeof(double);
+        GP_CUDA(cudaMemcpyAsync(host_grad_latest + lo * Q, c->grad_latest + lo * Q, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+        GP_CUDA(cudaMemcpyAsync(host_grad_latest + (n + lo) * Q, c->grad_latest + (n + lo) * Q, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+    }
+    GP_TRY(record(c, 7));
+    GP_CUDA(cudaStreamSynchronize(c->copy_stream));
+    GP_CUDA(cudaStreamSynchronize(c->stream));
     return GPARML_OK;
 }
 
@@ -410,6 +469,7 @@ extern "C" int gparml_array_device_ptr(gparml_ctx *c, int id, void **out)
 extern "C" int gparml_download(gparml_ctx *c, int id, double *dst, int64_t count)
 {
     CHECK_CTX(c);
+    GP_TRY(wait_y(c));
     if (id == GPARML_A_PSI1) {
         GP_TRY(prep_if_needed(c));
         if (!c->psi1) GP_TRY(dev_alloc(&c->psi1, (size_t)c->n * c->M));
@@ -558,7 +618,8 @@ extern "C" int gparml_phase_times(gparml_ctx *c, double *out5)
     CHECK_CTX(c);
     if (!c->timing) { gp_set_error("phase_times: timing not enabled"); return GPARML_ERR_STATE; }
     GP_CUDA(cudaStreamSynchronize(c->stream));
-    const int pairs[5][2] = {{0, 1}, {1, 2}, {2, 3}, {4, 5}, {6, 7}};
+    // out order: prep_points, psi1_stats, psi2_stats, global_step, embed_grads (psi2 runs before psi1)
+    const int pairs[5][2] = {{0, 1}, {2, 3}, {1, 2}, {4, 5}, {6, 7}};
     for (int i = 0; i < 5; ++i) {
         float ms = 0.f;
         cudaError_t e = cudaEventElapsedTime(&ms, c->ev[pairs[i][0]], c->ev[pairs[i][1]]);

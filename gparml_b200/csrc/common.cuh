@@ -117,7 +117,10 @@ struct gparml_ctx {
     double *s_sig = nullptr;    // (n, Q) d softplus / d raw (sigmoid) of this evaluation, 1 if positive domain
     double *gx_mu = nullptr, *gx_s = nullptr;  // (n, Q) positive-domain gradients
     double *psi1 = nullptr;     // (n, M) on demand
-    double yyt = 0.0;           // sum_n y_n . y_n of the shard (host copy)
+    double *d_yyt = nullptr;    // [0] = sum_n y_n . y_n of the shard, [1..] partials of its reduction
+    // second stream: the Y upload (needed only by psi1_stats) and the gradient download overlap compute
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_y = nullptr, ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     // globals
     double *Z = nullptr;        // (M, Q)
@@ -156,7 +159,9 @@ struct gparml_ctx {
 int gp_ensure_ws(gparml_ctx *c, size_t bytes);
 
 // kernels' host launchers (each returns GPARML_* codes)
-int gp_launch_yyt(gparml_ctx *c, double *host_out);
+int gp_launch_yyt(gparml_ctx *c, cudaStream_t s);          // -> c->d_yyt[0], on stream s, no host sync
+int gp_launch_set_yyt(gparml_ctx *c);                      // stats[ST_YYT] = d_yyt[0]
+int gp_launch_embed_grads_range(gparml_ctx *c, int64_t i_begin, int64_t i_end);
 int gp_launch_prep(gparml_ctx *c);
 int gp_launch_pair_table(gparml_ctx *c);
 int gp_launch_psi1_stats(gparml_ctx *c);

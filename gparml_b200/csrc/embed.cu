@@ -49,7 +49,8 @@
 struct EmbedParams {
     const double *rec1, *rec2, *Y, *Z, *G1;
     const double2 *pair_g;
-    int64_t n;
+    int64_t n;           // points in the shard (stride of the partial buffers)
+    int64_t i0, i1;      // this launch covers points [i0, i1)
     int M, D;
     int m_bounds[EMB_MAX_SPLITS + 1];
     double *partial;     // [splits][n][2Q + 1]  (AM, AS, AH)
@@ -76,9 +77,9 @@ embed_psi2_kernel(EmbedParams p)
     gp_exp_load_table(exp_tab);
     __syncthreads();
 
-    int64_t i = (int64_t)blockIdx.x * EMB_THREADS + tid;
-    const bool valid = i < p.n;
-    if (!valid) i = p.n - 1;                             // compute on a real record, never store
+    int64_t i = p.i0 + (int64_t)blockIdx.x * EMB_THREADS + tid;
+    const bool valid = i < p.i1;
+    if (!valid) i = p.i1 - 1;                            // compute on a real record, never store
     const double2 *r2 = reinterpret_cast<const double2 *>(p.rec2 + i * R);
     const double lc2 = p.rec2[i * R + 3 * Q];
     double sw[Q], sdm[Q], u[Q], am[Q], as[Q];
@@ -143,8 +144,8 @@ __global__ void __launch_bounds__(128) embed_psi1_kernel(EmbedParams p)
     for (int idx = tid; idx < M * Q; idx += 128) zs[idx] = p.Z[idx];
     gp_exp_load_table(exp_tab);
     __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * 128 + tid;
-    if (i >= p.n) return;
+    const int64_t i = p.i0 + (int64_t)blockIdx.x * 128 + tid;
+    if (i >= p.i1) return;
     const double2 *r1 = reinterpret_cast<const double2 *>(p.rec1 + i * R);
     const double lc1 = p.rec1[i * R + 3 * Q];
     const double *y = p.Y + i * p.D;
@@ -191,14 +192,15 @@ __global__ void __launch_bounds__(128) embed_psi1_kernel(EmbedParams p)
 // Combine the split partials and the Psi1 part, add the KL terms (partial_terms.py:385,418),
 // apply the softplus chain and the sign flip (local_MapReduce.py:357-360).
 __global__ void __launch_bounds__(256) embed_finish_kernel(const double *__restrict__ partial, int splits,
-                                                           const double *__restrict__ psi1_part, int64_t n, int Q, int R,
+                                                           const double *__restrict__ psi1_part, int64_t n, int64_t i0, int64_t cnt, int Q, int R,
                                                            const double *__restrict__ rec1, const double *__restrict__ rec2,
                                                            const double *__restrict__ s_pos, const double *__restrict__ s_sig,
                                                            double *__restrict__ gx_mu, double *__restrict__ gx_s,
                                                            double *__restrict__ grad_latest)
 {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n * Q) return;
+    const int64_t loc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (loc >= cnt * Q) return;
+    const int64_t idx = i0 * Q + loc;
     const int64_t i = idx / Q;
     const int q = (int)(idx % Q);
     const int W = 2 * Q + 1;
@@ -220,18 +222,19 @@ __global__ void __launch_bounds__(256) embed_finish_kernel(const double *__restr
     grad_latest[n * Q + idx] = -(gs * s_sig[idx]);
 }
 
-int gp_launch_embed_psi2_f32(gparml_ctx *c, const int *m_bounds, int splits, double *partial);
+int gp_launch_embed_psi2_f32(gparml_ctx *c, const int *m_bounds, int splits, double *partial, int64_t i0, int64_t i1);
 
 template <int Q>
-static int launch_q(gparml_ctx *c)
+static int launch_q(gparml_ctx *c, int64_t i0, int64_t i1)
 {
+    const int64_t cnt = i1 - i0;
     const size_t smem = (size_t)c->M * Q * sizeof(double);
     GP_CUDA(cudaFuncSetAttribute(embed_psi2_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GP_CUDA(cudaFuncSetAttribute(embed_psi1_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
     GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, embed_psi2_kernel<Q>, EMB_THREADS, smem));
     if (occ < 1) occ = 1;
-    const int64_t ntiles = (c->n + EMB_THREADS - 1) / EMB_THREADS;
+    const int64_t ntiles = (cnt + EMB_THREADS - 1) / EMB_THREADS;
     const int64_t slots = (int64_t)c->sm_count * occ;
     int max_splits = c->M < EMB_MAX_SPLITS ? c->M : EMB_MAX_SPLITS;
     int best = 1;
@@ -246,7 +249,7 @@ static int launch_q(gparml_ctx *c)
     const int splits = best;
     EmbedParams p;
     p.rec1 = c->rec1; p.rec2 = c->rec2; p.Y = c->Y; p.Z = c->Z; p.G1 = c->g_1; p.pair_g = c->pair_g;
-    p.n = c->n; p.M = c->M; p.D = c->D;
+    p.n = c->n; p.i0 = i0; p.i1 = i1; p.M = c->M; p.D = c->D;
     // split the m range so that every split owns about P / splits pairs (row m has M - m pairs)
     const double P = (double)c->L.P;
     p.m_bounds[0] = 0;
@@ -263,28 +266,30 @@ static int launch_q(gparml_ctx *c)
     GP_TRY(gp_ensure_ws(c, (size_t)(splits + 1) * c->n * W * sizeof(double)));
     p.partial = c->ws;
     p.psi1_part = c->ws + (size_t)splits * c->n * W;
-    embed_psi1_kernel<Q><<<(unsigned)((c->n + 127) / 128), 128, smem, c->stream>>>(p);
+    embed_psi1_kernel<Q><<<(unsigned)((cnt + 127) / 128), 128, smem, c->stream>>>(p);
     GP_LAUNCH_CHECK(c);
     if (c->flags & GPARML_FLAG_FP32_MAP) {               // opt-in fp32 evaluation of the Psi2 part
-        GP_TRY(gp_launch_embed_psi2_f32(c, p.m_bounds, splits, p.partial));
+        GP_TRY(gp_launch_embed_psi2_f32(c, p.m_bounds, splits, p.partial, i0, i1));
     } else {
         dim3 grid((unsigned)ntiles, splits);
         embed_psi2_kernel<Q><<<grid, EMB_THREADS, smem, c->stream>>>(p);
         GP_LAUNCH_CHECK(c);
     }
-    const int64_t total = c->n * Q;
-    embed_finish_kernel<<<(int)((total + 255) / 256), 256, 0, c->stream>>>(c->ws, splits, p.psi1_part, c->n, Q, gp_rec_len(Q), c->rec1,
+    const int64_t total = cnt * Q;
+    embed_finish_kernel<<<(int)((total + 255) / 256), 256, 0, c->stream>>>(c->ws, splits, p.psi1_part, c->n, i0, cnt, Q, gp_rec_len(Q), c->rec1,
                                                                            c->rec2, c->s_pos, c->s_sig, c->gx_mu, c->gx_s,
                                                                            c->grad_latest);
     GP_LAUNCH_CHECK(c);
     return GPARML_OK;
 }
 
-int gp_launch_embed_grads(gparml_ctx *c)
+int gp_launch_embed_grads(gparml_ctx *c) { return gp_launch_embed_grads_range(c, 0, c->n); }
+
+int gp_launch_embed_grads_range(gparml_ctx *c, int64_t i0, int64_t i1)
 {
-    if (c->n == 0) return GPARML_OK;
+    if (i1 <= i0) return GPARML_OK;
     switch (c->Q) {
-#define CASE_Q(q) case q: return launch_q<q>(c);
+#define CASE_Q(q) case q: return launch_q<q>(c, i0, i1);
         CASE_Q(1) CASE_Q(2) CASE_Q(3) CASE_Q(4) CASE_Q(5) CASE_Q(6) CASE_Q(7) CASE_Q(8)
         CASE_Q(9) CASE_Q(10) CASE_Q(11) CASE_Q(12) CASE_Q(13) CASE_Q(14) CASE_Q(15) CASE_Q(16)
 #undef CASE_Q

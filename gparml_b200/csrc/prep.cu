@@ -40,18 +40,27 @@ __global__ void __launch_bounds__(256) final_sum_kernel(const double *__restrict
     if (threadIdx.x == 0) dst[0] = scale * acc;
 }
 
-int gp_launch_yyt(gparml_ctx *c, double *host_out)
+// sum_n y_n . y_n -> d_yyt[0] on stream s (the copy stream right behind the Y upload); the partials
+// live in d_yyt[1..] so that the reduction cannot collide with red_ws users on the main stream.
+int gp_launch_yyt(gparml_ctx *c, cudaStream_t s)
 {
     const int64_t count = c->n * c->D;
     int blocks = (int)((count + 256 * 8 - 1) / (256 * 8));
     if (blocks < 1) blocks = 1;
     if (blocks > 1024) blocks = 1024;
-    sumsq_kernel<<<blocks, 256, 0, c->stream>>>(c->Y, count, c->red_ws);
+    sumsq_kernel<<<blocks, 256, 0, s>>>(c->Y, count, c->d_yyt + 1);
     GP_LAUNCH_CHECK(c);
-    final_sum_kernel<<<1, 256, 0, c->stream>>>(c->red_ws, blocks, 1.0, c->red_ws + 2048);
+    final_sum_kernel<<<1, 256, 0, s>>>(c->d_yyt + 1, blocks, 1.0, c->d_yyt);
     GP_LAUNCH_CHECK(c);
-    GP_CUDA(cudaMemcpyAsync(host_out, c->red_ws + 2048, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    GP_CUDA(cudaStreamSynchronize(c->stream));
+    return GPARML_OK;
+}
+
+__global__ void set_yyt_kernel(const double *__restrict__ d_yyt, double *__restrict__ stats) { stats[ST_YYT] = d_yyt[0]; }
+
+int gp_launch_set_yyt(gparml_ctx *c)
+{
+    set_yyt_kernel<<<1, 1, 0, c->stream>>>(c->d_yyt, c->stats);
+    GP_LAUNCH_CHECK(c);
     return GPARML_OK;
 }
 
@@ -166,7 +175,7 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_points_kernel(PrepParams p)
 
 // Final KL + header of the packed statistics buffer.  One block.
 __global__ void __launch_bounds__(256) prep_finish_kernel(const double *__restrict__ kl_partials, int k, double n_local, int Q, int mode,
-                                                          double yyt, double sf2, double *__restrict__ stats)
+                                                          double sf2, double *__restrict__ stats)
 {
     __shared__ double sh[33];
     double a = 0.0, z = 0.0;
@@ -181,8 +190,7 @@ __global__ void __launch_bounds__(256) prep_finish_kernel(const double *__restri
         if (mode == 2 || z == n_local * (double)Q) kl = 0.0;        // all variances zero: fixed embeddings (partial_terms.py:86-87)
         else if (z > 0.0) kl = INFINITY;                              // -log(0) for some but not all entries, as numpy would give
         else kl = a;
-        stats[ST_YYT] = yyt;
-        stats[ST_PSI0] = sf2 * n_local;                               // partial_terms.py:81
+        stats[ST_PSI0] = sf2 * n_local;                               // partial_terms.py:81 (ST_YYT: set_yyt_kernel)
         stats[ST_KL] = kl;
         stats[ST_NLOCAL] = n_local;                                   // partial_terms.py:318-320
     }
@@ -217,7 +225,7 @@ int gp_launch_prep(gparml_ctx *c)
     p.kl_partials = c->ws;
     prep_points_kernel<<<blocks, PREP_THREADS, smem, c->stream>>>(p);
     GP_LAUNCH_CHECK(c);
-    prep_finish_kernel<<<1, 256, 0, c->stream>>>(c->ws, blocks, (double)c->n, c->Q, p.mode, c->yyt, c->h_glob.sf2, c->stats);
+    prep_finish_kernel<<<1, 256, 0, c->stream>>>(c->ws, blocks, (double)c->n, c->Q, p.mode, c->h_glob.sf2, c->stats);
     GP_LAUNCH_CHECK(c);
     return GPARML_OK;
 }

@@ -205,7 +205,7 @@ struct Embed32Params {
     const double *Z;
     const GlobalsDev *glob;
     const double2 *pair_g;
-    int64_t n;
+    int64_t n, i0, i1;     // shard size (stride of the partial buffer) and the point range of this launch
     int M;
     int m_bounds[EMB32_MAX_SPLITS + 1];
     double *partial;
@@ -219,9 +219,9 @@ __global__ void __launch_bounds__(EMB32_THREADS, 4) embed_psi2_f32_kernel(Embed3
     const int tid = threadIdx.x, M = p.M;
     for (int idx = tid; idx < M * Q; idx += EMB32_THREADS) hzf[idx] = (float)(0.5 * (p.Z[idx] - p.glob->center[idx % Q]));
     __syncthreads();
-    int64_t i = (int64_t)blockIdx.x * EMB32_THREADS + tid;
-    const bool valid = i < p.n;
-    if (!valid) i = p.n - 1;
+    int64_t i = p.i0 + (int64_t)blockIdx.x * EMB32_THREADS + tid;
+    const bool valid = i < p.i1;
+    if (!valid) i = p.i1 - 1;
     const float *rec = p.rec2f + i * RF;
     const float lc2 = rec[3 * Q];
     float sw[Q], mu[Q], sdm[Q], u[Q], amf[Q], asf[Q];
@@ -274,23 +274,23 @@ __global__ void __launch_bounds__(EMB32_THREADS, 4) embed_psi2_f32_kernel(Embed3
 }
 
 template <int Q>
-static int launch_embed_f32(gparml_ctx *c, const int *m_bounds, int splits, double *partial)
+static int launch_embed_f32(gparml_ctx *c, const int *m_bounds, int splits, double *partial, int64_t i0, int64_t i1)
 {
     Embed32Params p;
-    p.rec2f = c->rec2f; p.Z = c->Z; p.glob = c->d_glob; p.pair_g = c->pair_g; p.n = c->n; p.M = c->M; p.partial = partial;
+    p.rec2f = c->rec2f; p.Z = c->Z; p.glob = c->d_glob; p.pair_g = c->pair_g; p.n = c->n; p.i0 = i0; p.i1 = i1; p.M = c->M; p.partial = partial;
     for (int s = 0; s <= splits; ++s) p.m_bounds[s] = m_bounds[s];
     const size_t smem = (size_t)c->M * Q * sizeof(float);
     GP_CUDA(cudaFuncSetAttribute(embed_psi2_f32_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)((c->n + EMB32_THREADS - 1) / EMB32_THREADS), splits);
+    dim3 grid((unsigned)((i1 - i0 + EMB32_THREADS - 1) / EMB32_THREADS), splits);
     embed_psi2_f32_kernel<Q><<<grid, EMB32_THREADS, smem, c->stream>>>(p);
     GP_LAUNCH_CHECK(c);
     return GPARML_OK;
 }
 
-int gp_launch_embed_psi2_f32(gparml_ctx *c, const int *m_bounds, int splits, double *partial)
+int gp_launch_embed_psi2_f32(gparml_ctx *c, const int *m_bounds, int splits, double *partial, int64_t i0, int64_t i1)
 {
     switch (c->Q) {
-#define CASE_Q(q) case q: return launch_embed_f32<q>(c, m_bounds, splits, partial);
+#define CASE_Q(q) case q: return launch_embed_f32<q>(c, m_bounds, splits, partial, i0, i1);
         CASE_Q(1) CASE_Q(2) CASE_Q(3) CASE_Q(4) CASE_Q(5) CASE_Q(6) CASE_Q(7) CASE_Q(8)
         CASE_Q(9) CASE_Q(10) CASE_Q(11) CASE_Q(12) CASE_Q(13) CASE_Q(14) CASE_Q(15) CASE_Q(16)
 #undef CASE_Q

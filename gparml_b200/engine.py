@@ -263,6 +263,16 @@ class ShardContext(object):
     def embedding_grads(self):
         _lib.check(self._lib.gparml_embedding_grads(self._h))
 
+    def embedding_grads_into(self, host_ptr, chunks=4):
+        """embedding_grads + download of grad_latest (2, n, Q) into host memory at ``host_ptr``
+        (e.g. a pinned torch tensor); the copy of one point range overlaps the next range's kernels."""
+        _lib.check(self._lib.gparml_embedding_grads_download(self._h, ctypes.c_void_p(host_ptr), int(chunks)))
+
+    def embedding_grads_numpy(self, chunks=4):
+        out = np.empty((2, self.n_local, self.Q), dtype=np.float64)
+        self.embedding_grads_into(out.ctypes.data, chunks)
+        return out
+
     def grad_latest(self):
         return self.download(_lib.A_GRAD_LATEST, (2, self.n_local, self.Q))
 

@@ -163,6 +163,11 @@ int gparml_update_global_statistics(gparml_ctx *ctx);
 /* grad_X_mu / grad_X_S (partial_terms.py:367-431) with the softplus chain and the
  * sign flip of local_MapReduce.py:357-360; result stays on device (GRAD_LATEST). */
 int gparml_embedding_grads(gparml_ctx *ctx);
+/* The same map followed by the download of GRAD_LATEST (2, n, Q) into caller-owned (ideally
+ * pinned) host memory -- the `.grad_latest.npy` the reference writes (local_MapReduce.py:359-360).
+ * The points are processed in `chunks` ranges (1..8) and the device-to-host copy of one range
+ * overlaps the kernels of the next.  Returns when the host array is complete. */
+int gparml_embedding_grads_download(gparml_ctx *ctx, double *host_grad_latest, int chunks);
 
 /* ---- partial_terms helper surface ------------------------------------------ */
 /* Kmm-side derivative tensors to caller-owned host memory:
