@@ -90,6 +90,7 @@ extern "C" int gparml_create(gparml_ctx **out, int device, int M, int Q, int D, 
     c->stream = c->own_stream;
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_kmm, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_y, cudaEventDisableTiming) != cudaSuccess) { gp_set_error("copy stream create failed"); return fail(GPARML_ERR_CUDA); }
     for (int i = 0; i < 8; ++i)
         if (cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming) != cudaSuccess) { gp_set_error("event create failed"); return fail(GPARML_ERR_CUDA); }
@@ -132,6 +133,7 @@ extern "C" int gparml_destroy(gparml_ctx *c)
     for (int i = 0; i < 8; ++i) if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
     if (c->ev_main) cudaEventDestroy(c->ev_main);
     if (c->ev_y) cudaEventDestroy(c->ev_y);
+    if (c->ev_kmm) cudaEventDestroy(c->ev_kmm);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -232,6 +234,7 @@ extern "C" int gparml_upload_shard(gparml_ctx *c, const double *Y, const double 
 static int wait_y(gparml_ctx *c)
 {
     GP_CUDA(cudaStreamWaitEvent(c->stream, c->ev_y, 0));
+    GP_CUDA(cudaStreamWaitEvent(c->stream, c->ev_kmm, 0));     // and for Kmm / Kmm^-1 of the current globals
     return GPARML_OK;
 }
 
@@ -259,6 +262,13 @@ extern "C" int gparml_set_globals(gparml_ctx *c, const double *Z, double sf2, co
     GP_CUDA(cudaMemcpyAsync(c->Z, Z, (size_t)c->M * c->Q * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     GP_CUDA(cudaMemcpyAsync(c->d_glob, &c->h_glob, sizeof(GlobalsDev), cudaMemcpyHostToDevice, c->stream));
     GP_TRY(gp_launch_pair_table(c));
+    // Kmm, Kmm^-1, log det Kmm depend on the hyper-parameters only (the reference's cache(),
+    // local_MapReduce.py:383-394): computed now on the side stream, concurrently with the
+    // statistics map, and joined by global_step / update_global_statistics through ev_kmm.
+    GP_CUDA(cudaEventRecord(c->ev_main, c->stream));
+    GP_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
+    GP_TRY(gp_launch_global_step(c, true, c->copy_stream));
+    GP_CUDA(cudaEventRecord(c->ev_kmm, c->copy_stream));
     c->have_globals = true;
     c->have_prep = c->have_stats = c->have_global_step = false;
     return GPARML_OK;
@@ -355,7 +365,7 @@ extern "C" int gparml_update_global_statistics(gparml_ctx *c)
 {
     CHECK_CTX(c);
     if (!c->have_globals) { gp_set_error("update_global_statistics: set_globals first"); return GPARML_ERR_STATE; }
-    GP_TRY(gp_launch_global_step(c, true));
+    GP_CUDA(cudaStreamWaitEvent(c->stream, c->ev_kmm, 0));     // launched by set_globals on the side stream
     return check_status(c, true);
 }
 
@@ -363,8 +373,9 @@ extern "C" int gparml_global_step(gparml_ctx *c, double *F, double *grad)
 {
     CHECK_CTX(c);
     if (!c->have_globals) { gp_set_error("global_step: set_globals first"); return GPARML_ERR_STATE; }
+    GP_CUDA(cudaStreamWaitEvent(c->stream, c->ev_kmm, 0));     // Kmm^-1 from the side stream
     GP_TRY(record(c, 4));
-    GP_TRY(gp_launch_global_step(c, false));
+    GP_TRY(gp_launch_global_step(c, false, c->stream));
     GP_TRY(record(c, 5));
     GP_TRY(check_status(c, true));
     c->have_global_step = true;
@@ -649,6 +660,7 @@ extern "C" int gparml_kmm_derivative(gparml_ctx *c, int which, double *out)
     CHECK_CTX(c);
     if (!c->have_globals || !out || which < 0 || which > 2) { gp_set_error("kmm_derivative: set_globals first / bad args"); return GPARML_ERR_ARG; }
     GP_TRY(ensure_named_tmp(c));
+    GP_CUDA(cudaStreamWaitEvent(c->stream, c->ev_kmm, 0));
     const size_t total = which == 2 ? (size_t)c->M * c->M : (size_t)c->M * c->M * c->Q;
     GP_TRY(gp_launch_kmm_deriv(c, which, c->named_tmp));
     GP_TRY(d2h(c, out, c->named_tmp, total));

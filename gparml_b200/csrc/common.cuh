@@ -120,6 +120,7 @@ struct gparml_ctx {
     double *d_yyt = nullptr;    // [0] = sum_n y_n . y_n of the shard, [1..] partials of its reduction
     // second stream: the Y upload (needed only by psi1_stats) and the gradient download overlap compute
     cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_kmm = nullptr;      // Kmm / Kmm^-1 of the current globals are ready (side stream)
     cudaEvent_t ev_main = nullptr, ev_y = nullptr, ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     // globals
@@ -167,7 +168,7 @@ int gp_launch_pair_table(gparml_ctx *c);
 int gp_launch_psi1_stats(gparml_ctx *c);
 int gp_launch_psi2_stats(gparml_ctx *c);
 int gp_launch_psi1_matrix(gparml_ctx *c);
-int gp_launch_global_step(gparml_ctx *c, bool kmm_only);
+int gp_launch_global_step(gparml_ctx *c, bool kmm_only, cudaStream_t s);
 int gp_launch_embed_grads(gparml_ctx *c);
 int gp_launch_expand(gparml_ctx *c, double *dev_out, int which);
 int gp_launch_compact(gparml_ctx *c, const double *dev_full_psi2, const double *dev_d2z, const double *dev_d2a);

@@ -63,8 +63,20 @@ struct EmbedParams {
 #define EMB_EXP(x) gp_exp((x), exp_tab)
 #endif
 
+// points per thread and resident CTAs the register budget is tuned for
+#ifdef EMB_POINTS
+template <int Q> struct EmbCfg { static constexpr int NP = EMB_POINTS; static constexpr int MINB = EMB_MINB_LOWQ; };
+#else
+// B200, Q = 10, N = 250k (tools/tune.py): 1 point / 4 CTAs 6.91 ms, 2 points / 2 CTAs 6.79 ms
+// (shared-memory wavefronts per FP64 instruction halve); 3 points no longer fit the registers.
+template <int Q> struct EmbCfg {
+    static constexpr int NP = (Q <= 10) ? 2 : 1;
+    static constexpr int MINB = (Q <= 10) ? ((Q <= 4) ? 4 : 2) : ((Q <= 13) ? 2 : 1);
+};
+#endif
+
 template <int Q>
-__global__ void __launch_bounds__(EMB_THREADS, (Q <= 10) ? EMB_MINB_LOWQ : ((Q <= 13) ? 2 : 1))
+__global__ void __launch_bounds__(EMB_THREADS, EmbCfg<Q>::MINB)
 embed_psi2_kernel(EmbedParams p)
 {
     constexpr int R = (3 * Q + 2) & ~1;
@@ -77,18 +89,26 @@ embed_psi2_kernel(EmbedParams p)
     gp_exp_load_table(exp_tab);
     __syncthreads();
 
-    int64_t i = p.i0 + (int64_t)blockIdx.x * EMB_THREADS + tid;
-    const bool valid = i < p.i1;
-    if (!valid) i = p.i1 - 1;                            // compute on a real record, never store
-    const double2 *r2 = reinterpret_cast<const double2 *>(p.rec2 + i * R);
-    const double lc2 = p.rec2[i * R + 3 * Q];
-    double sw[Q], sdm[Q], u[Q], am[Q], as[Q];
-    double ah = 0.0;
+    // NP points per thread (register blocking: every Z/2 and pair read feeds NP points)
+    constexpr int NP = EmbCfg<Q>::NP;
+    int64_t i[NP];
+    bool valid[NP];
+    const double2 *r2[NP];
+    double lc2[NP], sw[NP][Q], sdm[NP][Q], u[NP][Q], am[NP][Q], as[NP][Q], ah[NP];
 #pragma unroll
-    for (int q = 0; q < Q; ++q) {
-        sw[q] = sqrt(r2[q].y);
-        am[q] = 0.0;
-        as[q] = 0.0;
+    for (int v = 0; v < NP; ++v) {
+        i[v] = p.i0 + ((int64_t)blockIdx.x * NP + v) * EMB_THREADS + tid;
+        valid[v] = i[v] < p.i1;
+        if (!valid[v]) i[v] = p.i1 - 1;                  // compute on a real record, never store
+        r2[v] = reinterpret_cast<const double2 *>(p.rec2 + i[v] * R);
+        lc2[v] = p.rec2[i[v] * R + 3 * Q];
+        ah[v] = 0.0;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            sw[v][q] = sqrt(r2[v][q].y);
+            am[v][q] = 0.0;
+            as[v][q] = 0.0;
+        }
     }
     const int m_lo = p.m_bounds[blockIdx.y], m_hi = p.m_bounds[blockIdx.y + 1];
 
@@ -97,37 +117,53 @@ embed_psi2_kernel(EmbedParams p)
         const double2 *pg = p.pair_g + gp_pair_index(M, m, m);
         double2 g = __ldg(pg);                           // first pair of the row
 #pragma unroll
-        for (int q = 0; q < Q; ++q) sdm[q] = sw[q] * (r2[q].x - hm[q]);      // sw (mu - z_m / 2); mu re-read from L1
+        for (int v = 0; v < NP; ++v)
+#pragma unroll
+            for (int q = 0; q < Q; ++q) sdm[v][q] = sw[v][q] * (r2[v][q].x - hm[q]);   // sw (mu - z_m / 2); mu re-read from L1
 #pragma unroll EUNR
         for (int b = m; b < M; ++b) {
             const double2 gn = __ldg(pg + ((b + 1 < M) ? (b + 1 - m) : (b - m)));   // next pair, warp-uniform
             const double *hb = hz + b * Q;
-            double e0 = g.x, e1 = lc2;
+            double e0[NP], e1[NP], h[NP];
+#pragma unroll
+            for (int v = 0; v < NP; ++v) { e0[v] = g.x; e1[v] = lc2[v]; }
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
-                u[q] = fma(-sw[q], hb[q], sdm[q]);       // sw (mu - zbar)
-                if (q & 1) e1 = fma(-u[q], u[q], e1);
-                else e0 = fma(-u[q], u[q], e0);
-            }
-            const double h = g.y * EMB_EXP(e0 + e1);
-            ah += h;
+                const double hbq = hb[q];
 #pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                const double t = h * u[q];
-                am[q] += t;
-                as[q] = fma(t, u[q], as[q]);
+                for (int v = 0; v < NP; ++v) {
+                    u[v][q] = fma(-sw[v][q], hbq, sdm[v][q]);       // sw (mu - zbar)
+                    if (q & 1) e1[v] = fma(-u[v][q], u[v][q], e1[v]);
+                    else e0[v] = fma(-u[v][q], u[v][q], e0[v]);
+                }
             }
+#pragma unroll
+            for (int v = 0; v < NP; ++v) {
+                h[v] = g.y * EMB_EXP(e0[v] + e1[v]);
+                ah[v] += h[v];
+            }
+#pragma unroll
+            for (int q = 0; q < Q; ++q)
+#pragma unroll
+                for (int v = 0; v < NP; ++v) {
+                    const double t = h[v] * u[v][q];
+                    am[v][q] += t;
+                    as[v][q] = fma(t, u[v][q], as[v][q]);
+                }
             g = gn;
         }
     }
-    if (valid) {
-        double *out = p.partial + ((size_t)blockIdx.y * p.n + i) * (2 * Q + 1);
 #pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            out[q] = am[q];
-            out[Q + q] = as[q];
+    for (int v = 0; v < NP; ++v) {
+        if (valid[v]) {
+            double *out = p.partial + ((size_t)blockIdx.y * p.n + i[v]) * (2 * Q + 1);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                out[q] = am[v][q];
+                out[Q + q] = as[v][q];
+            }
+            out[2 * Q] = ah[v];
         }
-        out[2 * Q] = ah;
     }
 }
 
@@ -234,7 +270,8 @@ static int launch_q(gparml_ctx *c, int64_t i0, int64_t i1)
     int occ = 1;
     GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, embed_psi2_kernel<Q>, EMB_THREADS, smem));
     if (occ < 1) occ = 1;
-    const int64_t ntiles = (cnt + EMB_THREADS - 1) / EMB_THREADS;
+    const int64_t per_cta = (int64_t)EMB_THREADS * EmbCfg<Q>::NP;
+    const int64_t ntiles = (cnt + per_cta - 1) / per_cta;
     const int64_t slots = (int64_t)c->sm_count * occ;
     int max_splits = c->M < EMB_MAX_SPLITS ? c->M : EMB_MAX_SPLITS;
     int best = 1;

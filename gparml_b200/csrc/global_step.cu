@@ -181,31 +181,41 @@ __global__ void __launch_bounds__(GS_THREADS, 1) global_step_kernel(GsParams p)
     const double *P1Y = p.stats + p.off_p1y;
     double *P2 = p.psi2_full;
 
-    // ---- Kmm (kernels.py:108-111 with V = 2 ard^2 = 2 / alpha) and the full Psi2 -------------
-    for (size_t idx = tid; idx < MM; idx += GS_THREADS) {
-        const int i = (int)(idx / M), j = (int)(idx % M);
-        double s = 0.0;
-        for (int q = 0; q < Q; ++q) {
-            const double dz = p.Z[i * Q + q] - p.Z[j * Q + q];
-            s = fma(g.alpha[q] * dz, dz, s);
-        }
-        const double k = sf2 * exp(-0.5 * s);
-        X[idx] = k;
-        p.kmm[idx] = k;
-        if (!p.kmm_only) P2[idx] = S0[pidx(M, i, j)];
-    }
-    __syncthreads();
+    // The kernel runs in two launches.  kmm_only = 1 (launched from set_globals on the side stream,
+    // concurrently with the statistics map): Kmm, Kmm^-1 and log det Kmm, which depend on the
+    // hyper-parameters only (the reference's cache(), local_MapReduce.py:383-394).  kmm_only = 0:
+    // everything that needs the reduced statistics.
+    double *ldk_slot = p.out + 1 + M * Q + Q + 2;
     double ldK = 0.0, ldA = 0.0;
-    if (!gs_sweep_invert(X, M, tmp, piv, red, &ldK)) {
-        if (tid == 0) atomicOr(p.status, 1);
+    if (p.kmm_only) {
+        // ---- Kmm (kernels.py:108-111 with V = 2 ard^2 = 2 / alpha) ---------------------------
+        for (size_t idx = tid; idx < MM; idx += GS_THREADS) {
+            const int i = (int)(idx / M), j = (int)(idx % M);
+            double s = 0.0;
+            for (int q = 0; q < Q; ++q) {
+                const double dz = p.Z[i * Q + q] - p.Z[j * Q + q];
+                s = fma(g.alpha[q] * dz, dz, s);
+            }
+            const double k = sf2 * exp(-0.5 * s);
+            X[idx] = k;
+            p.kmm[idx] = k;
+        }
+        __syncthreads();
+        if (!gs_sweep_invert(X, M, tmp, piv, red, &ldK)) {
+            if (tid == 0) atomicOr(p.status, 1);
+            return;
+        }
+        for (size_t idx = tid; idx < MM; idx += GS_THREADS) p.kmm_inv[idx] = -X[idx];
+        if (tid == 0) ldk_slot[0] = ldK;
         return;
     }
+    if (*p.status & 1) return;                 // Kmm was not positive definite
+    ldK = ldk_slot[0];
     for (size_t idx = tid; idx < MM; idx += GS_THREADS) {
-        const double v = -X[idx];
-        W[idx] = v;                        // Kmm^-1
-        p.kmm_inv[idx] = v;
+        const int i = (int)(idx / M), j = (int)(idx % M);
+        W[idx] = p.kmm_inv[idx];               // Kmm^-1
+        P2[idx] = S0[pidx(M, i, j)];           // full Psi2
     }
-    if (p.kmm_only) return;
     __syncthreads();
 
     // ---- A = Kmm + beta Psi2, A^-1 (partial_terms.py:60) ---------------------------------------
@@ -273,7 +283,20 @@ __global__ void __launch_bounds__(GS_THREADS, 1) global_step_kernel(GsParams p)
 int gp_launch_global_step_large(gparml_ctx *c, GsParams &p);
 size_t gp_global_step_large_ws_doubles(int M, int sm_count);
 
-int gp_launch_global_step(gparml_ctx *c, bool kmm_only)
+static int launch_gs(gparml_ctx *c, bool kmm_only);
+
+// kmm_only launches go to the side stream `s` (concurrent with the statistics map), the rest to
+// the context's main stream; all helpers launch on c->stream, which is swapped for the call.
+int gp_launch_global_step(gparml_ctx *c, bool kmm_only, cudaStream_t s)
+{
+    cudaStream_t saved = c->stream;
+    c->stream = s;
+    const int r = launch_gs(c, kmm_only);
+    c->stream = saved;
+    return r;
+}
+
+static int launch_gs(gparml_ctx *c, bool kmm_only)
 {
     GsParams p;
     p.M = c->M; p.Q = c->Q; p.D = c->D; p.P = c->L.P;

@@ -304,12 +304,17 @@ int gp_launch_global_step_large(gparml_ctx *c, GsParams &p)
     double *part = pivA + M;                                      // (nparts, 6)
     const int nparts = c->sm_count * 2;
 
+    // two launches like the single-CTA kernel: kmm_only = 1 (from set_globals, side stream): Kmm,
+    // Kmm^-1 (W and kmm_inv) and its pivots; kmm_only = 0: everything that needs the statistics.
+    // The second launch re-runs the cheap build kernel only to expand Psi2 (it rewrites identical Kmm).
     gsl_build_kernel<<<eb, 256, 0, c->stream>>>(p, X);
     GP_LAUNCH_CHECK(c);
-    GP_TRY(block_sweep(c, X, pinv, T, Old, pivK, 1));
-    gsl_negate_kernel<<<eb, 256, 0, c->stream>>>(X, MM, W, c->kmm_inv);
-    GP_LAUNCH_CHECK(c);
-    if (p.kmm_only) return GPARML_OK;
+    if (p.kmm_only) {
+        GP_TRY(block_sweep(c, X, pinv, T, Old, pivK, 1));
+        gsl_negate_kernel<<<eb, 256, 0, c->stream>>>(X, MM, W, c->kmm_inv);
+        GP_LAUNCH_CHECK(c);
+        return GPARML_OK;
+    }
 
     gsl_form_a_kernel<<<eb, 256, 0, c->stream>>>(p, X);
     GP_LAUNCH_CHECK(c);

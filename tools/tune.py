@@ -24,20 +24,11 @@ ALL = ["capi.cu", "prep.cu", "psi1.cu", "psi2.cu", "psi2_f32.cu", "embed.cu", "g
 # name -> {source: [defines]}
 VARIANTS = {
     "base": {},
-    "p2_u4": {"psi2.cu": ["PSI2_UNROLL=4"]},
-    "p2_pp2_t256_b1_u1": {"psi2.cu": ["PSI2_PAIRS=2", "PSI2_MINB=1", "PSI2_UNROLL=1"]},
-    "p2_pp2_t256_b1_u2": {"psi2.cu": ["PSI2_PAIRS=2", "PSI2_MINB=1", "PSI2_UNROLL=2"]},
-    "p2_pp2_t128_b2_u1": {"psi2.cu": ["PSI2_PAIRS=2", "PSI2_THREADS=128", "PSI2_MINB=2", "PSI2_UNROLL=1"]},
-    "p2_pp2_t128_b2_u2": {"psi2.cu": ["PSI2_PAIRS=2", "PSI2_THREADS=128", "PSI2_MINB=2", "PSI2_UNROLL=2"]},
-    "p2_pp2_t128_b3_u1": {"psi2.cu": ["PSI2_PAIRS=2", "PSI2_THREADS=128", "PSI2_MINB=3", "PSI2_UNROLL=1"]},
-    "p2_pp2_t64_b5_u1": {"psi2.cu": ["PSI2_PAIRS=2", "PSI2_THREADS=64", "PSI2_MINB=5", "PSI2_UNROLL=1"]},
-    "p2_pp3_t128_b1_u1": {"psi2.cu": ["PSI2_PAIRS=3", "PSI2_THREADS=128", "PSI2_MINB=1", "PSI2_UNROLL=1"]},
-    "em_b4": {"embed.cu": ["EMB_MINB_LOWQ=4"]},
-    "em_b4_u2": {"embed.cu": ["EMB_MINB_LOWQ=4", "EMB_UNROLL=2"]},
-    "em_b3_u2": {"embed.cu": ["EMB_MINB_LOWQ=3", "EMB_UNROLL=2"]},
-    "em_b2_u2": {"embed.cu": ["EMB_MINB_LOWQ=2", "EMB_UNROLL=2"]},
-    "em_t64_b8": {"embed.cu": ["EMB_THREADS=64", "EMB_MINB_LOWQ=8"]},
-    "em_b5": {"embed.cu": ["EMB_MINB_LOWQ=5"]},
+    "em_np2_t128_b2": {"embed.cu": ["EMB_POINTS=2", "EMB_MINB_LOWQ=2", "EMB_UNROLL=1"]},
+    "em_np2_t128_b2_u2": {"embed.cu": ["EMB_POINTS=2", "EMB_MINB_LOWQ=2", "EMB_UNROLL=2"]},
+    "em_np2_t256_b1_u2": {"embed.cu": ["EMB_POINTS=2", "EMB_THREADS=256", "EMB_MINB_LOWQ=1", "EMB_UNROLL=2"]},
+    "em_np2_t64_b4_u2": {"embed.cu": ["EMB_POINTS=2", "EMB_THREADS=64", "EMB_MINB_LOWQ=4", "EMB_UNROLL=2"]},
+    "em_np3_t128_b1": {"embed.cu": ["EMB_POINTS=3", "EMB_MINB_LOWQ=1", "EMB_UNROLL=1"]},
 }
 
 
