@@ -12,15 +12,16 @@
 //   row (1+Q+q,m): Psi1 (ad_q^2 + v1_nq)      -> -2 alpha_q^2 dPsi1Y/dalpha[q,m,:]
 // and every row is contracted with Y over the points: C[row, d] = sum_n A[n, row] Y[n, d].
 //
-// One CTA owns MB <= 32 inducing points and walks its slice of the points in tiles of 8
-// (one warp per point).  Stage 1: lane = inducing point, the warp's point record is read from
-// shared memory as broadcasts, Psi1 and the 1+2Q row entries go to shared memory laid out
-// [point][row] with row = j * MB + m (lane-consecutive, conflict free).  Stage 2: a small
-// register-blocked GEMM over the tile, each thread owning RB = 4 rows x DC columns, so that one
-// 8-byte A read and one broadcast Y read feed DC resp. RB FMAs (0.45 shared-memory wavefronts
-// per FP64 instruction; the first version with one row per thread was LSU-bound at 1.2).
-// Q is a run-time value (row entries live in shared memory); DC is the template parameter.
-// ~4 % of the evaluation's work; FP64-pipe bound.
+// One CTA (128 threads) owns MB inducing points (MB * (1+2Q) <= 512 rows) and walks its slice of
+// the points in tiles of 8, loaded with 16-byte cp.async (LDGSTS) into a double buffer while the
+// previous tile is contracted.  Stage 1: one (point, inducing point) item per thread and round,
+// record fields read from shared memory, Psi1 and the 1+2Q row entries written to shared memory
+// laid out [point][row] with row = j * MB + m (conflict free).  Stage 2: a small register-blocked
+// GEMM over the tile, each thread owning RB = 4 rows x DC columns, so that one 8-byte A read and
+// one broadcast Y read feed DC resp. RB FMAs (0.45 shared-memory wavefronts per FP64
+// instruction; the first version with one row per thread and a run-time Q was LSU- and
+// issue-bound).  Templated on Q (stage 1 in registers) and DC (output columns per CTA, <= 10).
+// ~4 % of the evaluation's work; FP64 pipe 43 %, LSU 72 % (profiles/).
 #include <math.h>
 
 #include "common.cuh"

@@ -15,15 +15,16 @@
 // over the P = M(M+1)/2 pairs m <= m' only (all three are symmetric in (m, m'); the
 // antisymmetric Kmm-like part of dPsi2/dZ is point independent and added on expansion).
 //
-// Mapping.  One thread owns one pair and keeps its 1 + 2Q accumulators, zbar (Q) and wd (Q) in
-// registers; a CTA of 256 threads owns 256 pairs and walks its slice of the points.  Point
-// records (prep_points) are staged through shared memory by 1-D bulk async copies (TMA unit,
-// SASS UBLKCP) into a 2-stage ring guarded by mbarriers; every thread reads the same record
-// at the same time, so all shared-memory reads are broadcasts.  The grid is
-// (pair tiles) x (n splits), sized to whole waves of resident CTAs; per-split partial sums go
-// to a workspace and are added in a fixed order (deterministic, no atomics).
+// Mapping.  One thread owns PP pairs (2 for Q <= 10) and keeps their 1 + 2Q accumulators, zbar (Q)
+// and wd (Q) in registers; a CTA of 256 threads owns 256 PP pairs and walks its slice of the
+// points.  Point records (prep_points) are staged through shared memory by 1-D bulk async copies
+// (TMA unit, SASS UBLKCP) into a 2-stage ring guarded by mbarriers; every thread reads the same
+// record at the same time, so all shared-memory reads are broadcasts and each read feeds PP
+// pairs.  The grid is (pair tiles) x (n splits), sized to whole waves of resident CTAs; per-split
+// partial sums go to a workspace and are added in a fixed order (deterministic, no atomics).
 //
-// Bound: FP64 pipe.  6Q + 20 FP64 instructions per (point, pair) of which exp() is 18.
+// Bound: FP64 pipe.  Algorithmic count 6Q + 20 per (point, pair) with exp = 18;
+// executed: 6Q + 11 with the table-driven exp of gp_exp.cuh (9 FP64 instructions).
 #include <math.h>
 
 #include "common.cuh"
