@@ -283,8 +283,11 @@ class partial_terms(object):
     def _embed(self):
         if not self._have_data:
             raise ValueError("set_data must be called first")
-        self._global()
+        g = self._global()
+        if getattr(self, "_embed_for", None) is g:
+            return                      # grad_X_mu / grad_X_S of the same state: one map serves both
         self._ctx.embedding_grads()
+        self._embed_for = g
 
     def grad_X_mu(self):
         """partial_terms.py:367-398."""

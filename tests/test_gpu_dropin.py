@@ -194,3 +194,46 @@ def test_dropout_rescales_like_reference(tmp_path):
         assert part["sum_exp_K_mi_K_im"].shape == (5, 5)
     finally:
         b200_MapReduce.close()
+
+
+def test_predict_path_matches_oracle_and_improves(tmp_path):
+    """predict.py:116-144 replay: the test points' statistics are added to the stored 'f' statistics;
+    one evaluation against the oracle (1e-9), then a short optimisation must increase the bound."""
+    from gparml_b200 import b200_MapReduce, parallel_GPLVM as drv, predict
+    from gparml_b200.synthetic import make_problem
+    from oracle import gparml_oracle as O
+    p = make_problem(500, 8, 2, 3, seed=9)
+    dirs = _write_problem(tmp_path, p, 2)
+    np.random.seed(3)
+    opts = drv.default_options(M=8, Q=2, D=3, iterations=2, init="PCA", display=False, **dirs)
+    try:
+        drv.main(opts)                      # writes the *_f.npy checkpoint the prediction path reads
+    finally:
+        b200_MapReduce.close()
+    rng = np.random.default_rng(5)
+    Y_test = p["Y"][:7] + 0.01 * rng.standard_normal((7, 3))
+    try:
+        s = predict.setup(opts, Y_test)
+        gs, acc = s["global_statistics"], s["accumulated_statistics"]
+        mu = rng.standard_normal((7, 2)); S = rng.uniform(0.2, 0.8, (7, 2))
+        x = np.concatenate([mu.ravel(), O.softplus_inv(S).ravel()])
+        f, g = predict.likelihood_and_gradient(x)
+        # oracle: same composition of statistics
+        Z, sf2 = gs["Z"], float(np.squeeze(gs["sf2"]))
+        alpha, beta = np.atleast_1d(np.squeeze(gs["alpha"])), float(np.squeeze(gs["beta"]))
+        new = O.shard_statistics(Y_test, mu, S, Z, sf2, alpha)
+        tot = dict(new)
+        for k in ("sum_YYT", "sum_exp_K_mi_K_im", "sum_exp_K_miY", "sum_exp_K_ii", "sum_KL"):
+            tot[k] = acc[k] + new[k]
+        G = O.global_step(tot, Z, sf2, alpha, beta, opts["N"])
+        gm, gS = O.embedding_grads(Y_test, mu, S, Z, sf2, alpha, G["dF_dsum_exp_K_miY"], G["dF_dsum_exp_K_mi_K_im"])
+        g_ref = -np.concatenate([gm.ravel(), (gS * O.softplus_grad(O.softplus_inv(S))).ravel()])
+        assert abs(f + G["F"]) <= 1e-9 * abs(G["F"])
+        assert relerr(g, g_ref) < 1e-9
+        np.random.seed(4)
+        best = predict.test(opts, Y_test, random_iterations=15)
+        f0, _ = predict.likelihood_and_gradient(np.concatenate([best[0].ravel(), O.softplus_inv(best[1]).ravel()]))
+        assert best[0].shape == (7, 2) and np.all(best[1] > 0)
+        assert abs(-f0 - best[2]) <= 1e-8 * abs(best[2])
+    finally:
+        predict.close()
