@@ -262,3 +262,22 @@ def test_chunked_gradient_download_and_reupload():
             assert abs(F - ref["global"]["F"]) <= 1e-9 * abs(ref["global"]["F"])
             assert relerr(base, ref["grad_latest"][0]) < 1e-9
             assert relerr(c.stats_named()["sum_YYT"], ref["stats"]["sum_YYT"]) < 1e-13
+
+
+def test_empty_and_tiny_shards():
+    """Edge cases of the shard sizes: an empty shard (a rank with no points), a 1-point shard and a
+    2-point shard next to a normal one; M = 1 and D = 1."""
+    from gparml_b200.synthetic import make_problem
+    from oracle import c_oracle
+    p = make_problem(203, 1, 2, 1, seed=71, generic_hypers=True, with_direction=True)
+    cuts = [(0, 0), (0, 1), (1, 3), (3, 203)]
+    shards = [dict(Y=p["Y"][lo:hi], X_mu=p["X_mu"][lo:hi], X_S=p["X_S"][lo:hi], d=p["d"][:, lo:hi]) for lo, hi in cuts]
+    ref = c_oracle.evaluate([s for s in shards if len(s["Y"])], p["Z"], p["sf2"], p["alpha"], p["beta"], step_size=1e-3)
+    res = _gpu_evaluate(shards, p["Z"], p["sf2"], p["alpha"], p["beta"], step_size=1e-3)
+    for k, v in ref["stats"].items():
+        assert relerr(res["stats"][k], v) < TOL, k
+    assert abs(res["global"]["F"] - ref["global"]["F"]) <= TOL * abs(ref["global"]["F"])
+    assert relerr(res["global"]["grad_Z"], ref["global"]["grad_Z"]) < TOL
+    assert res["grad_latest"][0].shape == (2, 0, 2)
+    got = np.concatenate(res["grad_latest"][1:], axis=1)
+    assert relerr(got, np.concatenate(ref["grad_latest"], axis=1)) < TOL
