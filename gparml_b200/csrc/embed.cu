@@ -22,10 +22,11 @@
 //   sum_p Gs Psi2_n wd_q = sw_q AM_q,   sum_p Gs Psi2_n wd_q^2 = w_q AS_q
 // i.e. 2 FMAs per latent dimension for the exponent instead of sub + mul + FMA: 5Q + 12 FP64
 // instructions per (point, pair) instead of 6Q + 12.  Registers per thread: sw, sw (mu - z_m/2),
-// u, AM, AS (5Q doubles); Z/2 sits in shared memory and is read as broadcasts; (lk, Gs) per
-// pair is a warp-uniform 16-byte global load issued one pair ahead.  Grid = (point tiles) x
-// (splits of the m range, balanced by pair count); split partials are combined in a fixed
-// order by embed_finish.
+// u, AM, AS (5Q doubles) for each of the NP = 2 points a thread owns; Z/2 and -- when it fits
+// (M <= ~110) -- the (lk, Gs) pair table sit in shared memory and are read as broadcasts that feed
+// both points (B200, N = 250k: pair table by warp-uniform global loads 6.79 ms, from shared
+// memory 6.37 ms).  Grid = (point tiles) x (splits of the m range, balanced by pair count);
+// split partials are combined in a fixed order by embed_finish.
 //
 // Psi1 part (embed_psi1_kernel): thread per point, loop over the M inducing points.
 //
@@ -75,7 +76,8 @@ template <int Q> struct EmbCfg {
 };
 #endif
 
-template <int Q>
+// PS: the (lk, Gs) pair table is copied to shared memory (when P * 16 B fits next to Z / 2)
+template <int Q, bool PS>
 __global__ void __launch_bounds__(EMB_THREADS, EmbCfg<Q>::MINB)
 embed_psi2_kernel(EmbedParams p)
 {
@@ -86,6 +88,11 @@ embed_psi2_kernel(EmbedParams p)
     const int tid = threadIdx.x;
     const int M = p.M;
     for (int idx = tid; idx < M * Q; idx += EMB_THREADS) hz[idx] = 0.5 * p.Z[idx];
+    double2 *pgs = reinterpret_cast<double2 *>(hz + ((M * Q + 1) & ~1));
+    if (PS) {
+        const int64_t P = gp_pair_index(M, M - 1, M - 1) + 1;
+        for (int64_t idx = tid; idx < P; idx += EMB_THREADS) pgs[idx] = p.pair_g[idx];
+    }
     gp_exp_load_table(exp_tab);
     __syncthreads();
 
@@ -114,15 +121,16 @@ embed_psi2_kernel(EmbedParams p)
 
     for (int m = m_lo; m < m_hi; ++m) {
         const double *hm = hz + m * Q;
-        const double2 *pg = p.pair_g + gp_pair_index(M, m, m);
-        double2 g = __ldg(pg);                           // first pair of the row
+        const double2 *pg = (PS ? pgs : p.pair_g) + gp_pair_index(M, m, m);
+        double2 g = PS ? pg[0] : __ldg(pg);              // first pair of the row
 #pragma unroll
         for (int v = 0; v < NP; ++v)
 #pragma unroll
             for (int q = 0; q < Q; ++q) sdm[v][q] = sw[v][q] * (r2[v][q].x - hm[q]);   // sw (mu - z_m / 2); mu re-read from L1
 #pragma unroll EUNR
         for (int b = m; b < M; ++b) {
-            const double2 gn = __ldg(pg + ((b + 1 < M) ? (b + 1 - m) : (b - m)));   // next pair, warp-uniform
+            const int nxt = (b + 1 < M) ? (b + 1 - m) : (b - m);
+            const double2 gn = PS ? pg[nxt] : __ldg(pg + nxt);                      // next pair, warp-uniform
             const double *hb = hz + b * Q;
             double e0[NP], e1[NP], h[NP];
 #pragma unroll
@@ -265,10 +273,20 @@ static int launch_q(gparml_ctx *c, int64_t i0, int64_t i1)
 {
     const int64_t cnt = i1 - i0;
     const size_t smem = (size_t)c->M * Q * sizeof(double);
-    GP_CUDA(cudaFuncSetAttribute(embed_psi2_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // pair table in shared memory when it fits twice per SM next to Z / 2 (M <= ~110)
+    const size_t smem_ps = (((size_t)c->M * Q + 1) & ~(size_t)1) * sizeof(double) + (size_t)c->L.P * sizeof(double2);
+#ifdef EMB_NO_PAIR_SMEM
+    const bool ps = false;
+#else
+    const bool ps = smem_ps <= (size_t)100 * 1024;
+#endif
+    const size_t smem2 = ps ? smem_ps : smem;
+    GP_CUDA(cudaFuncSetAttribute(embed_psi2_kernel<Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ps > 200 * 1024 ? 200 * 1024 : (int)smem_ps));
+    GP_CUDA(cudaFuncSetAttribute(embed_psi2_kernel<Q, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GP_CUDA(cudaFuncSetAttribute(embed_psi1_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
-    GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, embed_psi2_kernel<Q>, EMB_THREADS, smem));
+    if (ps) GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, embed_psi2_kernel<Q, true>, EMB_THREADS, smem2));
+    else GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, embed_psi2_kernel<Q, false>, EMB_THREADS, smem2));
     if (occ < 1) occ = 1;
     const int64_t per_cta = (int64_t)EMB_THREADS * EmbCfg<Q>::NP;
     const int64_t ntiles = (cnt + per_cta - 1) / per_cta;
@@ -309,7 +327,8 @@ static int launch_q(gparml_ctx *c, int64_t i0, int64_t i1)
         GP_TRY(gp_launch_embed_psi2_f32(c, p.m_bounds, splits, p.partial, i0, i1));
     } else {
         dim3 grid((unsigned)ntiles, splits);
-        embed_psi2_kernel<Q><<<grid, EMB_THREADS, smem, c->stream>>>(p);
+        if (ps) embed_psi2_kernel<Q, true><<<grid, EMB_THREADS, smem2, c->stream>>>(p);
+        else embed_psi2_kernel<Q, false><<<grid, EMB_THREADS, smem2, c->stream>>>(p);
         GP_LAUNCH_CHECK(c);
     }
     const int64_t total = cnt * Q;

@@ -24,11 +24,7 @@ ALL = ["capi.cu", "prep.cu", "psi1.cu", "psi2.cu", "psi2_f32.cu", "embed.cu", "g
 # name -> {source: [defines]}
 VARIANTS = {
     "base": {},
-    "em_np2_t128_b2": {"embed.cu": ["EMB_POINTS=2", "EMB_MINB_LOWQ=2", "EMB_UNROLL=1"]},
-    "em_np2_t128_b2_u2": {"embed.cu": ["EMB_POINTS=2", "EMB_MINB_LOWQ=2", "EMB_UNROLL=2"]},
-    "em_np2_t256_b1_u2": {"embed.cu": ["EMB_POINTS=2", "EMB_THREADS=256", "EMB_MINB_LOWQ=1", "EMB_UNROLL=2"]},
-    "em_np2_t64_b4_u2": {"embed.cu": ["EMB_POINTS=2", "EMB_THREADS=64", "EMB_MINB_LOWQ=4", "EMB_UNROLL=2"]},
-    "em_np3_t128_b1": {"embed.cu": ["EMB_POINTS=3", "EMB_MINB_LOWQ=1", "EMB_UNROLL=1"]},
+    "em_nops": {"embed.cu": ["EMB_NO_PAIR_SMEM"]},
 }
 
 
