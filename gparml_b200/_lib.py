@@ -84,6 +84,12 @@ PROTOTYPES = {
     "gparml_enable_timing": (ctypes.c_int, [_vp, ctypes.c_int]),
     "gparml_phase_times": (ctypes.c_int, [_vp, _dp]),
     "gparml_measure_dfma_peak": (ctypes.c_int, [_vp, _dp]),
+    "gparml_upload_outputs": (ctypes.c_int, [_vp, _vp, _i64]),
+    "gparml_init_column_sums": (ctypes.c_int, [_vp, _vp]),
+    "gparml_init_scatter": (ctypes.c_int, [_vp, _vp, _vp]),
+    "gparml_init_project": (ctypes.c_int, [_vp, _vp, _vp]),
+    "gparml_init_random": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_uint64, _i64]),
+    "gparml_kmeans_step": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp]),
 }
 
 _lib = None

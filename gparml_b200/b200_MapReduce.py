@@ -20,6 +20,7 @@ from os.path import basename
 import numpy
 
 from . import _lib
+from . import init_device
 from . import partial_terms as pt
 from . import transforms as sp
 from .engine import ShardContext
@@ -106,8 +107,54 @@ def session_contexts(folder):
 
 
 # ------------------------------------------------------------------------------------------
-# init (local_MapReduce.py:27-104): one-off host work, identical files
+# init (local_MapReduce.py:27-104): same files; PCA / random draws on the device
 # ------------------------------------------------------------------------------------------
+def _device_init(options):
+    """Replaces the master-side 'load ALL data' PCA of local_MapReduce.py:52-65 and the draws of
+    :86-93: every CSV is parsed once into its shard context (which statistics_MR then reuses),
+    the PCA runs on the shards' partial sums, and the files the reference writes
+    (``.embedding.npy``, ``.variance.npy``) are flushed from the device."""
+    close(options)
+    s = _Session()
+    s.files = sorted(glob.glob(options["input"] + "/*"))
+    devs = _devices(options)
+    for i, f in enumerate(s.files):
+        Y = _load_csv(f)
+        c = ShardContext(options["M"], options["Q"], options["D"], options["N"], device=devs[i % len(devs)],
+                         fixed_beta=bool(options.get("fixed_beta")))
+        c.upload_outputs(Y)
+        s.ctx.append(c)
+    s.root = s.ctx[0]
+    seed = int(numpy.random.randint(0, 2 ** 31 - 1))     # follows numpy.random.seed like the reference's draws
+    if options["init"] == "PCA":
+        init_device.pca(s.ctx)
+    else:
+        init_device.random_means(s.ctx, seed + 1)
+    init_device.random_variances(s.ctx, seed)
+    _sessions[_key(options)] = s
+    for f, c in zip(s.files, s.ctx):
+        base = options["embeddings"] + "/" + basename(f)
+        for ext in (".embedding.npy", ".variance.npy", ".grad_d.npy"):
+            remove(base + ext)
+        save(base + ".embedding.npy", c.download(_lib.A_X_MU, (c.n_local, c.Q)))
+        save(base + ".variance.npy", c.download(_lib.A_X_S, (c.n_local, c.Q)))
+
+
+def kmeans(options, k):
+    """Device k-means over the embeddings the reference clusters (the first shards holding at
+    least ``k`` points, parallel_GPLVM.py:170-181); returns the code book like
+    ``scipy.cluster.vq.kmeans(...)[0]``."""
+    s = _session(options)
+    ctxs, n = [], 0
+    for c in s.ctx:
+        ctxs.append(c)
+        n += c.n_local
+        if n >= k:
+            break
+    cand = numpy.concatenate([c.download(_lib.A_X_MU, (c.n_local, c.Q)) for c in ctxs])
+    return init_device.kmeans(ctxs, k, candidates=cand)[0]
+
+
 def init(options):
     names = os.listdir(options["input"] + "/")
     lengths = []
@@ -120,6 +167,11 @@ def init(options):
         lengths.append(n)
     options["N"] = sum(lengths)
 
+    if not options["fixed_embeddings"] and not options["load"] and options.get("b200_device_init", True):
+        if options["init"] not in ("PCA", "random"):
+            raise ValueError("init=%r is not available in the b200 backend (PCA or random)" % options["init"])
+        _device_init(options)
+        return options
     if not options["fixed_embeddings"] and not options["load"]:
         X = None
         if options["init"] == "PCA":

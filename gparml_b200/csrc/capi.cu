@@ -230,6 +230,86 @@ extern "C" int gparml_upload_shard(gparml_ctx *c, const double *Y, const double 
     return GPARML_OK;
 }
 
+// ---- one-off initialisation on the device (init.cu) ----------------------------------------
+extern "C" int gparml_upload_outputs(gparml_ctx *c, const double *Y, int64_t n)
+{
+    CHECK_CTX(c);
+    if (n < 0 || (n > 0 && !Y)) { gp_set_error("upload_outputs: null array or negative n"); return GPARML_ERR_ARG; }
+    GP_TRY(ensure_shard_capacity(c, n));
+    const size_t nq = (size_t)n * c->Q;
+    GP_CUDA(cudaStreamWaitEvent(c->stream, c->ev_y, 0));   // an earlier upload of Y on the copy stream
+    if (n > 0) {
+        GP_CUDA(cudaMemcpyAsync(c->Y, Y, (size_t)n * c->D * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        GP_CUDA(cudaMemsetAsync(c->x_mu, 0, nq * sizeof(double), c->stream));
+        GP_CUDA(cudaMemsetAsync(c->x_s, 0, nq * sizeof(double), c->stream));
+    }
+    if (n != c->n) {
+        c->have_dir = false;
+        if (c->psi1) { cudaFree(c->psi1); c->psi1 = nullptr; }
+    }
+    c->n = n;
+    c->variance_domain = GPARML_VARIANCE_UNCONSTRAINED;
+    c->have_shard = true;
+    c->have_prep = c->have_stats = c->have_global_step = false;
+    GP_TRY(gp_launch_yyt(c, c->stream));
+    GP_CUDA(cudaEventRecord(c->ev_y, c->stream));
+    return GPARML_OK;
+}
+
+#define CHECK_SHARD(c, what)                                                              \
+    do {                                                                                  \
+        if (!(c)->have_shard) { gp_set_error(what ": no shard uploaded"); return GPARML_ERR_STATE; } \
+    } while (0)
+
+extern "C" int gparml_init_column_sums(gparml_ctx *c, double *out)
+{
+    CHECK_CTX(c);
+    CHECK_SHARD(c, "init_column_sums");
+    if (!out) { gp_set_error("init_column_sums: null output"); return GPARML_ERR_ARG; }
+    GP_CUDA(cudaStreamWaitEvent(c->stream, c->ev_y, 0));
+    return gp_init_colsum(c, out);
+}
+
+extern "C" int gparml_init_scatter(gparml_ctx *c, const double *mean, double *out)
+{
+    CHECK_CTX(c);
+    CHECK_SHARD(c, "init_scatter");
+    if (!mean || !out) { gp_set_error("init_scatter: null array"); return GPARML_ERR_ARG; }
+    GP_CUDA(cudaStreamWaitEvent(c->stream, c->ev_y, 0));
+    return gp_init_scatter(c, mean, out);
+}
+
+extern "C" int gparml_init_project(gparml_ctx *c, const double *mean, const double *W)
+{
+    CHECK_CTX(c);
+    CHECK_SHARD(c, "init_project");
+    if (!mean || !W) { gp_set_error("init_project: null array"); return GPARML_ERR_ARG; }
+    GP_CUDA(cudaStreamWaitEvent(c->stream, c->ev_y, 0));
+    c->have_prep = c->have_stats = c->have_global_step = false;
+    GP_TRY(gp_init_project(c, mean, W));
+    GP_CUDA(cudaStreamSynchronize(c->stream));     // W / mean may be pageable temporaries of the caller
+    return GPARML_OK;
+}
+
+extern "C" int gparml_init_random(gparml_ctx *c, int what, uint64_t seed, int64_t row_offset)
+{
+    CHECK_CTX(c);
+    CHECK_SHARD(c, "init_random");
+    if (what != 0 && what != 1) { gp_set_error("init_random: what must be 0 (variances) or 1 (means)"); return GPARML_ERR_ARG; }
+    if (row_offset < 0) { gp_set_error("init_random: negative row offset"); return GPARML_ERR_ARG; }
+    c->have_prep = c->have_stats = c->have_global_step = false;
+    if (what == 0) c->variance_domain = GPARML_VARIANCE_UNCONSTRAINED;
+    return gp_init_random(c, what, seed, row_offset);
+}
+
+extern "C" int gparml_kmeans_step(gparml_ctx *c, const double *centroids, int k, double *out)
+{
+    CHECK_CTX(c);
+    CHECK_SHARD(c, "kmeans_step");
+    if (!centroids || !out || k < 1) { gp_set_error("kmeans_step: null array or k < 1"); return GPARML_ERR_ARG; }
+    return gp_init_kmeans_step(c, centroids, k, out);
+}
+
 // make the main stream wait for the Y upload (and its sum of squares)
 static int wait_y(gparml_ctx *c)
 {

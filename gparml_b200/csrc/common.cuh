@@ -176,6 +176,11 @@ int gp_launch_stats_add(gparml_ctx *c, const double *src, double scale);
 int gp_scg_reduce(gparml_ctx *c, int op, double scale, double *host_out);
 int gp_scg_update(gparml_ctx *c, int op, double scale);
 int gp_measure_dfma(gparml_ctx *c, double *out);
+int gp_init_colsum(gparml_ctx *c, double *out_host);
+int gp_init_scatter(gparml_ctx *c, const double *mean_host, double *out_host);
+int gp_init_project(gparml_ctx *c, const double *mean_host, const double *W_host);
+int gp_init_random(gparml_ctx *c, int mode, uint64_t seed, int64_t row_offset);
+int gp_init_kmeans_step(gparml_ctx *c, const double *cent_host, int k, double *out_host);
 
 // ---------------------------------------------------------------------------
 // device helpers

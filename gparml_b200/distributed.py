@@ -56,6 +56,23 @@ def allreduce_scalars(values, op="sum", device=None):
     return [float(v) for v in t.cpu()]
 
 
+def allreduce_numpy(array, device=None):
+    """Sum a small float64 numpy array over ranks (the ``reduce_fn`` of ``init_device``: column
+    sums, the D x D scatter matrix, k-means cluster sums).  ``device``: where the temporary tensor
+    lives (a CUDA device for NCCL, None for gloo)."""
+    import numpy
+    import torch
+    import torch.distributed as dist
+    array = numpy.ascontiguousarray(array, dtype=numpy.float64)
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return array
+    t = torch.from_numpy(array.copy())
+    if device is not None:
+        t = t.to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy()
+
+
 def packed_reduce_fn():
     """reduce_fn for ``engine.evaluate``: all-reduces the context's packed statistics in place."""
     def fn(ctx):

@@ -309,6 +309,46 @@ class ShardContext(object):
         _lib.check(self._lib.gparml_measure_dfma_peak(self._h, ctypes.byref(out)))
         return float(out.value)
 
+    # -- one-off initialisation on the device (see init_device.py) --------
+    def upload_outputs(self, Y):
+        Y = _lib.as_f64(Y)
+        if Y.ndim == 1:
+            Y = np.ascontiguousarray(Y.reshape(-1, 1))
+        Y = _lib.as_f64(Y, (Y.shape[0], self.D))
+        _lib.check(self._lib.gparml_upload_outputs(self._h, _lib.ptr(Y), Y.shape[0]))
+
+    def init_column_sums(self):
+        out = np.empty(self.D)
+        _lib.check(self._lib.gparml_init_column_sums(self._h, _lib.ptr(out)))
+        return out
+
+    def init_scatter(self, mean):
+        mean = _lib.as_f64(mean, (self.D,))
+        out = np.empty((self.D, self.D))
+        _lib.check(self._lib.gparml_init_scatter(self._h, _lib.ptr(mean), _lib.ptr(out)))
+        return out
+
+    def init_project(self, mean, W):
+        mean = _lib.as_f64(mean, (self.D,))
+        W = _lib.as_f64(W, (self.D, self.Q))
+        _lib.check(self._lib.gparml_init_project(self._h, _lib.ptr(mean), _lib.ptr(W)))
+
+    def init_random_variances(self, seed, row_offset=0):
+        _lib.check(self._lib.gparml_init_random(self._h, 0, int(seed) & (2 ** 64 - 1), int(row_offset)))
+
+    def init_random_means(self, seed, row_offset=0):
+        _lib.check(self._lib.gparml_init_random(self._h, 1, int(seed) & (2 ** 64 - 1), int(row_offset)))
+
+    def kmeans_step(self, centroids):
+        """-> (counts (k,), sums (k, Q), summed distance to the nearest centroid)."""
+        centroids = _lib.as_f64(centroids)
+        k = centroids.shape[0]
+        centroids = _lib.as_f64(centroids, (k, self.Q))
+        out = np.empty(k * (1 + self.Q) + 1)
+        _lib.check(self._lib.gparml_kmeans_step(self._h, _lib.ptr(centroids), k, _lib.ptr(out)))
+        t = out[:-1].reshape(k, 1 + self.Q)
+        return t[:, 0].copy(), t[:, 1:].copy(), float(out[-1])
+
 
 def evaluate(contexts, Z, sf2, alpha, beta, step_size=0.0, reduce_fn=None):
     """One ELBO + gradient evaluation over shard contexts living in THIS process

@@ -91,8 +91,11 @@ def init_statistics(map_reduce, options):
                 (embeddings, map_reduce.load(options['embeddings'] + '/' + names[fid] + '.embedding.npy')))
         if embeddings.shape[1] != options['Q']:
             raise Exception('Given Q does not equal existing embedding data dimensions!')
-        import scipy.cluster.vq as cl
-        Z = cl.kmeans(embeddings, options['M'])[0]
+        if options.get('b200_device_init', True) and hasattr(map_reduce, 'kmeans'):
+            Z = map_reduce.kmeans(options, options['M'])      # same algorithm, one device pass per iteration
+        else:
+            import scipy.cluster.vq as cl
+            Z = cl.kmeans(embeddings, options['M'])[0]
         missing = options['M'] - Z.shape[0]
         if missing > 0:
             Z = numpy.concatenate((Z, embeddings[:missing]))

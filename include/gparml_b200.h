@@ -207,6 +207,30 @@ int gparml_scg_update_X(gparml_ctx *ctx, double alpha);             /* :193-216 
 int gparml_scg_update_grad_old(gparml_ctx *ctx);                    /* :218-230 */
 int gparml_scg_update_grad_new(gparml_ctx *ctx);                    /* :232-243 */
 
+/* ---- one-off initialisation on the device ------------------
+ * Replaces the master-side PCA over ALL outputs (local_MapReduce.py:52-65 ->
+ * supporting_functions.py:102-121), the variance draw (local_MapReduce.py:88-93) and the
+ * k-means for the inducing inputs (parallel_GPLVM.py:170-186 -> scipy.cluster.vq.kmeans).
+ * Every function works on ONE shard and returns partial sums the caller adds over shards. */
+/* upload only the outputs of a shard (n, D); X_mu / X_S are zero-filled (unconstrained domain)
+ * until gparml_init_project / gparml_init_random or gparml_upload write them. */
+int gparml_upload_outputs(gparml_ctx *ctx, const double *Y, int64_t n);
+/* out (D): sum_n y_n */
+int gparml_init_column_sums(gparml_ctx *ctx, double *out);
+/* out (D, D): sum_n (y_n - mean)(y_n - mean)^T, mean (D) = global column means */
+int gparml_init_scatter(gparml_ctx *ctx, const double *mean, double *out);
+/* X_mu = (Y - mean) W with W (D, Q): for PCA W[:, q] = v_q sqrt(N / lambda_q)
+ * (supporting_functions.py:117-120: U[:, :Q] / std) */
+int gparml_init_project(gparml_ctx *ctx, const double *mean, const double *W);
+/* what = 0: X_S = softplus^-1(clip(0.5 + 0.01 N(0,1), 0.001, 1)) (local_MapReduce.py:90-93);
+ * what = 1: X_mu = N(0,1) (init == 'random', local_MapReduce.py:86-87).  Counter-based:
+ * element (row_offset + i, q) of stream `seed` does not depend on the sharding. */
+int gparml_init_random(gparml_ctx *ctx, int what, uint64_t seed, int64_t row_offset);
+/* one assignment pass of k-means over the shard's X_mu against centroids (k, Q):
+ * out (k*(1+Q) + 1) = per cluster [count, sum of members (Q)], then the summed Euclidean
+ * distance to the nearest centroid (scipy.cluster.vq.vq + update_cluster_means). */
+int gparml_kmeans_step(gparml_ctx *ctx, const double *centroids, int k, double *out);
+
 /* ---- introspection for bench.py / tests ----------------------------------- */
 /* kernels launched by this context since creation (bench.py's gpu_launches). */
 int64_t gparml_launch_count(const gparml_ctx *ctx);

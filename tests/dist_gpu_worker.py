@@ -44,7 +44,19 @@ def main():
     ctx.scg_set_grads()
     ops = gd.DistributedLocalOps(ctx, device=torch.device("cuda", dev) if backend == "nccl" else None)
     kappa = ops.embeddings_get_grads_kappa("unused")
-    np.savez(os.path.join(sys.argv[2], "rank%d.npz" % rank), F=F, flat=g["flat"], gl=gl, lo=lo, hi=hi, kappa=kappa)
+    # device-side initialisation across ranks: PCA + Lloyd iterations from a common guess
+    from gparml_b200 import init_device
+    tdev = torch.device("cuda", dev) if backend == "nccl" else None
+    red = lambda a: gd.allreduce_numpy(a, device=tdev)   # noqa: E731
+    Y2 = make_problem(N, M, Q, 6, seed=78)["Y"]
+    ctx2 = ShardContext(M, Q, 6, N, device=dev)
+    ctx2.upload_outputs(Y2[lo:hi])
+    init_device.pca([ctx2], reduce_fn=red)
+    X0 = ctx2.download(_lib.A_X_MU, (hi - lo, Q))
+    book, distortion = init_device.kmeans_from_guess([ctx2], p["Z"][:8] * 0.3, reduce_fn=red)
+    ctx2.close()
+    np.savez(os.path.join(sys.argv[2], "rank%d.npz" % rank), F=F, flat=g["flat"], gl=gl, lo=lo, hi=hi, kappa=kappa,
+             X0=X0, book=book, distortion=distortion)
     dist.barrier()
     dist.destroy_process_group()
     ctx.close()

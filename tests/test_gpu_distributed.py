@@ -39,6 +39,17 @@ def _check(outs):
         assert relerr(o["flat"], flat_ref) < 1e-9
         assert relerr(o["gl"], ref["grad_latest"][0][:, int(o["lo"]):int(o["hi"])]) < 1e-9
         assert float(o["kappa"]) == pytest.approx(float(np.sum(ref["grad_latest"][0] ** 2)), rel=1e-9)
+    # device-side PCA / k-means with the partial sums all-reduced over ranks
+    import scipy.cluster.vq as cl
+    Y2 = make_problem(N, M, Q, 6, seed=78)["Y"]
+    svd = np.linalg.svd(Y2 - Y2.mean(axis=0), full_matrices=False)
+    ref_X = svd[0][:, :Q] / svd[0][:, :Q].std(axis=0)                # supporting_functions.py:116-120
+    X0 = np.concatenate([o["X0"] for o in outs])
+    assert relerr(X0 * np.sign(np.sum(X0 * ref_X, axis=0)), ref_X) < 1e-9
+    ref_book, ref_dist = cl.kmeans(X0, p["Z"][:8] * 0.3)
+    for o in outs:
+        assert o["book"].shape == ref_book.shape and relerr(o["book"], ref_book) < 1e-9
+        assert float(o["distortion"]) == pytest.approx(float(ref_dist), rel=1e-9)
 
 
 def test_two_ranks_one_gpu_gloo(tmp_path):
