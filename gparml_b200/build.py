@@ -13,12 +13,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libgparml_b200.so")
-SOURCES = ["capi.cu", "prep.cu", "psi1.cu", "psi2.cu", "psi2_f32.cu", "embed.cu", "global_step.cu", "global_step_large.cu", "misc.cu", "init.cu"]
+SOURCES = ["capi.cu", "prep.cu", "psi1.cu", "psi2.cu", "psi2_f32.cu", "embed.cu", "embed_x.cu", "global_step.cu", "global_step_large.cu", "misc.cu", "init.cu"]
 HEADERS = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cuh")] + [
     os.path.join(os.path.dirname(HERE), "include", "gparml_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
+EXTRA_FLAGS = {}     # per-source extra nvcc flags
 
 
 def _newer(target, deps):
@@ -33,7 +34,7 @@ def _compile(src, verbose):
     path = os.path.join(CSRC, src)
     if _newer(obj, [path] + HEADERS):
         return obj, ""
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+    cmd = [NVCC] + FLAGS + EXTRA_FLAGS.get(src, []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))

@@ -131,6 +131,8 @@ struct gparml_ctx {
     int2 *pair_idx = nullptr;   // (P) (m, m')
     double *pair_lk = nullptr;  // (P) -1/4 sum_q alpha_q (z_mq - z_m'q)^2
     double2 *pair_g = nullptr;  // (P) (lk, Gs) for embed_grads
+    double2 *pair_h = nullptr;  // (P) (lk + log|Gs|, sign(Gs)) for the expanded-basis embed_grads kernel
+    double2 *pair_zz = nullptr; // (P, Q) (zbar_q - center_q, (zbar_q - center_q)^2) for embed_grads
 
     // statistics
     StatLayout L;

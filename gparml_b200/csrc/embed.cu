@@ -36,27 +36,7 @@
 #include "common.cuh"
 #include "gp_exp.cuh"
 
-#ifndef EMB_THREADS
-#define EMB_THREADS 128
-#endif
-#ifndef EMB_MINB_LOWQ
-#define EMB_MINB_LOWQ 4        // resident CTAs per SM targeted for Q <= 10 (B200, Q=10: 3 -> 7.88 ms, 4 -> 7.51 ms at N=250k)
-#endif
-#ifndef EMB_UNROLL
-#define EMB_UNROLL 2           // pairs in flight per thread (7.51 -> 7.38 ms)
-#endif
-#define EMB_MAX_SPLITS 32
-
-struct EmbedParams {
-    const double *rec1, *rec2, *Y, *Z, *G1;
-    const double2 *pair_g;
-    int64_t n;           // points in the shard (stride of the partial buffers)
-    int64_t i0, i1;      // this launch covers points [i0, i1)
-    int M, D;
-    int m_bounds[EMB_MAX_SPLITS + 1];
-    double *partial;     // [splits][n][2Q + 1]  (AM, AS, AH)
-    double *psi1_part;   // [n][2Q + 1]          (sum_m h1 ad, sum_m h1 ad^2, sum_m h1),  h1 = B Psi1
-};
+#include "embed.cuh"
 
 #ifdef GP_USE_LIBM_EXP
 #define EMB_EXP(x) exp(x)
@@ -175,6 +155,26 @@ embed_psi2_kernel(EmbedParams p)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Expanded-basis Psi2 part (the fp64 default; kernel in embed_x.cu).  With mc = mu - center,
+// zc = zbar - center:
+//   -sum_q w_q (mc_q - zc_q)^2 = -sum_q w_q mc_q^2 + sum_q (2 w_q mc_q) zc_q - sum_q w_q zc_q^2
+// so the exponent of a (point, pair) is a dot product of the per-point vector (A_q = 2 w mc, W_q = w;
+// registers) with the per-pair vector (zc_q, zc_q^2; pair_zz table): 2Q FMAs.  The accumulators
+// are kept in the pair basis too,
+//   AH = sum_p h,  BZ_q = sum_p h zc_q,  BZZ_q = sum_p h zc_q^2          (h = Gs Psi2_n)
+//   sum_p h wd_q   = w_q (mc_q AH - BZ_q)
+//   sum_p h wd_q^2 = w_q^2 (mc_q^2 AH - 2 mc_q BZ_q + BZZ_q)            (embed_finish, basis 1)
+// another 2Q FMAs; with Gs folded into the exponent (pair_h: lk + log|Gs| and the sign, applied by an
+// integer XOR) 4Q + 11 FP64 instructions per (point, pair) instead of 5Q + 12.  Centring on the
+// column means of Z keeps the cancellation in these differences at the scale of the spread of Z,
+// not of its offset from the origin.  The pair table (P x 2Q doubles, 808 kB at M = 100, Q = 10) does
+// not fit shared memory: every CTA walks its pair range in order and stages it through a ring of
+// 1-D bulk async copies (TMA unit, SASS UBLKCP) guarded by mbarriers, together with the matching
+// pair_h entries; all reads are shared-memory broadcasts feeding the NP points of a thread.
+// Grid = (point tiles) x (pair-range splits), split partials combined in a fixed order.
+// ---------------------------------------------------------------------------------------------
+
 // Psi1 side (partial_terms.py:388-390, 421-423): h1 = B[n,m] Psi1[n,m];
 //   out[q] = sum_m h1 ad_q,  out[Q+q] = sum_m h1 ad_q^2,  out[2Q] = sum_m h1
 template <int Q>
@@ -240,7 +240,8 @@ __global__ void __launch_bounds__(256) embed_finish_kernel(const double *__restr
                                                            const double *__restrict__ rec1, const double *__restrict__ rec2,
                                                            const double *__restrict__ s_pos, const double *__restrict__ s_sig,
                                                            double *__restrict__ gx_mu, double *__restrict__ gx_s,
-                                                           double *__restrict__ grad_latest)
+                                                           double *__restrict__ grad_latest, int basis,
+                                                           const GlobalsDev *__restrict__ glob)
 {
     const int64_t loc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (loc >= cnt * Q) return;
@@ -258,8 +259,17 @@ __global__ void __launch_bounds__(256) embed_finish_kernel(const double *__restr
     const double *p1 = psi1_part + (size_t)i * W;
     const double mu = rec2[i * R + 2 * q], w = rec2[i * R + 2 * q + 1], a = rec1[i * R + 2 * q + 1];
     const double S = s_pos[idx];
-    const double gmu = -mu - p1[q] - 2.0 * sqrt(w) * am;
-    const double gs = -0.5 * (1.0 - 1.0 / S) + 0.5 * (p1[Q + q] - a * p1[2 * Q]) + w * (2.0 * as - ah);
+    double t1, t2;     // sum_p h wd_q,  sum_p h wd_q^2
+    if (basis == 0) {  // sqrt(w) basis: am = sum_p h u_q, as = sum_p h u_q^2
+        t1 = sqrt(w) * am;
+        t2 = w * as;
+    } else {           // expanded basis: am = sum_p h zc_q, as = sum_p h zc_q^2
+        const double mc = mu - glob->center[q];
+        t1 = w * fma(mc, ah, -am);
+        t2 = w * (w * fma(mc, fma(mc, ah, -2.0 * am), as));
+    }
+    const double gmu = -mu - p1[q] - 2.0 * t1;
+    const double gs = -0.5 * (1.0 - 1.0 / S) + 0.5 * (p1[Q + q] - a * p1[2 * Q]) + (2.0 * t2 - w * ah);
     gx_mu[idx] = gmu;
     gx_s[idx] = gs;
     grad_latest[idx] = -gmu;
@@ -268,30 +278,9 @@ __global__ void __launch_bounds__(256) embed_finish_kernel(const double *__restr
 
 int gp_launch_embed_psi2_f32(gparml_ctx *c, const int *m_bounds, int splits, double *partial, int64_t i0, int64_t i1);
 
-template <int Q>
-static int launch_q(gparml_ctx *c, int64_t i0, int64_t i1)
+// fewest splits of the reduction range that fill whole waves of resident CTAs
+static int pick_splits(int64_t ntiles, int64_t slots, int max_splits)
 {
-    const int64_t cnt = i1 - i0;
-    const size_t smem = (size_t)c->M * Q * sizeof(double);
-    // pair table in shared memory when it fits twice per SM next to Z / 2 (M <= ~110)
-    const size_t smem_ps = (((size_t)c->M * Q + 1) & ~(size_t)1) * sizeof(double) + (size_t)c->L.P * sizeof(double2);
-#ifdef EMB_NO_PAIR_SMEM
-    const bool ps = false;
-#else
-    const bool ps = smem_ps <= (size_t)100 * 1024;
-#endif
-    const size_t smem2 = ps ? smem_ps : smem;
-    GP_CUDA(cudaFuncSetAttribute(embed_psi2_kernel<Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ps > 200 * 1024 ? 200 * 1024 : (int)smem_ps));
-    GP_CUDA(cudaFuncSetAttribute(embed_psi2_kernel<Q, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GP_CUDA(cudaFuncSetAttribute(embed_psi1_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 1;
-    if (ps) GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, embed_psi2_kernel<Q, true>, EMB_THREADS, smem2));
-    else GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, embed_psi2_kernel<Q, false>, EMB_THREADS, smem2));
-    if (occ < 1) occ = 1;
-    const int64_t per_cta = (int64_t)EMB_THREADS * EmbCfg<Q>::NP;
-    const int64_t ntiles = (cnt + per_cta - 1) / per_cta;
-    const int64_t slots = (int64_t)c->sm_count * occ;
-    int max_splits = c->M < EMB_MAX_SPLITS ? c->M : EMB_MAX_SPLITS;
     int best = 1;
     double best_eff = -1.0;
     for (int s = 1; s <= max_splits; ++s) {
@@ -301,11 +290,55 @@ static int launch_q(gparml_ctx *c, int64_t i0, int64_t i1)
         if (eff > best_eff + 0.02) { best_eff = eff; best = s; }   // prefer fewer splits unless clearly better
         if (waves >= 8) break;
     }
-    const int splits = best;
+    return best;
+}
+
+template <int Q>
+static int launch_q(gparml_ctx *c, int64_t i0, int64_t i1)
+{
+    const int64_t cnt = i1 - i0;
+    const size_t smem = (size_t)c->M * Q * sizeof(double);
+    const bool fp32 = (c->flags & GPARML_FLAG_FP32_MAP) != 0;
+#ifdef EMB_SQRTW_BASIS
+    const bool expanded = false;
+#else
+    const bool expanded = !fp32;
+#endif
+    // sqrt(w)-basis kernel: pair table in shared memory when it fits twice per SM next to Z / 2 (M <= ~110)
+    const size_t smem_ps = (((size_t)c->M * Q + 1) & ~(size_t)1) * sizeof(double) + (size_t)c->L.P * sizeof(double2);
+#ifdef EMB_NO_PAIR_SMEM
+    const bool ps = false;
+#else
+    const bool ps = smem_ps <= (size_t)100 * 1024;
+#endif
+    const size_t smem2 = ps ? smem_ps : smem;
+    GP_CUDA(cudaFuncSetAttribute(embed_psi1_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1, np = 1;
+    if (expanded) {
+        np = gp_embed_psi2x_points_per_cta(Q) / EMB_THREADS;
+        GP_TRY(gp_embed_psi2x_occupancy(Q, &occ));
+    } else if (!fp32) {
+        np = EmbCfg<Q>::NP;
+        GP_CUDA(cudaFuncSetAttribute(embed_psi2_kernel<Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ps > 200 * 1024 ? 200 * 1024 : (int)smem_ps));
+        GP_CUDA(cudaFuncSetAttribute(embed_psi2_kernel<Q, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (ps) GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, embed_psi2_kernel<Q, true>, EMB_THREADS, smem2));
+        else GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, embed_psi2_kernel<Q, false>, EMB_THREADS, smem2));
+    } else {
+        occ = 4;
+    }
+    if (occ < 1) occ = 1;
+    const int64_t per_cta = (int64_t)EMB_THREADS * np;
+    const int64_t ntiles = (cnt + per_cta - 1) / per_cta;
+    const int64_t slots = (int64_t)c->sm_count * occ;
+    const int64_t Pn = c->L.P;
+    int max_splits = c->M < EMB_MAX_SPLITS ? c->M : EMB_MAX_SPLITS;
+    if (expanded && Pn / 64 < max_splits) max_splits = (int)(Pn / 64 > 0 ? Pn / 64 : 1);   // >= 64 pairs per split
+    const int splits = pick_splits(ntiles, slots, max_splits);
     EmbedParams p;
     p.rec1 = c->rec1; p.rec2 = c->rec2; p.Y = c->Y; p.Z = c->Z; p.G1 = c->g_1; p.pair_g = c->pair_g;
+    p.pair_zz = c->pair_zz; p.pair_h = c->pair_h; p.glob = c->d_glob;
     p.n = c->n; p.i0 = i0; p.i1 = i1; p.M = c->M; p.D = c->D;
-    // split the m range so that every split owns about P / splits pairs (row m has M - m pairs)
+    // row splits: every split owns about P / splits pairs (row m has M - m pairs)
     const double P = (double)c->L.P;
     p.m_bounds[0] = 0;
     int m = 0;
@@ -317,24 +350,29 @@ static int launch_q(gparml_ctx *c, int64_t i0, int64_t i1)
         p.m_bounds[s] = m;
     }
     p.m_bounds[splits] = c->M;
+    for (int s = 0; s <= splits; ++s) p.p_bounds[s] = (int)(Pn * s / splits);   // pair splits
     const size_t W = 2 * Q + 1;
     GP_TRY(gp_ensure_ws(c, (size_t)(splits + 1) * c->n * W * sizeof(double)));
     p.partial = c->ws;
     p.psi1_part = c->ws + (size_t)splits * c->n * W;
     embed_psi1_kernel<Q><<<(unsigned)((cnt + 127) / 128), 128, smem, c->stream>>>(p);
     GP_LAUNCH_CHECK(c);
-    if (c->flags & GPARML_FLAG_FP32_MAP) {               // opt-in fp32 evaluation of the Psi2 part
+    if (fp32) {                                          // opt-in fp32 evaluation of the Psi2 part
         GP_TRY(gp_launch_embed_psi2_f32(c, p.m_bounds, splits, p.partial, i0, i1));
     } else {
         dim3 grid((unsigned)ntiles, splits);
-        if (ps) embed_psi2_kernel<Q, true><<<grid, EMB_THREADS, smem2, c->stream>>>(p);
-        else embed_psi2_kernel<Q, false><<<grid, EMB_THREADS, smem2, c->stream>>>(p);
-        GP_LAUNCH_CHECK(c);
+        if (expanded) {
+            GP_TRY(gp_launch_embed_psi2x(c, p, (int)ntiles, splits));
+        } else {
+            if (ps) embed_psi2_kernel<Q, true><<<grid, EMB_THREADS, smem2, c->stream>>>(p);
+            else embed_psi2_kernel<Q, false><<<grid, EMB_THREADS, smem2, c->stream>>>(p);
+            GP_LAUNCH_CHECK(c);
+        }
     }
     const int64_t total = cnt * Q;
     embed_finish_kernel<<<(int)((total + 255) / 256), 256, 0, c->stream>>>(c->ws, splits, p.psi1_part, c->n, i0, cnt, Q, gp_rec_len(Q), c->rec1,
                                                                            c->rec2, c->s_pos, c->s_sig, c->gx_mu, c->gx_s,
-                                                                           c->grad_latest);
+                                                                           c->grad_latest, expanded ? 1 : 0, c->d_glob);
     GP_LAUNCH_CHECK(c);
     return GPARML_OK;
 }

@@ -316,7 +316,7 @@ static int launch_gs(gparml_ctx *c, bool kmm_only)
     p.g_k = c->g_k; p.g_1 = c->g_1; p.g_2 = c->g_2; p.c_mat = c->c_mat;
     p.psi2_full = c->psi2_full;
     p.X = c->scratch_x; p.W = c->scratch_w;
-    p.pair_g = c->pair_g;
+    p.pair_g = c->pair_g; p.pair_h = c->pair_h;
     p.out = c->glob_out;
     p.status = c->d_status;
     if (!p.use_smem) {

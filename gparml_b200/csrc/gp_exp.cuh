@@ -32,20 +32,32 @@ __device__ __forceinline__ void gp_exp_load_table(double *tab_smem)
     for (int i = threadIdx.x; i < GP_EXP_TAB; i += blockDim.x) tab_smem[i] = gp_exp_table_const[i];
 }
 
-__device__ __forceinline__ double gp_exp(double x, const double *tab_smem)
+// sign_word: 0 or 0x80000000, XORed into the sign bit of the result (integer pipe), i.e.
+// +-exp(x) without a multiplication
+__device__ __forceinline__ double gp_exp_signed(double x, const double *tab_smem, int sign_word);
+
+__device__ __forceinline__ double gp_exp(double x, const double *tab_smem) { return gp_exp_signed(x, tab_smem, 0); }
+
+__device__ __forceinline__ double gp_exp_signed(double x, const double *tab_smem, int sign_word)
 {
     const double SHIFT = 6755399441055744.0;                  // 1.5 * 2^52: the low word of t is round(v)
     const double t = fma(x, 46.16624130844683, SHIFT);        // 32 / ln2
     const int k = __double2loint(t);
     const double kd = t - SHIFT;
     const double r = fma(kd, -0.02166084939249829, x);        // ln2 / 32
+#ifdef GP_EXP_ESTRIN      // 6 instructions, dependency depth 3 (instead of 5 / 5)
+    const double r2 = r * r;
+    const double pa = fma(r, 1.0 / 6.0, 0.5), pb = fma(r, 1.0 / 120.0, 1.0 / 24.0), pd = 1.0 + r;
+    const double p = fma(r2, fma(r2, pb, pa), pd);
+#else
     double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
     p = fma(p, r, 1.0 / 6.0);
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
+#endif
     int m = k >> 5;
     m = m < -1021 ? -1021 : m;
     const double s = tab_smem[k & (GP_EXP_TAB - 1)] * p;      // in [1, 2.03)
-    return __hiloint2double(__double2hiint(s) + (m << 20), __double2loint(s));
+    return __hiloint2double((__double2hiint(s) + (m << 20)) ^ sign_word, __double2loint(s));
 }

@@ -20,7 +20,7 @@ struct GsParams {
     const double *pair_lk;
     double *kmm, *kmm_inv, *a_inv, *g_k, *g_1, *g_2, *c_mat, *psi2_full;
     double *X, *W;            // global scratch (used when !use_smem)
-    double2 *pair_g;
+    double2 *pair_g, *pair_h;
     double *out;              // [0] F, [1 .. 1+MQ+Q+2) grad (Z, sf2, alpha, beta), then [logdetK, logdetA, trKP, tr1]
     int *status;
 };
@@ -121,12 +121,15 @@ __device__ __forceinline__ void gs_tail(const GsParams &p, const double *X, cons
         grad[idx] = s;
     }
 
-    // ---- pair table for embed_grads: (lk, Gs) ----------------------------------------------------
+    // ---- pair tables for embed_grads: (lk, Gs) and (lk + log|Gs|, sign Gs) ----------------------------------------------------
     for (size_t idx = tid; idx < MM; idx += GS_THREADS) {
         const int i = (int)(idx / M), j = (int)(idx % M);
         if (j < i) continue;
         const int64_t pp = gp_pair_index(M, i, j);
         const double gs = (i == j) ? W[idx] : (W[idx] + W[(size_t)j * M + i]);
         p.pair_g[pp] = make_double2(p.pair_lk[pp], gs);
+        // h = Gs Psi2_n = +-exp(lk + log|Gs| + ...): folds the multiplication by Gs into the exponent
+        const double lg = log(fabs(gs));
+        p.pair_h[pp] = make_double2(p.pair_lk[pp] + (lg > -700.0 ? lg : -700.0), gs < 0.0 ? -1.0 : 1.0);
     }
 }

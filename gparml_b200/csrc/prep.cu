@@ -232,10 +232,12 @@ int gp_launch_prep(gparml_ctx *c)
 
 // ---------------------------------------------------------------------------
 // pair table: (m, m') indices of the upper triangle and the point-independent part
-// of the Psi2 exponent, lk = -1/4 sum_q alpha_q (z_mq - z_m'q)^2  (kernel_exp.py:143)
+// of the Psi2 exponent, lk = -1/4 sum_q alpha_q (z_mq - z_m'q)^2  (kernel_exp.py:143); for
+// embed_grads also the centred midpoints zc = (z_m + z_m')/2 - center and their squares.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pair_table_kernel(const double *__restrict__ Z, int M, int Q, const GlobalsDev *__restrict__ glob,
-                                                         int2 *__restrict__ pair_idx, double *__restrict__ pair_lk)
+                                                         int2 *__restrict__ pair_idx, double *__restrict__ pair_lk,
+                                                         double2 *__restrict__ pair_zz)
 {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)M * M) return;
@@ -249,12 +251,16 @@ __global__ void __launch_bounds__(256) pair_table_kernel(const double *__restric
     const int64_t p = gp_pair_index(M, a, b);
     pair_idx[p] = make_int2(a, b);
     pair_lk[p] = -0.25 * s;
+    for (int q = 0; q < Q; ++q) {
+        const double zc = 0.5 * (Z[a * Q + q] + Z[b * Q + q]) - glob->center[q];
+        pair_zz[p * Q + q] = make_double2(zc, zc * zc);
+    }
 }
 
 int gp_launch_pair_table(gparml_ctx *c)
 {
     const int64_t total = (int64_t)c->M * c->M;
-    pair_table_kernel<<<(int)((total + 255) / 256), 256, 0, c->stream>>>(c->Z, c->M, c->Q, c->d_glob, c->pair_idx, c->pair_lk);
+    pair_table_kernel<<<(int)((total + 255) / 256), 256, 0, c->stream>>>(c->Z, c->M, c->Q, c->d_glob, c->pair_idx, c->pair_lk, c->pair_zz);
     GP_LAUNCH_CHECK(c);
     return GPARML_OK;
 }

@@ -19,12 +19,16 @@ CSRC = os.path.join(ROOT, "gparml_b200", "csrc")
 VDIR = os.path.join(ROOT, "gparml_b200", "variants")
 NVCC = "/usr/local/cuda/bin/nvcc"
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
-ALL = ["capi.cu", "prep.cu", "psi1.cu", "psi2.cu", "psi2_f32.cu", "embed.cu", "global_step.cu", "global_step_large.cu", "misc.cu"]
+from gparml_b200.build import SOURCES as ALL  # noqa: E402
 
 # name -> {source: [defines]}
 VARIANTS = {
     "base": {},
-    "em_nops": {"embed.cu": ["EMB_NO_PAIR_SMEM"]},
+    "em_sqrtw": {"embed.cu": ["EMB_SQRTW_BASIS"]},
+    "emx_O1": {"embed_x.cu": ["-Xptxas", "-O1"]},
+    "emx_pf2": {"embed_x.cu": ["EMBX_PF=2"]},
+    "emx_pf5": {"embed_x.cu": ["EMBX_PF=5"]},
+    "emx_cp32": {"embed_x.cu": ["EMBX_CP=32", "EMBX_STAGES=3"]},
 }
 
 
@@ -40,7 +44,7 @@ def build(names=None):
         log = []
         for src, defs in spec.items():
             o = os.path.join(VDIR, "%s_%s.o" % (name, src.replace(".cu", "")))
-            cmd = [NVCC] + FLAGS + ["-Xptxas", "-v"] + ["-D" + d for d in defs] + ["-c", os.path.join(CSRC, src), "-o", o]
+            cmd = [NVCC] + FLAGS + ["-Xptxas", "-v"] + [d if d.startswith("-") else "-D" + d for d in defs] + ["-c", os.path.join(CSRC, src), "-o", o]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if r.returncode != 0:
                 print("variant %s failed:\n%s" % (name, r.stderr[-3000:]))
