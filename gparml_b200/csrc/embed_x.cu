@@ -8,11 +8,12 @@
 //     register reads takes 3 cycles (tools/micro/dfma_regbw.cu on B200: 3 fresh 66 %, one operand
 //     from the reuse cache 83 %, two 91 % of the DFMA peak).  The operand-reuse cache only serves
 //     the instruction issued directly after the one that loaded it, in the same operand slot;
-//   * ptxas -O3 reorders the FMAs of a loop body for latency, not for operand reuse (the compiler-
-//     scheduled version of this kernel ran at 67 % of the pipe, i.e. at the 3-fresh-operand rate).
+//   * ptxas keeps the FMA order of the source where latency does not force a change, and flags
+//     operand reuse between neighbours, so the source below is written in the intended issue order
+//     (the same arithmetic written q-outer / v-inner ran at 67 % of the pipe, this order at 74 %;
+//     ptxas -O1 was tried and schedules worse).
 //
-// So this translation unit is compiled with `-Xptxas -O1`, which keeps the instruction order of
-// the source, and the source is written in issue order:
+// Order of one loop iteration (pair j accumulates while the exponent of pair j+1 is evaluated):
 //   block E  (exponent of pair j+1): per latent dimension q the 2 NP FMAs are ordered
 //            (z.x, v=0) (z.x, v=1) (z.y, v=1) (z.y, v=0): every second FMA takes z from the
 //            reuse cache; 2 NP dependent chains, the same chain recurs every 2 NP instructions;

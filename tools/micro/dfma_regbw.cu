@@ -11,6 +11,10 @@
 template <int MODE>
 __global__ void __launch_bounds__(256) k(int iters, const double *in, double *sink)
 {
+    __shared__ double2 sm[64];
+    if (threadIdx.x < 64) sm[threadIdx.x] = make_double2(in[threadIdx.x & 31], in[(threadIdx.x + 7) & 31]);
+    __syncthreads();
+    int kk = threadIdx.x;
     double acc[16], u[8], v[8];
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = in[i] + threadIdx.x;
@@ -26,6 +30,29 @@ __global__ void __launch_bounds__(256) k(int iters, const double *in, double *si
         } else if (MODE == 2) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc[i] = fma(u[i & 7], v[(i * 3 + 1) & 7], acc[i]);
+        } else if (MODE == 4) {       // same register in two operand slots
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = fma(u[i & 7], u[i & 7], acc[i]);
+        } else if (MODE == 5) {       // mode 3 + one broadcast LDS.128 per 4 DFMAs feeding the next group
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const double2 w = sm[(it + a) & 63];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int bb = (a & 1) ? 3 - b : b;
+                    acc[a * 4 + bb] = fma((b & 2) ? w.x : w.y, v[bb], acc[a * 4 + bb]);
+                }
+            }
+        } else if (MODE == 6) {       // mode 3 + 4 integer instructions per 4 DFMAs
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                kk = (kk * 5 + a) ^ (kk >> 3);
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int bb = (a & 1) ? 3 - b : b;
+                    acc[a * 4 + bb] = fma(u[a], v[bb], acc[a * 4 + bb]);
+                }
+            }
         } else {
             // 4 x 4 grid of (u, v) pairs walked boustrophedon: neighbours share u or v
 #pragma unroll
@@ -40,7 +67,7 @@ __global__ void __launch_bounds__(256) k(int iters, const double *in, double *si
     double s = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) s += acc[i];
-    if (s == 123.456) sink[0] = s;
+    if (s == 123.456 || kk == 12345) sink[0] = s;
 }
 
 template <int MODE>
@@ -69,6 +96,9 @@ int main()
         run<1>(p.multiProcessorCount, w, in, sink);
         run<2>(p.multiProcessorCount, w, in, sink);
         run<3>(p.multiProcessorCount, w, in, sink);
+        run<4>(p.multiProcessorCount, w, in, sink);
+        run<5>(p.multiProcessorCount, w, in, sink);
+        run<6>(p.multiProcessorCount, w, in, sink);
     }
     return 0;
 }

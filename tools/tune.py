@@ -24,11 +24,8 @@ from gparml_b200.build import SOURCES as ALL  # noqa: E402
 # name -> {source: [defines]}
 VARIANTS = {
     "base": {},
-    "em_sqrtw": {"embed.cu": ["EMB_SQRTW_BASIS"]},
-    "emx_O1": {"embed_x.cu": ["-Xptxas", "-O1"]},
-    "emx_pf2": {"embed_x.cu": ["EMBX_PF=2"]},
-    "emx_pf5": {"embed_x.cu": ["EMBX_PF=5"]},
-    "emx_cp32": {"embed_x.cu": ["EMBX_CP=32", "EMBX_STAGES=3"]},
+    "emx_seq": {"embed_x.cu": ["EMBX_SEQ"]},
+    "emx_seq_estrin": {"embed_x.cu": ["EMBX_SEQ", "GP_EXP_ESTRIN"]},
 }
 
 
