@@ -248,8 +248,21 @@ static int launch_qdc(gparml_ctx *c, Psi1Params &p, int dchunks)
     return GPARML_OK;
 }
 
+// used by psi1_mma.cu: partial [splits][M (1+2Q)][D] in c->ws -> packed statistics
+void gp_psi1_reduce(gparml_ctx *c, int splits)
+{
+    const int64_t total = (int64_t)c->M * (1 + 2 * c->Q) * c->D;
+    psi1_reduce_kernel<<<(int)((total + 255) / 256), 256, 0, c->stream>>>(
+        c->ws, splits, c->M, c->Q, c->D, c->d_glob, c->stats, c->L.off_p1y, c->L.off_d1z, c->L.off_d1a);
+}
+
+int gp_launch_psi1_stats_mma(gparml_ctx *c);
+
 int gp_launch_psi1_stats(gparml_ctx *c)
 {
+#ifndef PSI1_LEGACY
+    return gp_launch_psi1_stats_mma(c);
+#endif
     Psi1Params p;
     p.rec1 = c->rec1; p.Y = c->Y; p.Z = c->Z;
     p.n = c->n; p.M = c->M; p.Q = c->Q; p.D = c->D; p.R = gp_rec_len(c->Q);

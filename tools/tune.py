@@ -24,8 +24,7 @@ from gparml_b200.build import SOURCES as ALL  # noqa: E402
 # name -> {source: [defines]}
 VARIANTS = {
     "base": {},
-    "emx_seq": {"embed_x.cu": ["EMBX_SEQ"]},
-    "emx_seq_estrin": {"embed_x.cu": ["EMBX_SEQ", "GP_EXP_ESTRIN"]},
+    "p1_legacy": {"psi1.cu": ["PSI1_LEGACY"]},
 }
 
 
