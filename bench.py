@@ -383,11 +383,18 @@ def main():
                 "peak_source": "pure-DFMA probe kernel measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                 "peak_nominal": 148 * 64 * 2 * 1.965e9 / 1e12,
                 "algorithmic_ops_per_launch": w_psi2, "launch_ms": med.get("psi2_stats"),
-                "ops_rule": "FP64-pipe lane-ops, FMA=1, exp=18: n_local * P * (6Q+20), TFLOP/s = 2*ops/t (SURVEY.md 8d)"}
+                "ops_rule": "FP64-pipe lane-ops, FMA=1, exp=18: n_local * P * (6Q+20), TFLOP/s = 2*ops/t (SURVEY.md 8d)",
+                # what the kernel actually issues (table-driven exp = 9): the FP64-pipe busy fraction
+                "executed_ops_per_launch": n_loc * P * (6 * Q + 11),
+                "executed_frac": (n_loc * P * (6 * Q + 11) / t_psi2 / dfma) if t_psi2 > 0 and dfma > 0 else None}
     if not fixed and med.get("embed_grads", 0) > 0:
         t_emb = med["embed_grads"] * 1e-3
+        x_emb = n_loc * (P * (4 * Q + 11) + M * (6 * Q + 12 + 2 * D))
         roofline["embed_grads"] = {"achieved": 2.0 * w_emb / t_emb / 1e12, "frac": (2.0 * w_emb / t_emb / 1e12) / peak,
-                                   "launch_ms": med["embed_grads"], "algorithmic_ops_per_launch": w_emb}
+                                   "launch_ms": med["embed_grads"], "algorithmic_ops_per_launch": w_emb,
+                                   "executed_ops_per_launch": x_emb, "executed_frac": x_emb / t_emb / dfma if dfma > 0 else None,
+                                   "note": "algorithmic count of SURVEY.md 8d (6Q+21 per point-pair); the expanded-basis kernel "
+                                           "issues 4Q+11, so frac can exceed the pipe-busy fraction (executed_frac)"}
     if args.fp32:
         roofline["note"] = "fp32 map kernels selected: the FP64-pipe roofline above does not describe them"
     total_ops = algorithmic_ops(N, M, Q, D, fixed)

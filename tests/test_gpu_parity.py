@@ -237,6 +237,53 @@ def test_template_paths_odd_shapes(Q, D, M):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("Q,D", [(10, 8), (10, 9), (10, 11), (10, 16), (10, 17), (4, 24), (12, 9), (16, 10)])
+def test_psi1_contraction_column_shapes(Q, D):
+    """psi1_stats column chunking: 8-wide tensor-core tiles, the DFMA remainder columns and several
+    chunks, for the wide (Q <= 10) and narrow (Q > 10) accumulator budgets; M not a multiple of 8."""
+    from gparml_b200.synthetic import make_problem
+    from oracle import c_oracle
+    M, n = 27, 531
+    p = make_problem(n, M, Q, D, seed=300 + Q + D, generic_hypers=True, with_direction=True)
+    shards = _shards_of(p, 2)
+    ref = c_oracle.evaluate(shards, p["Z"], p["sf2"], p["alpha"], p["beta"], step_size=1e-3)
+    res = _gpu_evaluate(shards, p["Z"], p["sf2"], p["alpha"], p["beta"], step_size=1e-3)
+    errs = {k: relerr(res["stats"][k], v) for k, v in ref["stats"].items()}
+    errs["F"] = relerr(res["global"]["F"], ref["global"]["F"])
+    for i, (a, b) in enumerate(zip(res["grad_latest"], ref["grad_latest"])):
+        errs["grad_latest_%d" % i] = relerr(a, b)
+    print(Q, D, "max rel err %.2e at %s" % (max(errs.values()), max(errs, key=errs.get)))
+    bad = {k2: v for k2, v in errs.items() if not v <= TOL}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("offset", [30.0, 1000.0])
+def test_latent_space_far_from_origin(offset):
+    """embed_grads evaluates the Psi2 exponent in an expanded (dot-product) form centred on the column
+    means of Z; a common translation of X_mu and Z far from the origin must not cost accuracy."""
+    from gparml_b200.synthetic import make_problem
+    from oracle import c_oracle
+    M, Q, D, n = 30, 5, 3, 900
+    p = make_problem(n, M, Q, D, seed=77, generic_hypers=True, with_direction=True)
+    shift = offset * np.array([1.0, -0.5, 0.25, 2.0, -1.0])
+    X_mu = p["X_mu"] + shift
+    Z = p["Z"] + shift
+    shards = []
+    from gparml_b200.synthetic import split_rows
+    for lo, hi in split_rows(n, 2):
+        shards.append(dict(Y=p["Y"][lo:hi], X_mu=X_mu[lo:hi], X_S=p["X_S"][lo:hi], d=p["d"][:, lo:hi]))
+    ref = c_oracle.evaluate(shards, Z, p["sf2"], p["alpha"], p["beta"], step_size=1e-3)
+    res = _gpu_evaluate(shards, Z, p["sf2"], p["alpha"], p["beta"], step_size=1e-3)
+    errs = {k: relerr(res["stats"][k], v) for k, v in ref["stats"].items()}
+    for key in ("F", "grad_Z", "grad_alpha", "grad_sf2", "grad_beta"):
+        errs[key] = relerr(res["global"][key], ref["global"][key])
+    for i, (a, b) in enumerate(zip(res["grad_latest"], ref["grad_latest"])):
+        errs["grad_latest_%d" % i] = relerr(a, b)
+    print(offset, "max rel err %.2e at %s" % (max(errs.values()), max(errs, key=errs.get)))
+    bad = {k2: v for k2, v in errs.items() if not v <= TOL}
+    assert not bad, bad
+
+
 def test_chunked_gradient_download_and_reupload():
     """embedding_grads_download (copy of one point range overlapping the next range's kernels) gives
     the same array as embedding_grads + download for any chunk count; re-uploading a different shard
