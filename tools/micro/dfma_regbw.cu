@@ -20,6 +20,9 @@ __global__ void __launch_bounds__(256) k(int iters, const double *in, double *si
     for (int i = 0; i < 16; ++i) acc[i] = in[i] + threadIdx.x;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { u[i] = in[16 + i] * threadIdx.x; v[i] = in[24 + i] * threadIdx.x; }
+    double uv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) uv[i] = in[32 + i];      // warp-uniform values: the compiler keeps them in uniform registers
     for (int it = 0; it < iters; ++it) {
         if (MODE == 0) {
 #pragma unroll
@@ -30,6 +33,12 @@ __global__ void __launch_bounds__(256) k(int iters, const double *in, double *si
         } else if (MODE == 2) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc[i] = fma(u[i & 7], v[(i * 3 + 1) & 7], acc[i]);
+        } else if (MODE == 7) {       // two fresh registers + one uniform-register operand
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = fma(u[i & 7], uv[(i * 3 + 1) & 7], acc[i]);
+        } else if (MODE == 8) {       // one fresh register (+ reused u0) + uniform operand
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = fma(u[0], uv[(i * 3 + 1) & 7], acc[i]);
         } else if (MODE == 4) {       // same register in two operand slots
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc[i] = fma(u[i & 7], u[i & 7], acc[i]);
@@ -99,6 +108,8 @@ int main()
         run<4>(p.multiProcessorCount, w, in, sink);
         run<5>(p.multiProcessorCount, w, in, sink);
         run<6>(p.multiProcessorCount, w, in, sink);
+        run<7>(p.multiProcessorCount, w, in, sink);
+        run<8>(p.multiProcessorCount, w, in, sink);
     }
     return 0;
 }
