@@ -175,17 +175,26 @@ embed_psi2_kernel(EmbedParams p)
 // Grid = (point tiles) x (pair-range splits), split partials combined in a fixed order.
 // ---------------------------------------------------------------------------------------------
 
-// Psi1 side (partial_terms.py:388-390, 421-423): h1 = B[n,m] Psi1[n,m];
+// Psi1 side (partial_terms.py:388-390, 421-423): h1 = B[n,m] Psi1[n,m], B = Y G1^T;
 //   out[q] = sum_m h1 ad_q,  out[Q+q] = sum_m h1 ad_q^2,  out[2Q] = sum_m h1
-template <int Q>
+// DR > 0: D <= DR, the point's Y row lives in registers and G1 (zero-padded to DR columns) in shared
+// memory next to Z (B200, c3: 1.39 -> see DESIGN.md); DR = 0: any D, Y and G1 read through L1.
+template <int Q, int DR>
 __global__ void __launch_bounds__(128) embed_psi1_kernel(EmbedParams p)
 {
     constexpr int R = (3 * Q + 2) & ~1;
-    extern __shared__ __align__(16) double zs[];         // [M][Q] = Z
+    constexpr int DRA = DR > 0 ? DR : 1;
+    extern __shared__ __align__(16) double zs[];         // [M][Q] = Z, then [M][DR] = G1
     __shared__ double exp_tab[GP_EXP_TAB];
     const int tid = threadIdx.x;
     const int M = p.M;
+    double *g1s = zs + (((size_t)M * Q + 1) & ~(size_t)1);
     for (int idx = tid; idx < M * Q; idx += 128) zs[idx] = p.Z[idx];
+    if (DR > 0)
+        for (int idx = tid; idx < M * DR; idx += 128) {
+            const int m = idx / DR, d = idx % DR;
+            g1s[idx] = d < p.D ? p.G1[(size_t)m * p.D + d] : 0.0;
+        }
     gp_exp_load_table(exp_tab);
     __syncthreads();
     const int64_t i = p.i0 + (int64_t)blockIdx.x * 128 + tid;
@@ -193,7 +202,7 @@ __global__ void __launch_bounds__(128) embed_psi1_kernel(EmbedParams p)
     const double2 *r1 = reinterpret_cast<const double2 *>(p.rec1 + i * R);
     const double lc1 = p.rec1[i * R + 3 * Q];
     const double *y = p.Y + i * p.D;
-    double mu[Q], a[Q], ad[Q], s1[Q], s2[Q];
+    double mu[Q], a[Q], ad[Q], s1[Q], s2[Q], yr[DRA];
     double s0 = 0.0;
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
@@ -203,6 +212,8 @@ __global__ void __launch_bounds__(128) embed_psi1_kernel(EmbedParams p)
         s1[q] = 0.0;
         s2[q] = 0.0;
     }
+#pragma unroll
+    for (int d = 0; d < DR; ++d) yr[d] = d < p.D ? y[d] : 0.0;
     for (int m = 0; m < M; ++m) {
         const double *z = zs + m * Q;
         double e = lc1;
@@ -212,9 +223,19 @@ __global__ void __launch_bounds__(128) embed_psi1_kernel(EmbedParams p)
             ad[q] = a[q] * d;
             e = fma(-0.5 * ad[q], d, e);
         }
-        double b = 0.0;
-        const double *g1 = p.G1 + (size_t)m * p.D;
-        for (int d = 0; d < p.D; ++d) b = fma(y[d], g1[d], b);
+        double b = 0.0, b2 = 0.0;
+        if (DR > 0) {
+            const double *g1 = g1s + m * DR;
+#pragma unroll
+            for (int d = 0; d < DR; ++d) {
+                if (d & 1) b2 = fma(yr[d], g1[d], b2);
+                else b = fma(yr[d], g1[d], b);
+            }
+            b += b2;
+        } else {
+            const double *g1 = p.G1 + (size_t)m * p.D;
+            for (int d = 0; d < p.D; ++d) b = fma(y[d], g1[d], b);
+        }
         const double h1 = b * EMB_EXP(e);
         s0 += h1;
 #pragma unroll
@@ -231,6 +252,16 @@ __global__ void __launch_bounds__(128) embed_psi1_kernel(EmbedParams p)
         out[Q + q] = s2[q];
     }
     out[2 * Q] = s0;
+}
+
+template <int Q, int DR>
+static int launch_psi1_part(gparml_ctx *c, const EmbedParams &p, int64_t cnt)
+{
+    const size_t smem = ((((size_t)c->M * Q + 1) & ~(size_t)1) + (size_t)c->M * DR) * sizeof(double);
+    GP_CUDA(cudaFuncSetAttribute(embed_psi1_kernel<Q, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    embed_psi1_kernel<Q, DR><<<(unsigned)((cnt + 127) / 128), 128, smem, c->stream>>>(p);
+    GP_LAUNCH_CHECK(c);
+    return GPARML_OK;
 }
 
 // Combine the split partials and the Psi1 part, add the KL terms (partial_terms.py:385,418),
@@ -312,7 +343,6 @@ static int launch_q(gparml_ctx *c, int64_t i0, int64_t i1)
     const bool ps = smem_ps <= (size_t)100 * 1024;
 #endif
     const size_t smem2 = ps ? smem_ps : smem;
-    GP_CUDA(cudaFuncSetAttribute(embed_psi1_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1, np = 1;
     if (expanded) {
         np = gp_embed_psi2x_points_per_cta(Q) / EMB_THREADS;
@@ -355,8 +385,13 @@ static int launch_q(gparml_ctx *c, int64_t i0, int64_t i1)
     GP_TRY(gp_ensure_ws(c, (size_t)(splits + 1) * c->n * W * sizeof(double)));
     p.partial = c->ws;
     p.psi1_part = c->ws + (size_t)splits * c->n * W;
-    embed_psi1_kernel<Q><<<(unsigned)((cnt + 127) / 128), 128, smem, c->stream>>>(p);
-    GP_LAUNCH_CHECK(c);
+    {   // Psi1 side: Y row in registers / G1 in shared memory when they fit
+        const bool fits = (size_t)c->M * (Q + 16) * sizeof(double) <= (size_t)96 * 1024;
+        if (fits && c->D <= 4) GP_TRY((launch_psi1_part<Q, 4>(c, p, cnt)));
+        else if (fits && c->D <= 10) GP_TRY((launch_psi1_part<Q, 10>(c, p, cnt)));
+        else if (fits && c->D <= 16) GP_TRY((launch_psi1_part<Q, 16>(c, p, cnt)));
+        else GP_TRY((launch_psi1_part<Q, 0>(c, p, cnt)));
+    }
     if (fp32) {                                          // opt-in fp32 evaluation of the Psi2 part
         GP_TRY(gp_launch_embed_psi2_f32(c, p.m_bounds, splits, p.partial, i0, i1));
     } else {

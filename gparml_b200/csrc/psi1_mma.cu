@@ -37,7 +37,9 @@
 #include "gp_exp.cuh"
 
 #define P1M_WARPS 8
+#ifndef P1M_TP
 #define P1M_TP 16        // points per tile (4 MMA steps)
+#endif
 
 struct Psi1MParams {
     const double *rec1, *Y, *Z;
@@ -141,7 +143,11 @@ psi1_mma_kernel(Psi1MParams p)
         }
         __syncwarp();                                     // tile t visible to the whole warp
         const double *rb = wb + buf * TILE, *yb = rb + P1M_TP * RS;
+#ifdef P1M_UNROLL2
+#pragma unroll 2
+#else
 #pragma unroll 1
+#endif
         for (int st = 0; st < P1M_TP / 4; ++st) {
             if (st * 4 >= cnt) break;                     // warp-uniform
             const int pl_raw = st * 4 + kk;
