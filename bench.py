@@ -297,10 +297,11 @@ def main():
         ctx.statistics()
         if world > 1:
             dist.all_reduce(stats_view, op=dist.ReduceOp.SUM)
-        F, g = ctx.global_step()
-        if not fixed:
-            ctx.embedding_grads()
-        return F, g
+        if fixed:
+            return ctx.global_step()
+        ctx.global_step_begin()          # F and the global gradients finish on a side stream ...
+        ctx.embedding_grads()            # ... next to the embeddings map, which only needs dF/dPsi1Y, dF/dPsi2
+        return ctx.global_step_end()     # F, gradient on the host
 
     def evaluation_e2e():
         # host buffers in, host buffers out: the Y upload overlaps prep_points + psi2_stats and the
@@ -311,10 +312,11 @@ def main():
         ctx.statistics()
         if world > 1:
             dist.all_reduce(stats_view, op=dist.ReduceOp.SUM)
-        F, g = ctx.global_step()
-        if not fixed:
-            ctx.embedding_grads_into(GLp.data_ptr(), chunks=4)
-        return F, g
+        if fixed:
+            return ctx.global_step()
+        ctx.global_step_begin()
+        ctx.embedding_grads_into(GLp.data_ptr(), chunks=4)
+        return ctx.global_step_end()
 
     def timed(fn, steps, collect_phases=False):
         if world > 1:

@@ -58,6 +58,8 @@ PROTOTYPES = {
     "gparml_stats_expand": (ctypes.c_int, [_vp, ctypes.POINTER(NamedStats)]),
     "gparml_stats_set_named": (ctypes.c_int, [_vp, ctypes.POINTER(NamedStats)]),
     "gparml_global_step": (ctypes.c_int, [_vp, _vp, _vp]),
+    "gparml_global_step_begin": (ctypes.c_int, [_vp]),
+    "gparml_global_step_end": (ctypes.c_int, [_vp, _vp, _vp]),
     "gparml_update_global_statistics": (ctypes.c_int, [_vp]),
     "gparml_embedding_grads": (ctypes.c_int, [_vp]),
     "gparml_embedding_grads_download": (ctypes.c_int, [_vp, _vp, ctypes.c_int]),

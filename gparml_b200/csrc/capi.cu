@@ -38,6 +38,17 @@ extern "C" int gparml_device_count(void)
         GP_CUDA(cudaSetDevice((c)->device));          \
     } while (0)
 
+// A gparml_global_step_begin whose _end has not been called yet still reads Z, the globals and the
+// statistics on its side stream: entry points that overwrite those finish it first.
+static int finish_pending_gs(gparml_ctx *c)
+{
+    if (c && c->gs_pending) {
+        const int r = gparml_global_step_end(c, nullptr, nullptr);
+        if (r != GPARML_OK && r != GPARML_ERR_NOT_PD && r != GPARML_ERR_RANGE) return r;
+    }
+    return GPARML_OK;
+}
+
 template <typename T>
 static int dev_alloc(T **p, size_t count)
 {
@@ -91,7 +102,11 @@ extern "C" int gparml_create(gparml_ctx **out, int device, int M, int Q, int D, 
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_kmm, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_y, cudaEventDisableTiming) != cudaSuccess) { gp_set_error("copy stream create failed"); return fail(GPARML_ERR_CUDA); }
+        cudaEventCreateWithFlags(&c->ev_y, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->gs_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_gs_head, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_gs_tail, cudaEventDisableTiming) != cudaSuccess ||
+        cudaMallocHost((void **)&c->glob_host, ((size_t)M * Q + Q + 16) * sizeof(double)) != cudaSuccess) { gp_set_error("copy stream create failed"); return fail(GPARML_ERR_CUDA); }
     for (int i = 0; i < 8; ++i)
         if (cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming) != cudaSuccess) { gp_set_error("event create failed"); return fail(GPARML_ERR_CUDA); }
     const size_t MM = (size_t)M * M;
@@ -130,7 +145,12 @@ extern "C" int gparml_destroy(gparml_ctx *c)
                     c->d_status, c->kmm, c->kmm_inv, c->a_inv, c->g_k, c->g_1, c->g_2, c->scratch_x, c->scratch_w, c->c_mat,
                     c->glob_out, c->named_tmp, c->psi2_full, c->gsl_ws, c->rec2f, c->d_yyt};
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    if (c->gs_stream) cudaStreamSynchronize(c->gs_stream);
     for (void *p : ptrs) if (p) cudaFree(p);
+    if (c->glob_host) cudaFreeHost(c->glob_host);
+    if (c->ev_gs_head) cudaEventDestroy(c->ev_gs_head);
+    if (c->ev_gs_tail) cudaEventDestroy(c->ev_gs_tail);
+    if (c->gs_stream) cudaStreamDestroy(c->gs_stream);
     for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 8; ++i) if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
     if (c->ev_main) cudaEventDestroy(c->ev_main);
@@ -323,6 +343,7 @@ static int wait_y(gparml_ctx *c)
 extern "C" int gparml_set_globals(gparml_ctx *c, const double *Z, double sf2, const double *alpha, double beta)
 {
     CHECK_CTX(c);
+    GP_TRY(finish_pending_gs(c));
     if (!Z || !alpha) { gp_set_error("set_globals: null array"); return GPARML_ERR_ARG; }
     if (!(sf2 > 0.0) || !(beta > 0.0)) { gp_set_error("set_globals: sf2 and beta must be positive (kernels.py:57 assert)"); return GPARML_ERR_ARG; }
     memset(&c->h_glob, 0, sizeof(c->h_glob));
@@ -398,6 +419,7 @@ static int prep_if_needed(gparml_ctx *c)
 extern "C" int gparml_statistics(gparml_ctx *c)
 {
     CHECK_CTX(c);
+    GP_TRY(finish_pending_gs(c));
     if (!c->have_shard || !c->have_globals) { gp_set_error("statistics: upload_shard and set_globals first"); return GPARML_ERR_STATE; }
     GP_TRY(record(c, 0));
     GP_TRY(gp_launch_prep(c));          // always: it also rewrites the header of the packed buffer
@@ -427,6 +449,7 @@ extern "C" int gparml_stats_device_ptr(gparml_ctx *c, void **p)
 extern "C" int gparml_stats_add(gparml_ctx *c, const void *other, double scale)
 {
     CHECK_CTX(c);
+    GP_TRY(finish_pending_gs(c));
     if (!other) { gp_set_error("stats_add: null pointer"); return GPARML_ERR_ARG; }
     GP_TRY(gp_launch_stats_add(c, (const double *)other, scale));
     c->have_global_step = false;
@@ -436,6 +459,7 @@ extern "C" int gparml_stats_add(gparml_ctx *c, const void *other, double scale)
 extern "C" int gparml_stats_copy(gparml_ctx *c, const void *other)
 {
     CHECK_CTX(c);
+    GP_TRY(finish_pending_gs(c));
     if (!other) { gp_set_error("stats_copy: null pointer"); return GPARML_ERR_ARG; }
     GP_CUDA(cudaMemcpyAsync(c->stats, other, (size_t)c->L.count * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     c->have_stats = true;
@@ -446,26 +470,65 @@ extern "C" int gparml_stats_copy(gparml_ctx *c, const void *other)
 extern "C" int gparml_update_global_statistics(gparml_ctx *c)
 {
     CHECK_CTX(c);
+    GP_TRY(finish_pending_gs(c));
     if (!c->have_globals) { gp_set_error("update_global_statistics: set_globals first"); return GPARML_ERR_STATE; }
     GP_CUDA(cudaStreamWaitEvent(c->stream, c->ev_kmm, 0));     // launched by set_globals on the side stream
     return check_status(c, true);
 }
 
-extern "C" int gparml_global_step(gparml_ctx *c, double *F, double *grad)
+// The master step in two halves (include/gparml_b200.h).  _begin launches everything and returns at once:
+// the part embed_grads depends on (A^-1, dF/dPsi1Y, dF/dPsi2 -> pair tables) on the context's stream, the
+// tail (F, gradients of Z / sf2 / alpha / beta) and its download on gs_stream, where it overlaps the
+// embeddings map.  _end waits for the tail and hands out F and the gradient.
+extern "C" int gparml_global_step_begin(gparml_ctx *c)
 {
     CHECK_CTX(c);
     if (!c->have_globals) { gp_set_error("global_step: set_globals first"); return GPARML_ERR_STATE; }
+    if (c->gs_pending) GP_TRY(gparml_global_step_end(c, nullptr, nullptr));
     GP_CUDA(cudaStreamWaitEvent(c->stream, c->ev_kmm, 0));     // Kmm^-1 from the side stream
     GP_TRY(record(c, 4));
-    GP_TRY(gp_launch_global_step(c, false, c->stream));
+    bool split = false;
+    GP_TRY(gp_launch_global_step_head(c, c->stream, &split));
     GP_TRY(record(c, 5));
-    GP_TRY(check_status(c, true));
-    c->have_global_step = true;
+    GP_CUDA(cudaEventRecord(c->ev_gs_head, c->stream));
+    GP_CUDA(cudaStreamWaitEvent(c->gs_stream, c->ev_gs_head, 0));
+    if (split) GP_TRY(gp_launch_global_step_tail(c, c->gs_stream));
     const size_t ng = (size_t)c->M * c->Q + c->Q + 2;
-    if (F) GP_CUDA(cudaMemcpyAsync(F, c->glob_out, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    if (grad) GP_CUDA(cudaMemcpyAsync(grad, c->glob_out + 1, ng * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    GP_CUDA(cudaStreamSynchronize(c->stream));
+    GP_CUDA(cudaMemcpyAsync(c->glob_host, c->glob_out, (1 + ng) * sizeof(double), cudaMemcpyDeviceToHost, c->gs_stream));
+    GP_CUDA(cudaMemcpyAsync(c->glob_host + 1 + ng, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->gs_stream));
+    GP_CUDA(cudaEventRecord(c->ev_gs_tail, c->gs_stream));
+    c->have_global_step = true;
+    c->gs_pending = true;
     return GPARML_OK;
+}
+
+extern "C" int gparml_global_step_end(gparml_ctx *c, double *F, double *grad)
+{
+    CHECK_CTX(c);
+    if (!c->gs_pending) { gp_set_error("global_step_end: no global_step_begin pending"); return GPARML_ERR_STATE; }
+    c->gs_pending = false;
+    GP_CUDA(cudaEventSynchronize(c->ev_gs_tail));
+    // later work on the context's stream (next set_globals / statistics) must not overtake the tail's reads
+    GP_CUDA(cudaStreamWaitEvent(c->stream, c->ev_gs_tail, 0));
+    const size_t ng = (size_t)c->M * c->Q + c->Q + 2;
+    int st = 0;
+    memcpy(&st, c->glob_host + 1 + ng, sizeof(int));           // device status word as of the end of the head
+    if (st) {
+        GP_CUDA(cudaMemsetAsync(c->d_status, 0, sizeof(int), c->stream));
+        if (st & 4) { gp_set_error("unconstrained variance outside (-36.04, 36.04) (supporting_functions.py:154 assert)"); return GPARML_ERR_RANGE; }
+        if (st & 1) { gp_set_error("Kmm is not positive definite (Cholesky pivot <= 0)"); return GPARML_ERR_NOT_PD; }
+        gp_set_error("Kmm + beta*Psi2 is not positive definite (Cholesky pivot <= 0)");
+        return GPARML_ERR_NOT_PD;
+    }
+    if (F) *F = c->glob_host[0];
+    if (grad) memcpy(grad, c->glob_host + 1, ng * sizeof(double));
+    return GPARML_OK;
+}
+
+extern "C" int gparml_global_step(gparml_ctx *c, double *F, double *grad)
+{
+    GP_TRY(gparml_global_step_begin(c));
+    return gparml_global_step_end(c, F, grad);
 }
 
 extern "C" int gparml_embedding_grads(gparml_ctx *c)
@@ -580,6 +643,7 @@ extern "C" int gparml_download(gparml_ctx *c, int id, double *dst, int64_t count
 extern "C" int gparml_upload(gparml_ctx *c, int id, const double *src, int64_t count)
 {
     CHECK_CTX(c);
+    GP_TRY(finish_pending_gs(c));
     if (id >= GPARML_A_KMM && id != GPARML_A_KMM && id != GPARML_A_KMM_INV) { gp_set_error("upload(%d): array is read-only", id); return GPARML_ERR_ARG; }
     double *p; int64_t n;
     GP_TRY(resolve(c, id, &p, &n, true));
@@ -640,6 +704,7 @@ extern "C" int gparml_stats_expand(gparml_ctx *c, const gparml_named_stats *o)
 extern "C" int gparml_stats_set_named(gparml_ctx *c, const gparml_named_stats *in)
 {
     CHECK_CTX(c);
+    GP_TRY(finish_pending_gs(c));
     if (!in) { gp_set_error("null input struct"); return GPARML_ERR_ARG; }
     if (!c->have_globals) { gp_set_error("stats_set_named: set_globals first"); return GPARML_ERR_STATE; }
     GP_TRY(ensure_named_tmp(c));
@@ -785,6 +850,7 @@ extern "C" int gparml_grad_contract(gparml_ctx *c, int which, const double *dF_d
 extern "C" int gparml_stats_add_peer(gparml_ctx *c, gparml_ctx *other, double scale)
 {
     CHECK_CTX(c);
+    GP_TRY(finish_pending_gs(c));
     if (!other || other->L.count != c->L.count) { gp_set_error("stats_add_peer: incompatible contexts"); return GPARML_ERR_ARG; }
     GP_CUDA(cudaSetDevice(other->device));
     GP_CUDA(cudaStreamSynchronize(other->stream));

@@ -121,6 +121,11 @@ struct gparml_ctx {
     // second stream: the Y upload (needed only by psi1_stats) and the gradient download overlap compute
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_kmm = nullptr;      // Kmm / Kmm^-1 of the current globals are ready (side stream)
+    // master step split: the tail (F, hyper-parameter gradients) and its download run on gs_stream next to embed_grads
+    cudaStream_t gs_stream = nullptr;
+    cudaEvent_t ev_gs_head = nullptr, ev_gs_tail = nullptr;
+    bool gs_pending = false;           // gparml_global_step_begin without its _end
+    double *glob_host = nullptr;       // pinned staging of [F, grad]
     cudaEvent_t ev_main = nullptr, ev_y = nullptr, ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     // globals
@@ -171,6 +176,8 @@ int gp_launch_psi1_stats(gparml_ctx *c);
 int gp_launch_psi2_stats(gparml_ctx *c);
 int gp_launch_psi1_matrix(gparml_ctx *c);
 int gp_launch_global_step(gparml_ctx *c, bool kmm_only, cudaStream_t s);
+int gp_launch_global_step_head(gparml_ctx *c, cudaStream_t s, bool *split);
+int gp_launch_global_step_tail(gparml_ctx *c, cudaStream_t s);
 int gp_launch_embed_grads(gparml_ctx *c);
 int gp_launch_expand(gparml_ctx *c, double *dev_out, int which);
 int gp_launch_compact(gparml_ctx *c, const double *dev_full_psi2, const double *dev_d2z, const double *dev_d2a);

@@ -270,6 +270,17 @@ __global__ void __launch_bounds__(GS_THREADS, 1) global_step_kernel(GsParams p)
     s_kk = gp_block_sum(s_kk, red);      // <dF/dKmm, Kmm>
     s_22 = gp_block_sum(s_22, red);      // <dF/dPsi2, Psi2>
     __syncthreads();
+    if (p.phase == 1) {
+        // embed_grads needs dF/dPsi1Y (g_1) and the pair tables only: publish them and the scalars of the
+        // tail, which runs as its own kernel (global_step_tail_kernel) next to the embeddings map
+        if (tid == 0) {
+            double *extra = p.out + 1 + M * Q + Q + 2;
+            extra[0] = ldK; extra[1] = ldA; extra[2] = trKP; extra[3] = tr1;
+            extra[4] = s_ap; extra[5] = s_cpc; extra[6] = s_kk; extra[7] = s_22;
+        }
+        gs_pair_tables(p, p.g_2);
+        return;
+    }
     // the work matrices are free now: keep dF/dKmm in X and dF/dPsi2 in W for the contractions
     for (size_t idx = tid; idx < MM; idx += GS_THREADS) {
         X[idx] = p.g_k[idx];
@@ -278,12 +289,24 @@ __global__ void __launch_bounds__(GS_THREADS, 1) global_step_kernel(GsParams p)
     __syncthreads();
 
     gs_tail(p, X, W, P2, ldK, ldA, tr1, trKP, s_ap, s_cpc, s_kk, s_22, qred, ia2);
+    gs_pair_tables(p, W);
+}
+
+// phase 2: bound and hyper-parameter gradients from the partial derivatives left in global memory by
+// phase 1 (O(M^2 Q) work of one CTA; independent of embed_grads, so it runs concurrently with it)
+__global__ void __launch_bounds__(GS_THREADS, 1) global_step_tail_kernel(GsParams p)
+{
+    __shared__ double qred[32 * GP_MAX_Q];
+    __shared__ double ia2[GP_MAX_Q];
+    if (*p.status & 3) return;
+    const double *extra = p.out + 1 + p.M * p.Q + p.Q + 2;
+    gs_tail(p, p.g_k, p.g_2, p.psi2_full, extra[0], extra[1], extra[3], extra[2], extra[4], extra[5], extra[6], extra[7], qred, ia2);
 }
 
 int gp_launch_global_step_large(gparml_ctx *c, GsParams &p);
 size_t gp_global_step_large_ws_doubles(int M, int sm_count);
 
-static int launch_gs(gparml_ctx *c, bool kmm_only);
+static int launch_gs(gparml_ctx *c, bool kmm_only, int phase);
 
 // kmm_only launches go to the side stream `s` (concurrent with the statistics map), the rest to
 // the context's main stream; all helpers launch on c->stream, which is swapped for the call.
@@ -291,14 +314,37 @@ int gp_launch_global_step(gparml_ctx *c, bool kmm_only, cudaStream_t s)
 {
     cudaStream_t saved = c->stream;
     c->stream = s;
-    const int r = launch_gs(c, kmm_only);
+    const int r = launch_gs(c, kmm_only, 0);
     c->stream = saved;
     return r;
 }
 
-static int launch_gs(gparml_ctx *c, bool kmm_only)
+// phase 1 (head) on `s`; *split = true if the tail still has to be launched (gp_launch_global_step_tail)
+int gp_launch_global_step_head(gparml_ctx *c, cudaStream_t s, bool *split)
+{
+    const size_t MM = (size_t)c->M * c->M;
+    const size_t vec = (size_t)(c->M > 256 ? c->M : 256) + c->M;
+    *split = (2 * MM + vec) * sizeof(double) <= (size_t)216 * 1024;      // single-CTA path only
+    cudaStream_t saved = c->stream;
+    c->stream = s;
+    const int r = launch_gs(c, false, *split ? 1 : 0);
+    c->stream = saved;
+    return r;
+}
+
+int gp_launch_global_step_tail(gparml_ctx *c, cudaStream_t s)
+{
+    cudaStream_t saved = c->stream;
+    c->stream = s;
+    const int r = launch_gs(c, false, 2);
+    c->stream = saved;
+    return r;
+}
+
+static int launch_gs(gparml_ctx *c, bool kmm_only, int phase)
 {
     GsParams p;
+    p.phase = phase;
     p.M = c->M; p.Q = c->Q; p.D = c->D; p.P = c->L.P;
     p.n_total = (double)c->n_total;
     p.fixed_beta = (c->flags & GPARML_FLAG_FIXED_BETA) ? 1 : 0;
@@ -323,6 +369,11 @@ static int launch_gs(gparml_ctx *c, bool kmm_only)
         // M too large for one SM's shared memory: multi-kernel path on L2-resident matrices
         if (!c->gsl_ws) GP_CUDA(cudaMalloc((void **)&c->gsl_ws, gp_global_step_large_ws_doubles(c->M, c->sm_count) * sizeof(double)));
         return gp_launch_global_step_large(c, p);
+    }
+    if (phase == 2) {
+        global_step_tail_kernel<<<1, GS_THREADS, 0, c->stream>>>(p);
+        GP_LAUNCH_CHECK(c);
+        return GPARML_OK;
     }
     GP_CUDA(cudaFuncSetAttribute(global_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     global_step_kernel<<<1, GS_THREADS, smem, c->stream>>>(p);

@@ -261,6 +261,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gsl_tail_kernel(GsParams p, con
     const double ldK = gp_block_sum(v, red), ldA = gp_block_sum(w, red);
     __syncthreads();
     gs_tail(p, p.g_k, p.g_2, p.psi2_full, ldK, ldA, s[5], s[4], s[0], s[1], s[2], s[3], qred, ia2);
+    gs_pair_tables(p, p.g_2);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -13,6 +13,7 @@ struct GsParams {
     int64_t P;
     double n_total;
     int fixed_beta, kmm_only, use_smem;
+    int phase;                // 0: whole master step, 1: up to dF/dPsi2 + pair tables (what embed_grads needs), 2: tail only
     const double *stats;
     int64_t off_p1y, off_d1z, off_d1a, off_s0, off_tz, off_ta;
     const double *Z;
@@ -28,6 +29,25 @@ struct GsParams {
 __device__ __forceinline__ int64_t pidx(int M, int i, int j)
 {
     return (i <= j) ? gp_pair_index(M, i, j) : gp_pair_index(M, j, i);
+}
+
+// Pair tables for embed_grads from dF/dPsi2 (W, M x M, shared or global memory): (lk, Gs) and
+// (lk + log|Gs|, sign Gs).  Callable by any number of threads of one CTA.
+__device__ __forceinline__ void gs_pair_tables(const GsParams &p, const double *W)
+{
+    const int M = p.M;
+    const int tid = threadIdx.x;
+    const size_t MM = (size_t)M * M;
+    for (size_t idx = tid; idx < MM; idx += GS_THREADS) {
+        const int i = (int)(idx / M), j = (int)(idx % M);
+        if (j < i) continue;
+        const int64_t pp = gp_pair_index(M, i, j);
+        const double gs = (i == j) ? W[idx] : (W[idx] + W[(size_t)j * M + i]);
+        p.pair_g[pp] = make_double2(p.pair_lk[pp], gs);
+        // h = Gs Psi2_n = +-exp(lk + log|Gs| + ...): folds the multiplication by Gs into the exponent
+        const double lg = log(fabs(gs));
+        p.pair_h[pp] = make_double2(p.pair_lk[pp] + (lg > -700.0 ? lg : -700.0), gs < 0.0 ? -1.0 : 1.0);
+    }
 }
 
 // Bound + gradients from the finished partial derivatives.  GK = dF/dKmm, G2 = dF/dPsi2 (M x M,
@@ -119,17 +139,5 @@ __device__ __forceinline__ void gs_tail(const GsParams &p, const double *X, cons
         const double *D1Z = p.stats + p.off_d1z + (int64_t)idx * D;
         for (int d = 0; d < D; ++d) s = fma(p.g_1[j * D + d], D1Z[d], s);
         grad[idx] = s;
-    }
-
-    // ---- pair tables for embed_grads: (lk, Gs) and (lk + log|Gs|, sign Gs) ----------------------------------------------------
-    for (size_t idx = tid; idx < MM; idx += GS_THREADS) {
-        const int i = (int)(idx / M), j = (int)(idx % M);
-        if (j < i) continue;
-        const int64_t pp = gp_pair_index(M, i, j);
-        const double gs = (i == j) ? W[idx] : (W[idx] + W[(size_t)j * M + i]);
-        p.pair_g[pp] = make_double2(p.pair_lk[pp], gs);
-        // h = Gs Psi2_n = +-exp(lk + log|Gs| + ...): folds the multiplication by Gs into the exponent
-        const double lg = log(fabs(gs));
-        p.pair_h[pp] = make_double2(p.pair_lk[pp] + (lg > -700.0 ? lg : -700.0), gs < 0.0 ? -1.0 : 1.0);
     }
 }

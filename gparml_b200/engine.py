@@ -259,6 +259,22 @@ class ShardContext(object):
                              "alpha": g[mq + 1:mq + 1 + self.Q].copy(), "beta": float(g[mq + 1 + self.Q]),
                              "flat": g}
 
+    def global_step_begin(self):
+        """Asynchronous first half of :meth:`global_step`: afterwards :meth:`embedding_grads` may be
+        launched; the bound and the global gradients finish on a side stream next to it."""
+        _lib.check(self._lib.gparml_global_step_begin(self._h))
+
+    def global_step_end(self):
+        """Second half: blocks until F and the global gradients are on the host; same return value as
+        :meth:`global_step`."""
+        F = np.zeros(1)
+        g = np.zeros(self.M * self.Q + self.Q + 2)
+        _lib.check(self._lib.gparml_global_step_end(self._h, _lib.ptr(F), _lib.ptr(g)))
+        mq = self.M * self.Q
+        return float(F[0]), {"Z": g[:mq].reshape(self.M, self.Q).copy(), "sf2": float(g[mq]),
+                             "alpha": g[mq + 1:mq + 1 + self.Q].copy(), "beta": float(g[mq + 1 + self.Q]),
+                             "flat": g}
+
     # -- map 2 ----------------------------------------------------------------------------
     def embedding_grads(self):
         _lib.check(self._lib.gparml_embedding_grads(self._h))
@@ -368,6 +384,12 @@ def evaluate(contexts, Z, sf2, alpha, beta, step_size=0.0, reduce_fn=None):
         root.stats_add_any(c)
     if reduce_fn is not None:
         reduce_fn(root)
+    if len(contexts) == 1 and not root.fixed_embeddings:
+        # the embeddings map only waits for the partial derivatives; F and the global gradients are
+        # finished and downloaded concurrently with it
+        root.global_step_begin()
+        root.embedding_grads()
+        return root.global_step_end()
     F, grad = root.global_step()
     if not root.fixed_embeddings:
         if len(contexts) > 1:

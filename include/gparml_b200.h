@@ -156,6 +156,17 @@ int gparml_stats_set_named(gparml_ctx *ctx, const gparml_named_stats *in);
  * M*Q + Q + 2 entries ordered Z, sf2, alpha, beta (positive domain, no softplus
  * chain).  Either may be NULL.  Returns GPARML_ERR_NOT_PD on a failed Cholesky. */
 int gparml_global_step(gparml_ctx *ctx, double *F, double *grad);
+
+/* The same master step in two halves, so that the caller can put the embeddings map between them:
+ *   gparml_global_step_begin(ctx);  gparml_embedding_grads(ctx);  gparml_global_step_end(ctx, &F, grad);
+ * _begin is asynchronous.  What embeddings_mapper needs from the master (partial_derivatives_*.npy:
+ * dF/dPsi1Y, dF/dPsi2; parallel_GPLVM.py:322-332) is produced on the context's stream; the bound and the
+ * gradients of Z, sf2, alpha, beta (parallel_GPLVM.py:336-369) are finished and downloaded on a side
+ * stream, concurrently with gparml_embedding_grads.  _end blocks until they are on the host and reports a
+ * non-positive-definite Kmm / Kmm + beta Psi2 (GPARML_ERR_NOT_PD) or a variance out of range
+ * (GPARML_ERR_RANGE).  F / grad may be NULL.  gparml_global_step == _begin followed by _end. */
+int gparml_global_step_begin(gparml_ctx *ctx);
+int gparml_global_step_end(gparml_ctx *ctx, double *F, double *grad);
 /* cache() only: Kmm and Kmm^-1 (local_MapReduce.py:383-394). */
 int gparml_update_global_statistics(gparml_ctx *ctx);
 

@@ -284,6 +284,42 @@ def test_latent_space_far_from_origin(offset):
     assert not bad, bad
 
 
+def test_split_master_step_matches_blocking_call():
+    """gparml_global_step_begin / embedding_grads / gparml_global_step_end (tail of the master step
+    concurrent with the embeddings map) gives bit-identical results to the blocking sequence, also when the
+    next evaluation is started while a begin is still pending."""
+    from gparml_b200 import _lib
+    from gparml_b200.engine import ShardContext
+    from gparml_b200.synthetic import make_problem
+    M, Q, D, n = 40, 6, 5, 3000
+    p = make_problem(n, M, Q, D, seed=11, generic_hypers=True, with_direction=True)
+    with ShardContext(M, Q, D, n) as c:
+        c.upload_shard(p["Y"], p["X_mu"], p["X_S"])
+        c.upload(_lib.A_GRAD_D, p["d"])
+        c.set_globals(p["Z"], p["sf2"], p["alpha"], p["beta"])
+        c.set_step(1e-3)
+        c.statistics()
+        F0, g0 = c.global_step()
+        c.embedding_grads()
+        gl0 = c.grad_latest()
+        for _ in range(3):
+            c.set_globals(p["Z"], p["sf2"], p["alpha"], p["beta"])
+            c.statistics()
+            c.global_step_begin()
+            c.embedding_grads()
+            F1, g1 = c.global_step_end()
+            gl1 = c.grad_latest()
+            assert F1 == F0 and np.array_equal(g1["flat"], g0["flat"]) and np.array_equal(gl1, gl0)
+        # a pending begin is finished by the next call that overwrites its inputs
+        c.global_step_begin()
+        c.set_globals(p["Z"] * 1.01, p["sf2"], p["alpha"], p["beta"])
+        c.statistics()
+        F2, _ = c.global_step()
+        assert np.isfinite(F2) and F2 != F0
+        with pytest.raises(ValueError):
+            c.global_step_end()
+
+
 def test_chunked_gradient_download_and_reupload():
     """embedding_grads_download (copy of one point range overlapping the next range's kernels) gives
     the same array as embedding_grads + download for any chunk count; re-uploading a different shard

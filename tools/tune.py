@@ -23,9 +23,7 @@ from gparml_b200.build import SOURCES as ALL  # noqa: E402
 
 # name -> {source: [defines]}
 VARIANTS = {
-    "base": {},
-    "p1m_unr2": {"psi1_mma.cu": ["P1M_UNROLL2"]},
-    "p1m_tp32": {"psi1_mma.cu": ["P1M_TP=32"]},
+    "gs_profile": {"global_step.cu": ["GS_PROFILE"]},
 }
 
 
