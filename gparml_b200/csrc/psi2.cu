@@ -62,6 +62,102 @@ template <int Q> struct Psi2Cfg {
 };
 #endif
 
+// One software-pipelined iteration for PP = 2 pairs per thread, written in issue order (see embed_x.cu for
+// the register-file argument: a DFMA with three fresh 64-bit register operands takes 3 issue cycles, one
+// with an operand from the reuse cache of the previous instruction takes 2):
+//   block E  (point i+1): per q  d0, d1 (mu shared), wd0, wd1 (w shared), e0, e1;
+//   block XA (exp of point i+1, accumulation of point i): each exp step of the two pairs is followed by
+//            half a chunk of accumulations; a chunk = two latent dimensions of one pair:
+//            g_a, g_b (wd twice: one register read), then acc1[q], acc1[q+1], acc2[q], acc2[q+1] with psi
+//            held in one operand slot (reuse) -- 2 fresh operands each after the first.
+struct Psi2Exp {
+    double x, t, r, p, tab;
+    int k;
+};
+
+template <int Q, bool DO_E, bool DO_A>
+__device__ __forceinline__ void psi2_step(const double *__restrict__ rn, const double *__restrict__ rc, const double (&lk)[2],
+                                          const double (&zb)[2][Q], double (&wdn)[2][Q], const double (&wdc)[2][Q],
+                                          const double (&psic)[2], double (&psin)[2], double (&acc)[2][1 + 2 * Q],
+                                          const double *exp_tab)
+{
+    Psi2Exp es[2];
+    if (DO_E) {
+        const double2 *r = reinterpret_cast<const double2 *>(rn);
+        const double lc2 = rn[3 * Q];
+        double e[2][2];
+        e[0][0] = lk[0]; e[1][0] = lk[1]; e[0][1] = lc2; e[1][1] = lc2;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const double2 mw = r[q];           // (mu_q, w_q), broadcast; feeds both pairs
+            const double d0 = mw.x - zb[0][q];
+            const double d1 = mw.x - zb[1][q];
+            wdn[0][q] = mw.y * d0;
+            wdn[1][q] = mw.y * d1;
+            e[0][q & 1] = fma(-wdn[0][q], d0, e[0][q & 1]);
+            e[1][q & 1] = fma(-wdn[1][q], d1, e[1][q & 1]);
+        }
+        es[0].x = e[0][0] + e[0][1];
+        es[1].x = e[1][0] + e[1][1];
+    }
+    const double2 *rv = reinterpret_cast<const double2 *>(rc) + Q;      // (v_2k, v_2k+1)
+    if (DO_A) {
+        acc[0][0] += psic[0];
+        acc[1][0] += psic[1];
+    }
+    // chunk k of pair u: latent dimensions 2k, 2k+1
+#define PSI2_CHUNK(k, u)                                                                             \
+    if (DO_A && 2 * (k) < Q) {                                                                       \
+        constexpr int qa = 2 * (k) < Q ? 2 * (k) : 0, qb = 2 * (k) + 1 < Q ? 2 * (k) + 1 : 0;        \
+        const double2 v2 = rv[(k)];                                                                  \
+        const double ga = fma(wdc[u][qa], wdc[u][qa], v2.x);                                         \
+        const double gb = fma(wdc[u][qb], wdc[u][qb], v2.y);                                         \
+        acc[u][1 + qa] = fma(psic[u], wdc[u][qa], acc[u][1 + qa]);                                   \
+        if (2 * (k) + 1 < Q) acc[u][1 + qb] = fma(psic[u], wdc[u][qb], acc[u][1 + qb]);              \
+        acc[u][1 + Q + qa] = fma(psic[u], ga, acc[u][1 + Q + qa]);                                   \
+        if (2 * (k) + 1 < Q) acc[u][1 + Q + qb] = fma(psic[u], gb, acc[u][1 + Q + qb]);              \
+    }
+#define PSI2_EXP(stmt)                                          \
+    if (DO_E) {                                                 \
+        _Pragma("unroll") for (int u = 0; u < 2; ++u) { stmt; } \
+    }
+    PSI2_EXP(es[u].t = fma(es[u].x, 46.16624130844683, 6755399441055744.0))
+    PSI2_CHUNK(0, 0)
+    PSI2_EXP(es[u].k = __double2loint(es[u].t); es[u].t = es[u].t - 6755399441055744.0)
+    PSI2_CHUNK(0, 1)
+    PSI2_EXP(es[u].r = fma(es[u].t, -0.02166084939249829, es[u].x); es[u].tab = exp_tab[es[u].k & (GP_EXP_TAB - 1)])
+    PSI2_CHUNK(1, 0)
+    PSI2_EXP(es[u].p = fma(es[u].r, 1.0 / 120.0, 1.0 / 24.0))
+    PSI2_CHUNK(1, 1)
+    PSI2_EXP(es[u].p = fma(es[u].p, es[u].r, 1.0 / 6.0))
+    PSI2_CHUNK(2, 0)
+    PSI2_EXP(es[u].p = fma(es[u].p, es[u].r, 0.5))
+    PSI2_CHUNK(2, 1)
+    PSI2_EXP(es[u].p = fma(es[u].p, es[u].r, 1.0))
+    PSI2_CHUNK(3, 0)
+    PSI2_EXP(es[u].p = fma(es[u].p, es[u].r, 1.0))
+    PSI2_CHUNK(3, 1)
+    PSI2_EXP(es[u].p = es[u].tab * es[u].p)
+    PSI2_CHUNK(4, 0)
+    PSI2_CHUNK(4, 1)
+    PSI2_CHUNK(5, 0)
+    PSI2_CHUNK(5, 1)
+    PSI2_CHUNK(6, 0)
+    PSI2_CHUNK(6, 1)
+    PSI2_CHUNK(7, 0)
+    PSI2_CHUNK(7, 1)
+#undef PSI2_CHUNK
+#undef PSI2_EXP
+    if (DO_E) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            int m = es[u].k >> 5;
+            m = m < -1021 ? -1021 : m;
+            psin[u] = __hiloint2double(__double2hiint(es[u].p) + (m << 20), __double2loint(es[u].p));
+        }
+    }
+}
+
 template <int Q>
 __global__ void __launch_bounds__(PSI2_THREADS, Psi2Cfg<Q>::MINB)
 psi2_stats_kernel(const double *__restrict__ rec2, int64_t n, const double *__restrict__ Z, int64_t P,
@@ -120,6 +216,27 @@ psi2_stats_kernel(const double *__restrict__ rec2, int64_t n, const double *__re
         const int cnt = (int)((n_hi - base < PSI2_TN) ? (n_hi - base) : PSI2_TN);
         gp_mbar_wait(&bar[s], parity);
         const double *tb = tile + (size_t)s * PSI2_TN * R;
+#ifndef PSI2_COMPILER_ORDER
+        if constexpr (PP == 2) {
+            // software pipeline over the points of the tile (psi2_step): prologue, steady state, epilogue
+            double wda[2][Q], wdb[2][Q], psa[2], psb[2];
+            if (cnt > 0) {
+                psi2_step<Q, true, false>(tb, tb, lk, zb, wda, wda, psa, psa, acc, exp_tab);
+                int i = 0;
+                for (; i + 2 < cnt; i += 2) {
+                    psi2_step<Q, true, true>(tb + (i + 1) * R, tb + i * R, lk, zb, wdb, wda, psa, psb, acc, exp_tab);
+                    psi2_step<Q, true, true>(tb + (i + 2) * R, tb + (i + 1) * R, lk, zb, wda, wdb, psb, psa, acc, exp_tab);
+                }
+                if (i + 1 < cnt) {
+                    psi2_step<Q, true, true>(tb + (i + 1) * R, tb + i * R, lk, zb, wdb, wda, psa, psb, acc, exp_tab);
+                    psi2_step<Q, false, true>(tb, tb + (i + 1) * R, lk, zb, wda, wdb, psb, psa, acc, exp_tab);
+                } else {
+                    psi2_step<Q, false, true>(tb, tb + i * R, lk, zb, wdb, wda, psa, psb, acc, exp_tab);
+                }
+            }
+        } else
+#endif
+        {
 #pragma unroll UNR
         for (int i = 0; i < cnt; ++i) {
             const double2 *r = reinterpret_cast<const double2 *>(tb + i * R);
@@ -164,6 +281,7 @@ psi2_stats_kernel(const double *__restrict__ rec2, int64_t n, const double *__re
                     }
                 }
             }
+        }
         }
         __syncthreads();      // every thread is done reading stage s
         if (tid == 0 && t + PSI2_STAGES < ntiles) {

@@ -23,7 +23,8 @@ from gparml_b200.build import SOURCES as ALL  # noqa: E402
 
 # name -> {source: [defines]}
 VARIANTS = {
-    "gs_profile": {"global_step.cu": ["GS_PROFILE"]},
+    "base": {},
+    "p2_compiler": {"psi2.cu": ["PSI2_COMPILER_ORDER"]},
 }
 
 
