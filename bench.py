@@ -27,6 +27,9 @@ import time
 
 import numpy as np
 
+# stdout carries exactly one JSON line (rank 0): NCCL's own banner / debug output goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -403,7 +406,7 @@ def main():
     roofline["whole_evaluation_frac"] = (2.0 * total_ops / world / (ms_per_step * 1e-3) / 1e12) / peak
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture of the same workload
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01c.json")))
         ent = tr.get(args.config, {}).get("psi2_stats_kernel")
         if ent and int(ent["n_local"]) == n_loc:
             roofline["traffic"] = ent["dram_bytes"]
