@@ -13,20 +13,12 @@
 //   g_mu[n,q] = -mu_nq - sum_m B Psi1 ad_q - 2 sum_p Gs Psi2_n wd_q
 //   g_S[n,q]  = -1/2 (1 - 1/S_nq) + 1/2 sum_m B Psi1 (ad_q^2 - a_nq) + sum_p Gs Psi2_n (2 wd_q^2 - w_nq)
 //
-// Psi2 part (embed_psi2_kernel, >97 % of the work).  The reduction runs over pairs for each
-// point (the opposite direction to psi2_stats), so one thread owns one point.  Because the
-// accumulators belong to a point, the per-point factor sqrt(w_nq) can be pulled out of the
-// pair loop: with sw = sqrt(w), u_q = sw_q (mu_q - zbar_q) = fma(-sw_q, z_m'q / 2, sw_q (mu_q - z_mq / 2))
-//   Psi2_n = exp(lk + lc2 - sum_q u_q^2),   h = Gs Psi2_n,
-//   AM_q = sum_p h u_q,  AS_q = sum_p h u_q^2,  AH = sum_p h
-//   sum_p Gs Psi2_n wd_q = sw_q AM_q,   sum_p Gs Psi2_n wd_q^2 = w_q AS_q
-// i.e. 2 FMAs per latent dimension for the exponent instead of sub + mul + FMA: 5Q + 12 FP64
-// instructions per (point, pair) instead of 6Q + 12.  Registers per thread: sw, sw (mu - z_m/2),
-// u, AM, AS (5Q doubles) for each of the NP = 2 points a thread owns; Z/2 and -- when it fits
-// (M <= ~110) -- the (lk, Gs) pair table sit in shared memory and are read as broadcasts that feed
-// both points (B200, N = 250k: pair table by warp-uniform global loads 6.79 ms, from shared
-// memory 6.37 ms).  Grid = (point tiles) x (splits of the m range, balanced by pair count);
-// split partials are combined in a fixed order by embed_finish.
+// Psi2 part (>97 % of the work): embed_psi2x_kernel in embed_x.cu for fp64 (expanded basis, below),
+// embed_psi2_f32_kernel in psi2_f32.cu for the opt-in fp32 path (sqrt(w) basis: u_q = sqrt(w_q) (mu_q - zbar_q),
+// partial sums AM_q = sum_p h u_q, AS_q = sum_p h u_q^2, AH = sum_p h; embed_finish basis 0).  The reduction
+// runs over pairs for each point (the opposite direction to psi2_stats), so a thread owns points.
+// Grid = (point tiles) x (splits of the pair range); split partials are combined in a fixed order by
+// embed_finish.
 //
 // Psi1 part (embed_psi1_kernel): thread per point, loop over the M inducing points.
 //
@@ -43,117 +35,6 @@
 #else
 #define EMB_EXP(x) gp_exp((x), exp_tab)
 #endif
-
-// points per thread and resident CTAs the register budget is tuned for
-#ifdef EMB_POINTS
-template <int Q> struct EmbCfg { static constexpr int NP = EMB_POINTS; static constexpr int MINB = EMB_MINB_LOWQ; };
-#else
-// B200, Q = 10, N = 250k (tools/tune.py): 1 point / 4 CTAs 6.91 ms, 2 points / 2 CTAs 6.79 ms
-// (shared-memory wavefronts per FP64 instruction halve); 3 points no longer fit the registers.
-template <int Q> struct EmbCfg {
-    static constexpr int NP = (Q <= 10) ? 2 : 1;
-    static constexpr int MINB = (Q <= 10) ? ((Q <= 4) ? 4 : 2) : ((Q <= 13) ? 2 : 1);
-};
-#endif
-
-// PS: the (lk, Gs) pair table is copied to shared memory (when P * 16 B fits next to Z / 2)
-template <int Q, bool PS>
-__global__ void __launch_bounds__(EMB_THREADS, EmbCfg<Q>::MINB)
-embed_psi2_kernel(EmbedParams p)
-{
-    constexpr int R = (3 * Q + 2) & ~1;
-    constexpr int EUNR = EMB_UNROLL;
-    extern __shared__ __align__(16) double hz[];        // [M][Q] = Z / 2
-    __shared__ double exp_tab[GP_EXP_TAB];
-    const int tid = threadIdx.x;
-    const int M = p.M;
-    for (int idx = tid; idx < M * Q; idx += EMB_THREADS) hz[idx] = 0.5 * p.Z[idx];
-    double2 *pgs = reinterpret_cast<double2 *>(hz + ((M * Q + 1) & ~1));
-    if (PS) {
-        const int64_t P = gp_pair_index(M, M - 1, M - 1) + 1;
-        for (int64_t idx = tid; idx < P; idx += EMB_THREADS) pgs[idx] = p.pair_g[idx];
-    }
-    gp_exp_load_table(exp_tab);
-    __syncthreads();
-
-    // NP points per thread (register blocking: every Z/2 and pair read feeds NP points)
-    constexpr int NP = EmbCfg<Q>::NP;
-    int64_t i[NP];
-    bool valid[NP];
-    const double2 *r2[NP];
-    double lc2[NP], sw[NP][Q], sdm[NP][Q], u[NP][Q], am[NP][Q], as[NP][Q], ah[NP];
-#pragma unroll
-    for (int v = 0; v < NP; ++v) {
-        i[v] = p.i0 + ((int64_t)blockIdx.x * NP + v) * EMB_THREADS + tid;
-        valid[v] = i[v] < p.i1;
-        if (!valid[v]) i[v] = p.i1 - 1;                  // compute on a real record, never store
-        r2[v] = reinterpret_cast<const double2 *>(p.rec2 + i[v] * R);
-        lc2[v] = p.rec2[i[v] * R + 3 * Q];
-        ah[v] = 0.0;
-#pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            sw[v][q] = sqrt(r2[v][q].y);
-            am[v][q] = 0.0;
-            as[v][q] = 0.0;
-        }
-    }
-    const int m_lo = p.m_bounds[blockIdx.y], m_hi = p.m_bounds[blockIdx.y + 1];
-
-    for (int m = m_lo; m < m_hi; ++m) {
-        const double *hm = hz + m * Q;
-        const double2 *pg = (PS ? pgs : p.pair_g) + gp_pair_index(M, m, m);
-        double2 g = PS ? pg[0] : __ldg(pg);              // first pair of the row
-#pragma unroll
-        for (int v = 0; v < NP; ++v)
-#pragma unroll
-            for (int q = 0; q < Q; ++q) sdm[v][q] = sw[v][q] * (r2[v][q].x - hm[q]);   // sw (mu - z_m / 2); mu re-read from L1
-#pragma unroll EUNR
-        for (int b = m; b < M; ++b) {
-            const int nxt = (b + 1 < M) ? (b + 1 - m) : (b - m);
-            const double2 gn = PS ? pg[nxt] : __ldg(pg + nxt);                      // next pair, warp-uniform
-            const double *hb = hz + b * Q;
-            double e0[NP], e1[NP], h[NP];
-#pragma unroll
-            for (int v = 0; v < NP; ++v) { e0[v] = g.x; e1[v] = lc2[v]; }
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                const double hbq = hb[q];
-#pragma unroll
-                for (int v = 0; v < NP; ++v) {
-                    u[v][q] = fma(-sw[v][q], hbq, sdm[v][q]);       // sw (mu - zbar)
-                    if (q & 1) e1[v] = fma(-u[v][q], u[v][q], e1[v]);
-                    else e0[v] = fma(-u[v][q], u[v][q], e0[v]);
-                }
-            }
-#pragma unroll
-            for (int v = 0; v < NP; ++v) {
-                h[v] = g.y * EMB_EXP(e0[v] + e1[v]);
-                ah[v] += h[v];
-            }
-#pragma unroll
-            for (int q = 0; q < Q; ++q)
-#pragma unroll
-                for (int v = 0; v < NP; ++v) {
-                    const double t = h[v] * u[v][q];
-                    am[v][q] += t;
-                    as[v][q] = fma(t, u[v][q], as[v][q]);
-                }
-            g = gn;
-        }
-    }
-#pragma unroll
-    for (int v = 0; v < NP; ++v) {
-        if (valid[v]) {
-            double *out = p.partial + ((size_t)blockIdx.y * p.n + i[v]) * (2 * Q + 1);
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                out[q] = am[v][q];
-                out[Q + q] = as[v][q];
-            }
-            out[2 * Q] = ah[v];
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // Expanded-basis Psi2 part (the fp64 default; kernel in embed_x.cu).  With mc = mu - center,
@@ -328,33 +209,11 @@ template <int Q>
 static int launch_q(gparml_ctx *c, int64_t i0, int64_t i1)
 {
     const int64_t cnt = i1 - i0;
-    const size_t smem = (size_t)c->M * Q * sizeof(double);
     const bool fp32 = (c->flags & GPARML_FLAG_FP32_MAP) != 0;
-#ifdef EMB_SQRTW_BASIS
-    const bool expanded = false;
-#else
-    const bool expanded = !fp32;
-#endif
-    // sqrt(w)-basis kernel: pair table in shared memory when it fits twice per SM next to Z / 2 (M <= ~110)
-    const size_t smem_ps = (((size_t)c->M * Q + 1) & ~(size_t)1) * sizeof(double) + (size_t)c->L.P * sizeof(double2);
-#ifdef EMB_NO_PAIR_SMEM
-    const bool ps = false;
-#else
-    const bool ps = smem_ps <= (size_t)100 * 1024;
-#endif
-    const size_t smem2 = ps ? smem_ps : smem;
-    int occ = 1, np = 1;
-    if (expanded) {
+    int occ = 4, np = 1;                                  // fp32 kernel: one point per thread, 4 CTAs per SM
+    if (!fp32) {
         np = gp_embed_psi2x_points_per_cta(Q) / EMB_THREADS;
         GP_TRY(gp_embed_psi2x_occupancy(Q, &occ));
-    } else if (!fp32) {
-        np = EmbCfg<Q>::NP;
-        GP_CUDA(cudaFuncSetAttribute(embed_psi2_kernel<Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ps > 200 * 1024 ? 200 * 1024 : (int)smem_ps));
-        GP_CUDA(cudaFuncSetAttribute(embed_psi2_kernel<Q, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (ps) GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, embed_psi2_kernel<Q, true>, EMB_THREADS, smem2));
-        else GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, embed_psi2_kernel<Q, false>, EMB_THREADS, smem2));
-    } else {
-        occ = 4;
     }
     if (occ < 1) occ = 1;
     const int64_t per_cta = (int64_t)EMB_THREADS * np;
@@ -362,13 +221,13 @@ static int launch_q(gparml_ctx *c, int64_t i0, int64_t i1)
     const int64_t slots = (int64_t)c->sm_count * occ;
     const int64_t Pn = c->L.P;
     int max_splits = c->M < EMB_MAX_SPLITS ? c->M : EMB_MAX_SPLITS;
-    if (expanded && Pn / 64 < max_splits) max_splits = (int)(Pn / 64 > 0 ? Pn / 64 : 1);   // >= 64 pairs per split
+    if (!fp32 && Pn / 64 < max_splits) max_splits = (int)(Pn / 64 > 0 ? Pn / 64 : 1);   // >= 64 pairs per split
     const int splits = pick_splits(ntiles, slots, max_splits);
     EmbedParams p;
     p.rec1 = c->rec1; p.rec2 = c->rec2; p.Y = c->Y; p.Z = c->Z; p.G1 = c->g_1; p.pair_g = c->pair_g;
     p.pair_zz = c->pair_zz; p.pair_h = c->pair_h; p.glob = c->d_glob;
     p.n = c->n; p.i0 = i0; p.i1 = i1; p.M = c->M; p.D = c->D;
-    // row splits: every split owns about P / splits pairs (row m has M - m pairs)
+    // row splits (fp32 kernel): every split owns about P / splits pairs (row m has M - m pairs)
     const double P = (double)c->L.P;
     p.m_bounds[0] = 0;
     int m = 0;
@@ -380,7 +239,7 @@ static int launch_q(gparml_ctx *c, int64_t i0, int64_t i1)
         p.m_bounds[s] = m;
     }
     p.m_bounds[splits] = c->M;
-    for (int s = 0; s <= splits; ++s) p.p_bounds[s] = (int)(Pn * s / splits);   // pair splits
+    for (int s = 0; s <= splits; ++s) p.p_bounds[s] = (int)(Pn * s / splits);   // pair splits (fp64 kernel)
     const size_t W = 2 * Q + 1;
     GP_TRY(gp_ensure_ws(c, (size_t)(splits + 1) * c->n * W * sizeof(double)));
     p.partial = c->ws;
@@ -392,22 +251,12 @@ static int launch_q(gparml_ctx *c, int64_t i0, int64_t i1)
         else if (fits && c->D <= 16) GP_TRY((launch_psi1_part<Q, 16>(c, p, cnt)));
         else GP_TRY((launch_psi1_part<Q, 0>(c, p, cnt)));
     }
-    if (fp32) {                                          // opt-in fp32 evaluation of the Psi2 part
-        GP_TRY(gp_launch_embed_psi2_f32(c, p.m_bounds, splits, p.partial, i0, i1));
-    } else {
-        dim3 grid((unsigned)ntiles, splits);
-        if (expanded) {
-            GP_TRY(gp_launch_embed_psi2x(c, p, (int)ntiles, splits));
-        } else {
-            if (ps) embed_psi2_kernel<Q, true><<<grid, EMB_THREADS, smem2, c->stream>>>(p);
-            else embed_psi2_kernel<Q, false><<<grid, EMB_THREADS, smem2, c->stream>>>(p);
-            GP_LAUNCH_CHECK(c);
-        }
-    }
+    if (fp32) GP_TRY(gp_launch_embed_psi2_f32(c, p.m_bounds, splits, p.partial, i0, i1));   // opt-in fp32 evaluation of the Psi2 part
+    else GP_TRY(gp_launch_embed_psi2x(c, p, (int)ntiles, splits));
     const int64_t total = cnt * Q;
     embed_finish_kernel<<<(int)((total + 255) / 256), 256, 0, c->stream>>>(c->ws, splits, p.psi1_part, c->n, i0, cnt, Q, gp_rec_len(Q), c->rec1,
                                                                            c->rec2, c->s_pos, c->s_sig, c->gx_mu, c->gx_s,
-                                                                           c->grad_latest, expanded ? 1 : 0, c->d_glob);
+                                                                           c->grad_latest, fp32 ? 0 : 1, c->d_glob);
     GP_LAUNCH_CHECK(c);
     return GPARML_OK;
 }

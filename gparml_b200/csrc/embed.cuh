@@ -5,12 +5,6 @@
 #ifndef EMB_THREADS
 #define EMB_THREADS 128
 #endif
-#ifndef EMB_MINB_LOWQ
-#define EMB_MINB_LOWQ 4        // resident CTAs per SM targeted for Q <= 10 (B200, Q=10: 3 -> 7.88 ms, 4 -> 7.51 ms at N=250k)
-#endif
-#ifndef EMB_UNROLL
-#define EMB_UNROLL 2           // pairs in flight per thread (7.51 -> 7.38 ms)
-#endif
 #define EMB_MAX_SPLITS 32
 
 struct EmbedParams {
