@@ -254,14 +254,22 @@ static int launch_q(gparml_ctx *c, Psi1MParams &p)
         const double cost = chunks * (2.0 * (6 * Q + 11) + J * (16.0 * cfgs[i].nt + 2.0 * cfgs[i].dr));
         if (best < 0 || cost < best_cost) { best = i; best_cost = cost; best_chunks = chunks; }
     }
-    // slices: one wave of P1M_WARPS warps per SM (times the column chunks), >= 4 tiles per slice
+    // slices: tasks = groups x slices x column chunks fill whole waves of P1M_WARPS warps per SM; among the
+    // slice counts up to four waves the fewest that come within 2 % of the best fill, >= 4 tiles per slice
     const int64_t warps = (int64_t)c->sm_count * P1M_WARPS;
-    int64_t S = (warps + p.G / 2) / p.G;
-    if (best_chunks > 1) S = (S + best_chunks - 1) / best_chunks;
-    const int64_t max_s = (c->n + 4 * P1M_TP - 1) / (4 * P1M_TP);
-    if (S > max_s) S = max_s;
+    const int64_t per_s = (int64_t)p.G * best_chunks;           // tasks per slice
+    int64_t max_s = (c->n + 4 * P1M_TP - 1) / (4 * P1M_TP);
     const int64_t ws_cap = ((int64_t)256 << 20) / ((int64_t)c->M * J * c->D * (int64_t)sizeof(double));
-    if (S > ws_cap) S = ws_cap;
+    if (max_s > ws_cap) max_s = ws_cap;
+    if (max_s > 4 * warps / per_s + 1) max_s = 4 * warps / per_s + 1;
+    if (max_s < 1) max_s = 1;
+    int64_t S = 1;
+    double best_eff = -1.0;
+    for (int64_t cand = 1; cand <= max_s; ++cand) {
+        const int64_t total = per_s * cand, waves = (total + warps - 1) / warps;
+        const double eff = (double)total / (double)(waves * warps);
+        if (eff > best_eff + 0.02) { best_eff = eff; S = cand; }
+    }
     if (S < 1) S = 1;
     int64_t per = (c->n + S - 1) / S;
     per = (per + P1M_TP - 1) / P1M_TP * P1M_TP;          // slices start on tile boundaries (16-byte aligned Y tiles)
