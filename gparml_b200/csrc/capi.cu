@@ -29,13 +29,24 @@ extern "C" int gparml_device_count(void)
     return n;
 }
 
-#define CHECK_CTX(c)                                  \
+// entry points that take part in the upload -> statistics pipeline (they never touch X_mu / X_S)
+#define CHECK_CTX_PIPE(c)                             \
     do {                                              \
         if (!(c)) {                                   \
             gp_set_error("null context");             \
             return GPARML_ERR_ARG;                    \
         }                                             \
         GP_CUDA(cudaSetDevice((c)->device));          \
+    } while (0)
+// every other entry point first orders the context's stream behind a row-range upload of X_mu / X_S that
+// gparml_statistics has not consumed (gparml_upload_shard sends them on the copy stream)
+#define CHECK_CTX(c)                                  \
+    do {                                              \
+        CHECK_CTX_PIPE(c);                            \
+        if ((c)->x_pending > 0) {                     \
+            GP_CUDA(cudaStreamWaitEvent((c)->stream, (c)->ev_x[(c)->x_pending - 1], 0)); \
+            (c)->x_pending = 0;                       \
+        }                                             \
     } while (0)
 
 // A gparml_global_step_begin whose _end has not been called yet still reads Z, the globals and the
@@ -109,6 +120,8 @@ extern "C" int gparml_create(gparml_ctx **out, int device, int M, int Q, int D, 
         cudaMallocHost((void **)&c->glob_host, ((size_t)M * Q + Q + 16) * sizeof(double)) != cudaSuccess) { gp_set_error("copy stream create failed"); return fail(GPARML_ERR_CUDA); }
     for (int i = 0; i < 8; ++i)
         if (cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming) != cudaSuccess) { gp_set_error("event create failed"); return fail(GPARML_ERR_CUDA); }
+    for (int i = 0; i < 4; ++i)
+        if (cudaEventCreateWithFlags(&c->ev_x[i], cudaEventDisableTiming) != cudaSuccess) { gp_set_error("event create failed"); return fail(GPARML_ERR_CUDA); }
     const size_t MM = (size_t)M * M;
 #define A_(ptr, count) if ((r = dev_alloc(&(ptr), (count))) != GPARML_OK) return fail(r)
     A_(c->Z, (size_t)M * Q);
@@ -153,6 +166,7 @@ extern "C" int gparml_destroy(gparml_ctx *c)
     if (c->gs_stream) cudaStreamDestroy(c->gs_stream);
     for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 8; ++i) if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
+    for (int i = 0; i < 4; ++i) if (c->ev_x[i]) cudaEventDestroy(c->ev_x[i]);
     if (c->ev_main) cudaEventDestroy(c->ev_main);
     if (c->ev_y) cudaEventDestroy(c->ev_y);
     if (c->ev_kmm) cudaEventDestroy(c->ev_kmm);
@@ -222,21 +236,33 @@ static int ensure_shard_capacity(gparml_ctx *c, int64_t n)
 
 extern "C" int gparml_upload_shard(gparml_ctx *c, const double *Y, const double *X_mu, const double *X_S, int64_t n, int domain)
 {
-    CHECK_CTX(c);
+    CHECK_CTX_PIPE(c);
     if (n < 0 || (n > 0 && (!Y || !X_mu || !X_S))) { gp_set_error("upload_shard: null array or negative n"); return GPARML_ERR_ARG; }
     if (domain != GPARML_VARIANCE_UNCONSTRAINED && domain != GPARML_VARIANCE_POSITIVE) { gp_set_error("upload_shard: bad variance domain %d", domain); return GPARML_ERR_ARG; }
     GP_TRY(ensure_shard_capacity(c, n));
     const size_t nq = (size_t)n * c->Q;
-    // Y is needed only by psi1_stats / the Psi1 part of embed_grads: it travels on the copy stream
-    // (ordered behind everything already queued on the main stream, which may still read the old Y)
-    // and overlaps prep_points + psi2_stats; X_mu / X_S go first on the main stream.
+    // Everything travels on the copy stream (ordered behind all work already queued on the main stream,
+    // which may still read the old arrays): X_mu / X_S first, in up to 4 row ranges with an event each --
+    // gparml_statistics runs prep_points + psi2_stats of range k while range k + 1 is still arriving --,
+    // then Y, which only psi1_stats / the Psi1 part of embed_grads need.
     GP_CUDA(cudaEventRecord(c->ev_main, c->stream));
     GP_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
+    int ranges = (int)(n / 62500);
+    if (ranges > 4) ranges = 4;
+    if (ranges < 1 || (c->flags & GPARML_FLAG_FP32_MAP)) ranges = 1;
+    for (int k = 0; k <= ranges; ++k) c->x_bounds[k] = n * k / ranges;
     if (n > 0) {
-        GP_CUDA(cudaMemcpyAsync(c->x_mu, X_mu, nq * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        GP_CUDA(cudaMemcpyAsync(c->x_s, X_S, nq * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        for (int k = 0; k < ranges; ++k) {
+            const size_t off = (size_t)c->x_bounds[k] * c->Q, cnt = (size_t)(c->x_bounds[k + 1] - c->x_bounds[k]) * c->Q;
+            GP_CUDA(cudaMemcpyAsync(c->x_mu + off, X_mu + off, cnt * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+            GP_CUDA(cudaMemcpyAsync(c->x_s + off, X_S + off, cnt * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+            GP_CUDA(cudaEventRecord(c->ev_x[k], c->copy_stream));
+        }
         GP_CUDA(cudaMemcpyAsync(c->Y, Y, (size_t)n * c->D * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+    } else {
+        GP_CUDA(cudaEventRecord(c->ev_x[0], c->copy_stream));
     }
+    c->x_pending = ranges;
     if (n != c->n) {
         c->have_dir = false;
         if (c->psi1) { cudaFree(c->psi1); c->psi1 = nullptr; }
@@ -342,7 +368,7 @@ static int wait_y(gparml_ctx *c)
 
 extern "C" int gparml_set_globals(gparml_ctx *c, const double *Z, double sf2, const double *alpha, double beta)
 {
-    CHECK_CTX(c);
+    CHECK_CTX_PIPE(c);
     GP_TRY(finish_pending_gs(c));
     if (!Z || !alpha) { gp_set_error("set_globals: null array"); return GPARML_ERR_ARG; }
     if (!(sf2 > 0.0) || !(beta > 0.0)) { gp_set_error("set_globals: sf2 and beta must be positive (kernels.py:57 assert)"); return GPARML_ERR_ARG; }
@@ -379,7 +405,7 @@ extern "C" int gparml_set_globals(gparml_ctx *c, const double *Z, double sf2, co
 
 extern "C" int gparml_set_step(gparml_ctx *c, double step)
 {
-    CHECK_CTX(c);
+    CHECK_CTX_PIPE(c);
     c->step_size = step;
     c->have_prep = false;
     return GPARML_OK;
@@ -418,14 +444,40 @@ static int prep_if_needed(gparml_ctx *c)
 
 extern "C" int gparml_statistics(gparml_ctx *c)
 {
-    CHECK_CTX(c);
+    CHECK_CTX_PIPE(c);
     GP_TRY(finish_pending_gs(c));
     if (!c->have_shard || !c->have_globals) { gp_set_error("statistics: upload_shard and set_globals first"); return GPARML_ERR_STATE; }
     GP_TRY(record(c, 0));
-    GP_TRY(gp_launch_prep(c));          // always: it also rewrites the header of the packed buffer
-    c->have_prep = true;
-    GP_TRY(record(c, 1));
-    GP_TRY(gp_launch_psi2_stats(c));    // needs only X: runs while Y may still be arriving on the copy stream
+    if (c->x_pending > 1 && c->n > 0) {
+        // pipelined with the upload: range k is prepared and reduced while range k + 1 is still arriving
+        const int ranges = c->x_pending;
+        c->x_pending = 0;
+        int splits = 1, slice = 0, blocks = 0;
+        GP_TRY(gp_psi2_plan_range(c, c->x_bounds[1] - c->x_bounds[0], &splits));
+        GP_TRY(gp_ensure_ws(c, (size_t)ranges * splits * (1 + 2 * c->Q) * c->L.P * sizeof(double)));
+        const int kl_blocks = 4096 / 2 / ranges;                       // KL block partials of all ranges share red_ws
+        for (int k = 0; k < ranges; ++k) {
+            GP_CUDA(cudaStreamWaitEvent(c->stream, c->ev_x[k], 0));
+            int b = 0;
+            GP_TRY(gp_launch_prep_range(c, c->x_bounds[k], c->x_bounds[k + 1], c->red_ws + 2 * blocks, kl_blocks, &b));
+            blocks += b;
+            if (k == 0) GP_TRY(record(c, 1));
+            GP_TRY(gp_launch_psi2_stats_range(c, c->x_bounds[k], c->x_bounds[k + 1], slice, splits));
+            slice += splits;
+        }
+        GP_TRY(gp_launch_prep_finish(c, c->red_ws, blocks));
+        GP_TRY(gp_launch_psi2_reduce(c, slice));
+        c->have_prep = true;
+    } else {
+        if (c->x_pending > 0) {
+            GP_CUDA(cudaStreamWaitEvent(c->stream, c->ev_x[c->x_pending - 1], 0));
+            c->x_pending = 0;
+        }
+        GP_TRY(gp_launch_prep(c));          // always: it also rewrites the header of the packed buffer
+        c->have_prep = true;
+        GP_TRY(record(c, 1));
+        GP_TRY(gp_launch_psi2_stats(c));    // needs only X: runs while Y may still be arriving on the copy stream
+    }
     GP_TRY(record(c, 2));
     GP_TRY(wait_y(c));
     GP_TRY(gp_launch_set_yyt(c));

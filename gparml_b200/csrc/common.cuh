@@ -126,6 +126,11 @@ struct gparml_ctx {
     cudaEvent_t ev_gs_head = nullptr, ev_gs_tail = nullptr;
     bool gs_pending = false;           // gparml_global_step_begin without its _end
     double *glob_host = nullptr;       // pinned staging of [F, grad]
+    // gparml_upload_shard sends X_mu / X_S in up to 4 row ranges; gparml_statistics consumes them range by
+    // range (prep_points + psi2_stats of range k overlap the transfer of range k+1)
+    cudaEvent_t ev_x[4] = {nullptr, nullptr, nullptr, nullptr};
+    int x_pending = 0;                 // ranges of the last upload the main stream has not been ordered behind yet
+    int64_t x_bounds[5] = {0, 0, 0, 0, 0};
     cudaEvent_t ev_main = nullptr, ev_y = nullptr, ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     // globals
@@ -171,6 +176,11 @@ int gp_launch_yyt(gparml_ctx *c, cudaStream_t s);          // -> c->d_yyt[0], on
 int gp_launch_set_yyt(gparml_ctx *c);                      // stats[ST_YYT] = d_yyt[0]
 int gp_launch_embed_grads_range(gparml_ctx *c, int64_t i_begin, int64_t i_end);
 int gp_launch_prep(gparml_ctx *c);
+int gp_launch_prep_range(gparml_ctx *c, int64_t i0, int64_t i1, double *kl_partials, int max_blocks, int *blocks_used);
+int gp_launch_prep_finish(gparml_ctx *c, const double *kl_partials, int blocks);
+int gp_psi2_plan_range(gparml_ctx *c, int64_t cnt, int *splits);
+int gp_launch_psi2_stats_range(gparml_ctx *c, int64_t i0, int64_t i1, int slice0, int splits);
+int gp_launch_psi2_reduce(gparml_ctx *c, int slices);
 int gp_launch_pair_table(gparml_ctx *c);
 int gp_launch_psi1_stats(gparml_ctx *c);
 int gp_launch_psi2_stats(gparml_ctx *c);

@@ -68,7 +68,8 @@ int gp_launch_set_yyt(gparml_ctx *c)
 // prep_points
 // ---------------------------------------------------------------------------
 struct PrepParams {
-    int64_t n;
+    int64_t n;              // points in the shard (offset of the variance half of grad_d)
+    int64_t i0, i1;         // this launch covers points [i0, i1)
     int Q, R;
     const double *x_mu, *x_s, *grad_d;  // grad_d may be null
     double step;
@@ -104,8 +105,8 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_points_kernel(PrepParams p)
     double kl = 0.0, zeros = 0.0;
     bool bad = false;
     const bool stepping = p.mode == 0 && p.grad_d != nullptr && p.step != 0.0;
-    for (int64_t base = (int64_t)blockIdx.x * PREP_TP; base < p.n; base += (int64_t)gridDim.x * PREP_TP) {
-        const int cnt = (int)((p.n - base < PREP_TP) ? (p.n - base) : PREP_TP);
+    for (int64_t base = p.i0 + (int64_t)blockIdx.x * PREP_TP; base < p.i1; base += (int64_t)gridDim.x * PREP_TP) {
+        const int cnt = (int)((p.i1 - base < PREP_TP) ? (p.i1 - base) : PREP_TP);
         for (int e = tid; e < cnt * Q; e += PREP_THREADS) {
             const int pt = e / Q, q = e - pt * Q;
             const int64_t gi = base * Q + e;
@@ -196,10 +197,11 @@ __global__ void __launch_bounds__(256) prep_finish_kernel(const double *__restri
     }
 }
 
-int gp_launch_prep(gparml_ctx *c)
+// prep_points over the points [i0, i1); block partials of the KL sum go to kl_partials[2 * blocks]
+int gp_launch_prep_range(gparml_ctx *c, int64_t i0, int64_t i1, double *kl_partials, int max_blocks, int *blocks_used)
 {
     PrepParams p;
-    p.n = c->n;
+    p.n = c->n; p.i0 = i0; p.i1 = i1;
     p.Q = c->Q;
     p.R = gp_rec_len(c->Q);
     p.x_mu = c->x_mu;
@@ -215,19 +217,33 @@ int gp_launch_prep(gparml_ctx *c)
     p.status = c->d_status;
     p.rec2f = (c->flags & GPARML_FLAG_FP32_MAP) ? c->rec2f : nullptr;
     p.RF = gp_rec_len_f32(c->Q);
-    int blocks = (int)((c->n + PREP_TP - 1) / PREP_TP);
-    if (blocks > c->sm_count * 8) blocks = c->sm_count * 8;
+    int blocks = (int)((i1 - i0 + PREP_TP - 1) / PREP_TP);
+    if (blocks > max_blocks) blocks = max_blocks;
     if (blocks < 1) blocks = 1;
     const size_t smem = ((size_t)2 * PREP_TP * p.R + (size_t)2 * PREP_TP * p.Q) * sizeof(double) +
                         (p.rec2f ? (size_t)PREP_TP * p.RF * sizeof(float) : 0);
     GP_CUDA(cudaFuncSetAttribute(prep_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GP_TRY(gp_ensure_ws(c, (size_t)blocks * 2 * sizeof(double)));
-    p.kl_partials = c->ws;
+    p.kl_partials = kl_partials;
     prep_points_kernel<<<blocks, PREP_THREADS, smem, c->stream>>>(p);
     GP_LAUNCH_CHECK(c);
-    prep_finish_kernel<<<1, 256, 0, c->stream>>>(c->ws, blocks, (double)c->n, c->Q, p.mode, c->h_glob.sf2, c->stats);
+    *blocks_used = blocks;
+    return GPARML_OK;
+}
+
+int gp_launch_prep_finish(gparml_ctx *c, const double *kl_partials, int blocks)
+{
+    const int mode = (c->flags & GPARML_FLAG_FIXED_EMBEDDINGS) ? 2 : (c->variance_domain == GPARML_VARIANCE_POSITIVE ? 1 : 0);
+    prep_finish_kernel<<<1, 256, 0, c->stream>>>(kl_partials, blocks, (double)c->n, c->Q, mode, c->h_glob.sf2, c->stats);
     GP_LAUNCH_CHECK(c);
     return GPARML_OK;
+}
+
+int gp_launch_prep(gparml_ctx *c)
+{
+    int blocks = 1;
+    GP_TRY(gp_ensure_ws(c, (size_t)c->sm_count * 8 * 2 * sizeof(double)));
+    GP_TRY(gp_launch_prep_range(c, 0, c->n, c->ws, c->sm_count * 8, &blocks));
+    return gp_launch_prep_finish(c, c->ws, blocks);
 }
 
 // ---------------------------------------------------------------------------

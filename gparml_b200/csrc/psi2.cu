@@ -314,8 +314,9 @@ __global__ void __launch_bounds__(256) psi2_reduce_kernel(const double *__restri
     dst[i] = a;
 }
 
+// number of n-splits for `cnt` points: whole waves of resident CTAs, >= 4 point tiles per split, bounded workspace
 template <int Q>
-static int launch_q(gparml_ctx *c)
+static int plan_q(gparml_ctx *c, int64_t cnt, int *splits_out)
 {
     constexpr int R = (3 * Q + 2) & ~1;
     const size_t smem = (size_t)PSI2_STAGES * PSI2_TN * R * sizeof(double);
@@ -326,10 +327,9 @@ static int launch_q(gparml_ctx *c)
     const int64_t P = c->L.P;
     const int tiles = (int)((P + PSI2_THREADS * Psi2Cfg<Q>::PP - 1) / (PSI2_THREADS * Psi2Cfg<Q>::PP));
     const int64_t slots = (int64_t)c->sm_count * occ;
-    // number of n-splits: whole waves of resident CTAs, >= 4 point tiles per split, bounded workspace
     const int64_t rows_x_P = (int64_t)(1 + 2 * Q) * P;
-    int64_t max_splits = (c->n + 4 * PSI2_TN - 1) / (4 * PSI2_TN);
-    const int64_t ws_cap = ((int64_t)256 << 20) / (rows_x_P * (int64_t)sizeof(double));
+    int64_t max_splits = (cnt + 4 * PSI2_TN - 1) / (4 * PSI2_TN);
+    const int64_t ws_cap = ((int64_t)256 << 20) / (rows_x_P * (int64_t)sizeof(double)) / 4;   // up to 4 ranges per evaluation
     if (max_splits > ws_cap) max_splits = ws_cap;
     if (max_splits > 65535) max_splits = 65535;
     if (max_splits < 1) max_splits = 1;
@@ -342,13 +342,56 @@ static int launch_q(gparml_ctx *c)
         const double eff = (double)total / (double)(waves * slots);
         if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
     }
-    const int splits = (int)best;
-    const int64_t n_per_split = (c->n + splits - 1) / splits;
-    GP_TRY(gp_ensure_ws(c, (size_t)splits * rows_x_P * sizeof(double)));
+    *splits_out = (int)best;
+    return GPARML_OK;
+}
+
+// psi2_stats over the points [i0, i1): partial sums into the workspace slices [slice0, slice0 + splits)
+template <int Q>
+static int launch_range_q(gparml_ctx *c, int64_t i0, int64_t i1, int slice0, int splits)
+{
+    constexpr int R = (3 * Q + 2) & ~1;
+    const size_t smem = (size_t)PSI2_STAGES * PSI2_TN * R * sizeof(double);
+    const int64_t P = c->L.P, cnt = i1 - i0;
+    const int tiles = (int)((P + PSI2_THREADS * Psi2Cfg<Q>::PP - 1) / (PSI2_THREADS * Psi2Cfg<Q>::PP));
+    const int64_t rows_x_P = (int64_t)(1 + 2 * Q) * P;
+    const int64_t n_per_split = (cnt + splits - 1) / splits;
     dim3 grid(tiles, splits);
-    psi2_stats_kernel<Q><<<grid, PSI2_THREADS, smem, c->stream>>>(c->rec2, c->n, c->Z, P, c->pair_idx, c->pair_lk, n_per_split, c->ws);
+    psi2_stats_kernel<Q><<<grid, PSI2_THREADS, smem, c->stream>>>(c->rec2 + i0 * R, cnt, c->Z, P, c->pair_idx, c->pair_lk, n_per_split,
+                                                                  c->ws + (size_t)slice0 * rows_x_P);
     GP_LAUNCH_CHECK(c);
-    psi2_reduce_kernel<<<(int)((rows_x_P + 255) / 256), 256, 0, c->stream>>>(c->ws, splits, rows_x_P, c->stats + c->L.off_s0);
+    return GPARML_OK;
+}
+
+#define PSI2_ALL_Q(F) F(1) F(2) F(3) F(4) F(5) F(6) F(7) F(8) F(9) F(10) F(11) F(12) F(13) F(14) F(15) F(16)
+
+int gp_psi2_plan_range(gparml_ctx *c, int64_t cnt, int *splits)
+{
+    switch (c->Q) {
+#define CASE_Q(q) case q: return plan_q<q>(c, cnt, splits);
+        PSI2_ALL_Q(CASE_Q)
+#undef CASE_Q
+    }
+    gp_set_error("psi2_stats: unsupported Q=%d (1..%d)", c->Q, GP_MAX_Q);
+    return GPARML_ERR_ARG;
+}
+
+int gp_launch_psi2_stats_range(gparml_ctx *c, int64_t i0, int64_t i1, int slice0, int splits)
+{
+    switch (c->Q) {
+#define CASE_Q(q) case q: return launch_range_q<q>(c, i0, i1, slice0, splits);
+        PSI2_ALL_Q(CASE_Q)
+#undef CASE_Q
+    }
+    gp_set_error("psi2_stats: unsupported Q=%d (1..%d)", c->Q, GP_MAX_Q);
+    return GPARML_ERR_ARG;
+}
+
+// fixed-order sum over the workspace slices -> packed statistics (S0, TZ, TA)
+int gp_launch_psi2_reduce(gparml_ctx *c, int slices)
+{
+    const int64_t rows_x_P = (int64_t)(1 + 2 * c->Q) * c->L.P;
+    psi2_reduce_kernel<<<(int)((rows_x_P + 255) / 256), 256, 0, c->stream>>>(c->ws, slices, rows_x_P, c->stats + c->L.off_s0);
     GP_LAUNCH_CHECK(c);
     return GPARML_OK;
 }
@@ -358,12 +401,9 @@ int gp_launch_psi2_stats_f32(gparml_ctx *c);
 int gp_launch_psi2_stats(gparml_ctx *c)
 {
     if (c->flags & GPARML_FLAG_FP32_MAP) return gp_launch_psi2_stats_f32(c);      // opt-in fp32 evaluation
-    switch (c->Q) {
-#define CASE_Q(q) case q: return launch_q<q>(c);
-        CASE_Q(1) CASE_Q(2) CASE_Q(3) CASE_Q(4) CASE_Q(5) CASE_Q(6) CASE_Q(7) CASE_Q(8)
-        CASE_Q(9) CASE_Q(10) CASE_Q(11) CASE_Q(12) CASE_Q(13) CASE_Q(14) CASE_Q(15) CASE_Q(16)
-#undef CASE_Q
-    }
-    gp_set_error("psi2_stats: unsupported Q=%d (1..%d)", c->Q, GP_MAX_Q);
-    return GPARML_ERR_ARG;
+    int splits = 1;
+    GP_TRY(gp_psi2_plan_range(c, c->n, &splits));
+    GP_TRY(gp_ensure_ws(c, (size_t)splits * (1 + 2 * c->Q) * c->L.P * sizeof(double)));
+    GP_TRY(gp_launch_psi2_stats_range(c, 0, c->n, 0, splits));
+    return gp_launch_psi2_reduce(c, splits);
 }

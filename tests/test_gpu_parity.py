@@ -320,6 +320,58 @@ def test_split_master_step_matches_blocking_call():
             c.global_step_end()
 
 
+def test_kmm_like_reference_kernel_selftest():
+    """kernels.py:131-157 (`python kernels.py -t`): the closed form of one entry, and an infinite
+    length-scale (alpha = 0) switches its input dimension off."""
+    from gparml_b200 import _lib
+    from gparml_b200.engine import ShardContext
+    rng = np.random.default_rng(4)
+    M = 10
+    Z3 = rng.uniform(-5.0, 5.0, (M, 3))
+    with ShardContext(M, 3, 1, 0) as c3, ShardContext(M, 2, 1, 0) as c2:
+        c3.set_globals(Z3, 16.0, np.array([0.5, 0.5, 0.0]), 1.0)
+        c3.update_global_statistics()
+        K3 = c3.download(_lib.A_KMM, (M, M))
+        c2.set_globals(np.ascontiguousarray(Z3[:, :2]), 16.0, np.array([0.5, 0.5]), 1.0)
+        c2.update_global_statistics()
+        K2 = c2.download(_lib.A_KMM, (M, M))
+    a, b = 3, 5
+    expect = 16.0 * np.exp(-np.sum((Z3[a, :2] - Z3[b, :2]) ** 2) / 4.0)
+    assert abs(K3[a, b] - expect) <= 1e-12 * expect
+    assert np.array_equal(K3, K3.T)
+    assert np.allclose(K3, K2, rtol=1e-14, atol=0.0)
+
+
+def test_statistics_pipelined_with_upload_match_resident_path():
+    """gparml_upload_shard sends X_mu / X_S in row ranges and the first gparml_statistics consumes them range
+    by range (prep_points + psi2_stats per range); a second call on the resident data takes the one-launch
+    path.  Same statistics, bound and gradients (summation order differs: 1e-12)."""
+    from gparml_b200 import _lib
+    from gparml_b200.engine import ShardContext
+    from gparml_b200.synthetic import make_problem
+    M, Q, D, n = 24, 3, 2, 200000            # 3 row ranges
+    p = make_problem(n, M, Q, D, seed=21, generic_hypers=True, with_direction=True)
+    with ShardContext(M, Q, D, n) as c:
+        out = []
+        for rep in range(2):
+            if rep == 0:
+                c.upload_shard(p["Y"], p["X_mu"], p["X_S"])
+                c.set_globals(p["Z"], p["sf2"], p["alpha"], p["beta"])
+            c.statistics()
+            st = c.stats_named()
+            F, g = c.global_step()
+            c.embedding_grads()
+            out.append((st, F, g["flat"], c.grad_latest()))
+        for key, v in out[0][0].items():
+            assert relerr(out[1][0][key], v) <= 1e-12, key
+        assert relerr(out[1][1], out[0][1]) <= 1e-12
+        assert relerr(out[1][2], out[0][2]) <= 1e-11
+        assert relerr(out[1][3], out[0][3]) <= 1e-11
+        # a consumer of X_mu between upload and statistics orders itself behind the ranges
+        c.upload_shard(p["Y"], p["X_mu"] + 1.0, p["X_S"])
+        assert np.array_equal(c.download(_lib.A_X_MU, (n, Q)), p["X_mu"] + 1.0)
+
+
 def test_chunked_gradient_download_and_reupload():
     """embedding_grads_download (copy of one point range overlapping the next range's kernels) gives
     the same array as embedding_grads + download for any chunk count; re-uploading a different shard
