@@ -247,6 +247,7 @@ def main():
     ap.add_argument("--cpu-points", type=int, default=0, help="points per CPU worker in the baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="point ranges of the overlapped gradient download (1..8)")
     ap.add_argument("--fp32", action="store_true", help="opt-in fp32 map path (psi2_stats / embed_grads in fp32, fp64 sums); "
                                                         "not the headline configuration")
     args = ap.parse_args()
@@ -269,7 +270,20 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the communicator is created; stdout must carry
+        # exactly one JSON line, so file descriptor 1 points at stderr until the first collective is done
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        try:
+            os.dup2(2, 1)
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     k = dict(CONFIGS[args.config])
     if args.n:
@@ -318,7 +332,7 @@ def main():
         if fixed:
             return ctx.global_step()
         ctx.global_step_begin()
-        ctx.embedding_grads_into(GLp.data_ptr(), chunks=4)
+        ctx.embedding_grads_into(GLp.data_ptr(), chunks=args.e2e_chunks)
         return ctx.global_step_end()
 
     def timed(fn, steps, collect_phases=False):
