@@ -113,7 +113,12 @@ int gparml_set_n_total(gparml_ctx *ctx, int64_t n_total);
 /* ---- shard data (device-resident between evaluations) ------------------- */
 /* Copies Y (n,D), X_mu (n,Q), X_S (n,Q) host -> device; replaces the per-evaluation
  * genfromtxt + load of local_MapReduce.py:195-201 / 323-329.  Also computes
- * sum_n y_n.y_n (partial_terms.py:40).  May be called again with a different n. */
+ * sum_n y_n.y_n (partial_terms.py:40).  May be called again with a different n.
+ * Asynchronous: the copies run on the context's copy stream (X_mu / X_S in up to four row ranges,
+ * then Y) and the next gparml_statistics starts on the first range while the others are still in
+ * flight; every other entry point waits for them.  Pageable host arrays may be reused when the call
+ * returns, pinned ones must stay valid until the next call that synchronises (gparml_statistics with
+ * unconstrained variances, gparml_global_step[_end], gparml_download, gparml_synchronize). */
 int gparml_upload_shard(gparml_ctx *ctx, const double *Y, const double *X_mu, const double *X_S,
                         int64_t n_local, int variance_domain);
 int64_t gparml_n_local(const gparml_ctx *ctx);
