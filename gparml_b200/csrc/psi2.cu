@@ -22,6 +22,9 @@
 // record at the same time, so all shared-memory reads are broadcasts and each read feeds PP
 // pairs.  The grid is (pair tiles) x (n splits), sized to whole waves of resident CTAs; per-split
 // partial sums go to a workspace and are added in a fixed order (deterministic, no atomics).
+// With two pairs per thread the point loop is the hand-ordered software pipeline psi2_step below (B200,
+// N = 250k: 6.24 -> 6.11 ms); one pair per thread (Q > 10) keeps the compiler-scheduled loop.  The
+// launchers work on point ranges so that gparml_statistics can follow a row-range upload (capi.cu).
 //
 // Bound: FP64 pipe.  Algorithmic count 6Q + 20 per (point, pair) with exp = 18;
 // executed: 6Q + 11 with the table-driven exp of gp_exp.cuh (9 FP64 instructions).
