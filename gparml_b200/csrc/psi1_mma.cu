@@ -143,11 +143,7 @@ psi1_mma_kernel(Psi1MParams p)
         }
         __syncwarp();                                     // tile t visible to the whole warp
         const double *rb = wb + buf * TILE, *yb = rb + P1M_TP * RS;
-#ifdef P1M_UNROLL2
-#pragma unroll 2
-#else
-#pragma unroll 1
-#endif
+#pragma unroll 1      // unrolling by 2 changes nothing: 255 registers, the steps stay serialised
         for (int st = 0; st < P1M_TP / 4; ++st) {
             if (st * 4 >= cnt) break;                     // warp-uniform
             const int pl_raw = st * 4 + kk;

@@ -49,8 +49,6 @@
 #ifndef PSI2_STAGES
 #define PSI2_STAGES 2
 #endif
-#define PSI2_STR2(x) #x
-#define PSI2_STR(x) PSI2_STR2(x)
 
 // Pairs per thread (register blocking: each shared-memory read feeds PP pairs) and the number
 // of resident CTAs the register budget is tuned for.  Measured on B200 at Q=10 (tools/tune.py,
