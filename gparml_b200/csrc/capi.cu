@@ -378,14 +378,18 @@ extern "C" int gparml_set_globals(gparml_ctx *c, const double *Z, double sf2, co
     c->h_glob.log_sf2 = log(sf2);
     for (int q = 0; q < c->Q; ++q) {
         if (!(alpha[q] >= 0.0)) { gp_set_error("set_globals: alpha[%d] negative (kernel_exp.py:30 assert)", q); return GPARML_ERR_ARG; }
-        c->h_glob.alpha[q] = alpha[q];
+        // alpha_q = 0 is legal in the reference (kernel_exp.py:30 asserts >= 0) and switches dimension q off.  The
+        // packed buffer keeps the alpha-derivative sums scaled by alpha^2 (TA, rows 1+Q.. of K1), which is 0 * inf
+        // there; 2^-400 instead of 0 gives bit-identical kernel values (exp(-2^-400 x) rounds to 1), alpha^2 = 2^-800
+        // is an exact power of two far above the denormals, and the derivative comes out as the limit alpha -> 0+.
+        c->h_glob.alpha[q] = alpha[q] > 0.0 ? alpha[q] : 0x1p-400;
     }
-    if (c->flags & GPARML_FLAG_FP32_MAP) {          // centre of the inducing inputs (fp32 maps subtract it)
-        for (int q = 0; q < c->Q; ++q) {
-            double s = 0.0;
-            for (int m = 0; m < c->M; ++m) s += Z[(size_t)m * c->Q + q];
-            c->h_glob.center[q] = s / c->M;
-        }
+    // centre of the inducing inputs: the expanded basis of embed_grads (embed.cu) and the fp32 maps work on
+    // mu - center, zbar - center, so their cancellation scales with the spread of Z, not its offset from the origin
+    for (int q = 0; q < c->Q; ++q) {
+        double s = 0.0;
+        for (int m = 0; m < c->M; ++m) s += Z[(size_t)m * c->Q + q];
+        c->h_glob.center[q] = s / c->M;
     }
     // pageable host memory: the async copies below stage synchronously, so Z/alpha may be reused by the caller on return
     GP_CUDA(cudaMemcpyAsync(c->Z, Z, (size_t)c->M * c->Q * sizeof(double), cudaMemcpyHostToDevice, c->stream));

@@ -83,8 +83,8 @@ __device__ __forceinline__ void embx_step(const double2 *__restrict__ zn, const 
         }
 #pragma unroll
         for (int v = 0; v < NP; ++v) {
-            if (NC == 2) es[v].x = (e0[v][0] + e0[v][NC - 1]) + (e1[v][0] + e1[v][NC - 1]);
-            else es[v].x = e0[v][0] + e1[v][0];
+            if (NC == 2) es[v].x = gp_exp_clamp((e0[v][0] + e0[v][NC - 1]) + (e1[v][0] + e1[v][NC - 1]));
+            else es[v].x = gp_exp_clamp(e0[v][0] + e1[v][0]);
         }
     }
     // ---- block XA: exp steps of the next pair, each followed by one group of accumulations ---------

@@ -9,8 +9,13 @@
 // <= ~1e-14 for |x| < 100 (argument reduction with a single rounded ln2/32: |k| * 2e-18
 // absolute error in r), far inside the 1e-9 parity budget on the summed statistics.
 //
-// Domain: x <= 700 (Psi values are bounded by sf^2 resp. sf^4); x < -709 flushes to ~1e-308
-// instead of a denormal/zero (m is clamped), which contributes nothing to any sum.
+// Domain: any x <= 700 including -inf (Psi values are bounded by sf^2 resp. sf^4).  The argument is first
+// clamped to >= -745.25 by gp_exp_clamp -- an unsigned integer min on the high word (negative doubles order
+// like their bit patterns), one integer-pipe instruction, no FP64 slot -- because k = round(x 32/ln2) is read
+// from the low word of t and would wrap for x < -4.65e7 (an exponent that size is what un-normalised
+// regression inputs give: alpha = 1, inputs spanning 1e4, kernel_exp.py:143-146 then calls np.exp(-1e8) = 0).
+// x < -709 returns ~4e-308..9e-308 instead of a denormal / zero (m is clamped), which contributes nothing
+// to any sum.
 #pragma once
 
 #define GP_EXP_TAB 32
@@ -32,6 +37,13 @@ __device__ __forceinline__ void gp_exp_load_table(double *tab_smem)
     for (int i = threadIdx.x; i < GP_EXP_TAB; i += blockDim.x) tab_smem[i] = gp_exp_table_const[i];
 }
 
+// x >= -745.25 for every x (positive x, and x >= -745.25, pass through bit-identically)
+__device__ __forceinline__ double gp_exp_clamp(double x)
+{
+    const unsigned hi = (unsigned)__double2hiint(x);
+    return __hiloint2double((int)(hi < 0xC0874A00u ? hi : 0xC0874A00u), __double2loint(x));
+}
+
 // sign_word: 0 or 0x80000000, XORed into the sign bit of the result (integer pipe), i.e.
 // +-exp(x) without a multiplication
 __device__ __forceinline__ double gp_exp_signed(double x, const double *tab_smem, int sign_word);
@@ -40,6 +52,7 @@ __device__ __forceinline__ double gp_exp(double x, const double *tab_smem) { ret
 
 __device__ __forceinline__ double gp_exp_signed(double x, const double *tab_smem, int sign_word)
 {
+    x = gp_exp_clamp(x);
     const double SHIFT = 6755399441055744.0;                  // 1.5 * 2^52: the low word of t is round(v)
     const double t = fma(x, 46.16624130844683, SHIFT);        // 32 / ln2
     const int k = __double2loint(t);

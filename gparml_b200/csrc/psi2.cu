@@ -98,8 +98,8 @@ __device__ __forceinline__ void psi2_step(const double *__restrict__ rn, const d
             e[0][q & 1] = fma(-wdn[0][q], d0, e[0][q & 1]);
             e[1][q & 1] = fma(-wdn[1][q], d1, e[1][q & 1]);
         }
-        es[0].x = e[0][0] + e[0][1];
-        es[1].x = e[1][0] + e[1][1];
+        es[0].x = gp_exp_clamp(e[0][0] + e[0][1]);
+        es[1].x = gp_exp_clamp(e[1][0] + e[1][1]);
     }
     const double2 *rv = reinterpret_cast<const double2 *>(rc) + Q;      // (v_2k, v_2k+1)
     if (DO_A) {

@@ -5,7 +5,7 @@ never imports it.
 
 Pinning: this restatement is checked against the *live* reference
 (``oracle/ref_shim.py`` imports ``/root/reference/partial_terms.py`` unmodified)
-in ``tests/test_oracle_vs_reference.py`` and against the committed golden
+in ``tests/test_oracle.py`` and against the committed golden
 vectors ``tests/golden/*.npz`` that ``oracle/gen_golden.py`` produced from the
 live reference.  The reference itself ships no golden vectors or seeded tests
 (SURVEY.md section 4), so the reference-run fixtures are the pin.

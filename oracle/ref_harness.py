@@ -7,7 +7,7 @@ imported, so the bodies of ``statistics_mapper`` (local_MapReduce.py:183-248),
 ``calculate_global_derivatives`` (parallel_GPLVM.py:302-369) and
 ``embeddings_mapper`` (local_MapReduce.py:310-363) are replayed here on
 in-memory arrays, every arithmetic call going to the reference object.
-Used by ``oracle/gen_golden.py`` and ``tests/test_oracle_vs_reference.py``; only
+Used by ``oracle/gen_golden.py`` and ``tests/test_oracle.py``; only
 works where ``/root/reference`` exists.
 """
 import numpy as np

@@ -257,11 +257,22 @@ def test_psi1_contraction_column_shapes(Q, D):
     assert not bad, bad
 
 
-@pytest.mark.parametrize("offset", [30.0, 1000.0])
+def _compare_all(res, ref, keys=("F", "grad_Z", "grad_alpha", "grad_sf2", "grad_beta")):
+    errs = {k: relerr(res["stats"][k], v) for k, v in ref["stats"].items()}
+    for key in keys:
+        errs[key] = relerr(res["global"][key], ref["global"][key])
+    for i, (a, b) in enumerate(zip(res["grad_latest"], ref["grad_latest"])):
+        errs["grad_latest_%d" % i] = relerr(a, b)
+    return errs
+
+
+@pytest.mark.parametrize("offset", [30.0, 1000.0, 1.0e4])
 def test_latent_space_far_from_origin(offset):
     """embed_grads evaluates the Psi2 exponent in an expanded (dot-product) form centred on the column
-    means of Z; a common translation of X_mu and Z far from the origin must not cost accuracy."""
-    from gparml_b200.synthetic import make_problem
+    means of Z; a common translation of X_mu and Z far from the origin must not cost accuracy.  Generic
+    (unquantised) inputs: here the comparison is limited by the REFERENCE's own rounding of
+    mu - 0.5 z_m - 0.5 z_m' (kernel_exp.py:145), eps * offset in every distance."""
+    from gparml_b200.synthetic import make_problem, split_rows
     from oracle import c_oracle
     M, Q, D, n = 30, 5, 3, 900
     p = make_problem(n, M, Q, D, seed=77, generic_hypers=True, with_direction=True)
@@ -269,17 +280,127 @@ def test_latent_space_far_from_origin(offset):
     X_mu = p["X_mu"] + shift
     Z = p["Z"] + shift
     shards = []
-    from gparml_b200.synthetic import split_rows
     for lo, hi in split_rows(n, 2):
         shards.append(dict(Y=p["Y"][lo:hi], X_mu=X_mu[lo:hi], X_S=p["X_S"][lo:hi], d=p["d"][:, lo:hi]))
     ref = c_oracle.evaluate(shards, Z, p["sf2"], p["alpha"], p["beta"], step_size=1e-3)
     res = _gpu_evaluate(shards, Z, p["sf2"], p["alpha"], p["beta"], step_size=1e-3)
-    errs = {k: relerr(res["stats"][k], v) for k, v in ref["stats"].items()}
-    for key in ("F", "grad_Z", "grad_alpha", "grad_sf2", "grad_beta"):
-        errs[key] = relerr(res["global"][key], ref["global"][key])
-    for i, (a, b) in enumerate(zip(res["grad_latest"], ref["grad_latest"])):
-        errs["grad_latest_%d" % i] = relerr(a, b)
-    print(offset, "max rel err %.2e at %s" % (max(errs.values()), max(errs, key=errs.get)))
+    errs = _compare_all(res, ref)
+    print("offset %g: max rel err %.2e at %s" % (offset, max(errs.values()), max(errs, key=errs.get)))
+    bad = {k2: v for k2, v in errs.items() if not v <= TOL}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("log2_offset", [13, 17])
+def test_expanded_basis_is_centred_exact_translation(log2_offset):
+    """Pins the centring of the expanded basis (capi.cu gparml_set_globals: center = column means of Z).
+    X_mu and Z are quantised to multiples of 2^-30 and translated by multiples of 2^log2_offset (8192 and
+    131072 units), so the translated inputs are exact doubles and every difference the reference forms
+    (mu - 0.5 z - 0.5 z', z - z', mu - z) is exact: the oracle in the translated frame is as accurate as
+    at the origin and the comparison isolates the CUDA path's own error.  With center = 0 (the round-1
+    defect) the expanded exponent loses eps * w * offset^2 = 1e-8 .. 4e-6 here; centred it must stay
+    <= 1e-11 on everything, per-point gradients included."""
+    from gparml_b200.synthetic import make_problem, split_rows
+    from oracle import c_oracle
+    M, Q, D, n = 30, 5, 3, 900
+    p = make_problem(n, M, Q, D, seed=78, generic_hypers=True)
+    quant = lambda a: np.round(a * 2.0 ** 30) / 2.0 ** 30
+    shift = 2.0 ** log2_offset * np.array([1.0, -0.5, 0.25, 2.0, -1.0])
+    X_mu = quant(p["X_mu"]) + shift
+    Z = quant(p["Z"]) + shift
+    assert np.array_equal(X_mu - shift, quant(p["X_mu"])) and np.array_equal(Z - shift, quant(p["Z"]))
+    shards = [dict(Y=p["Y"][lo:hi], X_mu=X_mu[lo:hi], X_S=p["X_S"][lo:hi]) for lo, hi in split_rows(n, 2)]
+    ref = c_oracle.evaluate(shards, Z, p["sf2"], p["alpha"], p["beta"])
+    res = _gpu_evaluate(shards, Z, p["sf2"], p["alpha"], p["beta"])
+    errs = _compare_all(res, ref)
+    worst_gl = max(v for k, v in errs.items() if k.startswith("grad_latest"))
+    print("offset 2^%d: grad_latest rel err %.2e, overall max %.2e at %s"
+          % (log2_offset, worst_gl, max(errs.values()), max(errs, key=errs.get)))
+    bad = {k2: v for k2, v in errs.items() if not v <= 1e-11}
+    assert not bad, bad
+
+
+def test_unnormalised_regression_inputs_huge_negative_exponents():
+    """BASELINE config-2 style sparse GP regression on un-normalised inputs: S = 0, alpha = 1 (the reference's
+    initial value, parallel_GPLVM.py:189-194), inputs spanning 1e4 per dimension, so the Psi exponents
+    (kernel_exp.py:80,143-146) reach -1e8, beyond where k = round(x 32/ln2) fits the 32-bit word the table
+    exp reads it from (x < -4.65e7).  numpy's exp gives 0 there; the device exp clamps its argument
+    (gp_exp.cuh gp_exp_clamp) and must agree on every statistic, the bound and the gradients."""
+    from oracle import c_oracle
+    rng = np.random.default_rng(20141208 + 202)
+    n, M, Q, D = 4096, 50, 4, 1
+    X = rng.uniform(0.0, 1.0e4, (n, Q))
+    # half of the inducing points sit on data points (so Psi1 / Psi2 are not all zero), a few are near each
+    # other (non-trivial Kmm), the rest are far from everything
+    Z = np.concatenate([X[rng.choice(n, 25, replace=False)] + 0.3 * rng.standard_normal((25, Q)),
+                        rng.uniform(0.0, 1.0e4, (25, Q))])
+    Z[1] = Z[0] + 0.7
+    Z[30] = Z[29] + np.array([1.0, -0.5, 0.2, 0.1])
+    Y = np.sin(X[:, :1] / 500.0) + 0.1 * rng.standard_normal((n, 1))
+    S = np.zeros((n, Q))
+    alpha = np.ones(Q)
+    lk_min = -0.25 * np.max(np.sum((Z[:, None, :] - Z[None, :, :]) ** 2, axis=2))
+    assert lk_min < -4.65e7, lk_min                       # the exponent range this test is about
+    shards = [dict(Y=Y[:2000], X_mu=X[:2000], X_S=S[:2000]), dict(Y=Y[2000:], X_mu=X[2000:], X_S=S[2000:])]
+    ref = c_oracle.evaluate(shards, Z, 1.0, alpha, 1.0, fixed_embeddings=True)
+    res = _gpu_evaluate(shards, Z, 1.0, alpha, 1.0, fixed_embeddings=True)
+    assert np.max(np.abs(ref["stats"]["sum_exp_K_mi_K_im"])) > 0.1      # not a vacuous comparison
+    for k, v in res["stats"].items():
+        assert np.all(np.isfinite(np.asarray(v))), k
+    errs = _compare_all(res, ref)
+    print("min pair exponent %.3g: max rel err %.2e at %s" % (lk_min, max(errs.values()), max(errs, key=errs.get)))
+    bad = {k2: v for k2, v in errs.items() if not v <= TOL}
+    assert not bad, bad
+
+
+def test_huge_negative_exponents_gplvm_path():
+    """The same exponent range through the GPLVM kernels (psi2_stats with S > 0, embed_psi1 / embed_psi2x):
+    latent means spanning 2e4 with a few inducing points on data points."""
+    from gparml_b200.synthetic import softplus_inv
+    from oracle import c_oracle
+    rng = np.random.default_rng(20141208 + 203)
+    n, M, Q, D = 1200, 24, 3, 2
+    X = rng.uniform(-1.0e4, 1.0e4, (n, Q))
+    Z = np.concatenate([X[rng.choice(n, 12, replace=False)] + 0.2 * rng.standard_normal((12, Q)),
+                        rng.uniform(-1.0e4, 1.0e4, (12, Q))])
+    Z[1] = Z[0] + 0.5
+    Y = rng.standard_normal((n, D))
+    S_raw = softplus_inv(np.clip(0.5 + 0.01 * rng.standard_normal((n, Q)), 0.001, 1.0))
+    alpha = np.array([1.0, 0.7, 1.3])
+    shards = [dict(Y=Y, X_mu=X, X_S=S_raw)]
+    ref = c_oracle.evaluate(shards, Z, 1.3, alpha, 2.0)
+    res = _gpu_evaluate(shards, Z, 1.3, alpha, 2.0)
+    assert np.all(np.isfinite(res["grad_latest"][0]))
+    errs = _compare_all(res, ref)
+    print("max rel err %.2e at %s" % (max(errs.values()), max(errs, key=errs.get)))
+    bad = {k2: v for k2, v in errs.items() if not v <= TOL}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("zero_dims", [(1,), (0, 3)])
+def test_alpha_zero_switches_dimension_off_with_finite_gradient(zero_dims):
+    """alpha_q = 0 (infinite length-scale) is legal in the reference (kernel_exp.py:30,130 assert >= 0;
+    kernels.py self-test) and its alpha-derivatives are finite there (partial_terms.py:256-284 never divide by
+    alpha).  The packed buffer keeps those sums scaled by alpha_q^2, so the device substitutes 2^-400 for 0
+    (capi.cu gparml_set_globals); statistics, bound and ALL gradients -- grad_alpha[q] of the switched-off
+    dimensions included -- must match the oracle evaluated at alpha_q = 0 exactly."""
+    from gparml_b200.synthetic import make_problem
+    from oracle import c_oracle
+    M, Q, D, n = 12, 5, 4, 700           # log10 cond(Kmm) = 0.9 / 1.1 with the dimensions switched off
+    p = make_problem(n, M, Q, D, seed=55, generic_hypers=True, with_direction=True)
+    alpha = p["alpha"].copy()
+    for q in zero_dims:
+        alpha[q] = 0.0
+    shards = _shards_of(p, 2)
+    ref = c_oracle.evaluate(shards, p["Z"], p["sf2"], alpha, p["beta"], step_size=1e-3)
+    res = _gpu_evaluate(shards, p["Z"], p["sf2"], alpha, p["beta"], step_size=1e-3)
+    assert np.all(np.isfinite(res["global"]["grad_alpha"]))
+    assert all(abs(ref["global"]["grad_alpha"][q]) > 1e-3 for q in zero_dims)      # a real number to match
+    errs = _compare_all(res, ref, keys=("F", "grad_Z", "grad_alpha", "grad_sf2", "grad_beta", "dF_dKmm",
+                                        "dF_dsum_exp_K_miY", "dF_dsum_exp_K_mi_K_im"))
+    errs["grad_alpha_elementwise"] = float(np.max(np.abs(res["global"]["grad_alpha"] - ref["global"]["grad_alpha"])
+                                                  / np.abs(ref["global"]["grad_alpha"])))
+    print("alpha = 0 at", zero_dims, "grad_alpha", res["global"]["grad_alpha"],
+          "max rel err %.2e at %s" % (max(errs.values()), max(errs, key=errs.get)))
     bad = {k2: v for k2, v in errs.items() if not v <= TOL}
     assert not bad, bad
 
