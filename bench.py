@@ -3,25 +3,34 @@
 ELBO+gradient evaluations per second at N=1M, M=100, Q=10, D=10 on 1/2/4/8 B200).
 
     python bench.py --gpus N --steps K --warmup W            # our arm
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU arithmetic on the host cores
 
 One "step" = one full evaluation: globals host->device, prep_points,
-psi1_stats, psi2_stats, [NCCL all-reduce of the packed sums], global_step (F and the global
+psi2_stats, psi1_stats, [NCCL all-reduce of the packed sums], global_step (F and the global
 gradient back on the host), embed_grads.  N > 1 shards the points over the ranks
 (strong scaling: the problem size is fixed by the metric).
 
-``value``  : device-resident shard (Y, X_mu, X_S uploaded once before the timed region).
-``e2e``    : the same evaluation through the host-buffer API every step: the shard is copied
-             from pinned host memory (what ``partial_terms.set_data`` receives in the
-             reference's mappers, local_MapReduce.py:197-224) and the per-point gradients
-             are copied back (the ``.grad_latest.npy`` the reference writes, :359-360).
+``value``          : device-resident shard (Y, X_mu, X_S uploaded once before the timed region), C-ABI calls.
+``e2e``            : the same evaluation through the host-buffer API every step: the shard is copied
+                     from pinned host memory (what ``partial_terms.set_data`` receives in the
+                     reference's mappers, local_MapReduce.py:197-224) and the per-point gradients
+                     are copied back (the ``.grad_latest.npy`` the reference writes, :359-360).
+``through_driver`` : the same evaluation through the reference's own interface -- the replayed
+                     ``parallel_GPLVM.likelihood_and_gradient(x, i, step)`` callback on the ``b200_MapReduce``
+                     backend (device-resident shards, ``b200_write_files=False``).
+``other_configs``  : BASELINE configs 5, 4 and 2 measured in the same run (fewer steps), with their own clocks.
+
+Synthetic data is generated in 8 independent row blocks (gparml_b200/synthetic.py) so that every rank builds
+only its rows and the problem -- hence F -- is the same for 1, 2, 4 and 8 ranks; F is checked against the
+committed value in tests/golden/bench_expected_F.json.
 """
 import argparse
 import json
-import math
 import os
+import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -34,11 +43,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from gparml_b200.synthetic import CONFIGS, make_problem, split_rows  # noqa: E402
+from gparml_b200.synthetic import CONFIGS, ROW_BLOCKS, block_problem_globals, block_problem_rows  # noqa: E402
 
 E_EXP = 18  # FP64-pipe instructions of exp()
 METRIC = "ELBO+grad evals/sec"
 UNIT = "evals/s"
+EXPECTED_F = os.path.join(ROOT, "tests", "golden", "bench_expected_F.json")
 
 
 def algorithmic_ops(N, M, Q, D, fixed):
@@ -50,8 +60,10 @@ def algorithmic_ops(N, M, Q, D, fixed):
 
 
 # ----------------------------------------------------------------------------------------
-# CPU baseline: the numpy oracle (a port of the reference's per-point numpy loops) hosted in a
-# multiprocessing.Pool with one shard per worker, as local_MapReduce.py:134 does.
+# CPU arm: the reference's own arithmetic (unmodified partial_terms.py / kernel_exp.py / kernels.py through
+# oracle/ref_shim.py, mapper bodies replayed by oracle/ref_harness.py) hosted in a multiprocessing.Pool with
+# one shard per worker, as local_MapReduce.py:134 does.  Where the reference files are not available
+# (neither /root/reference nor the staged oracle/_ref), the numpy port oracle/gparml_oracle.py runs instead.
 # ----------------------------------------------------------------------------------------
 def _cpu_init():
     os.environ["OMP_NUM_THREADS"] = "1"
@@ -60,34 +72,47 @@ def _cpu_init():
 
 
 def _cpu_stats_worker(a):
-    from oracle import gparml_oracle as O
-    sh, Z, sf2, alpha, fixed = a
+    kind, sh, Z, sf2, alpha, beta, N, D, fixed = a
     t = time.time()
-    mu, S, _ = O.effective_embedding(sh["X_mu"], sh["X_S"], None, 0.0, fixed)
-    st = O.shard_statistics_chunked(sh["Y"], mu, S, Z, sf2, alpha, chunk=256)
+    if kind == "reference":
+        from oracle import ref_harness as H
+        st = H.map_statistics(sh, Z, sf2, alpha, beta, N, D, 0.0, fixed)
+    else:
+        from oracle import gparml_oracle as O
+        mu, S, _ = O.effective_embedding(sh["X_mu"], sh["X_S"], None, 0.0, fixed)
+        st = O.shard_statistics_chunked(sh["Y"], mu, S, Z, sf2, alpha, chunk=256)
     return st, time.time() - t
 
 
 def _cpu_embed_worker(a):
-    from oracle import gparml_oracle as O
-    sh, Z, sf2, alpha, G1, G2 = a
+    kind, sh, stats, Z, sf2, alpha, beta, N, D, G1, G2 = a
     t = time.time()
-    mu, S, sraw = O.effective_embedding(sh["X_mu"], sh["X_S"], None, 0.0, False)
-    gm, gs = O.embedding_grads(sh["Y"], mu, S, Z, sf2, alpha, G1, G2)
-    g = -np.array([gm, gs * O.softplus_grad(sraw)])
+    if kind == "reference":
+        from oracle import ref_harness as H
+        g = H.map_embeddings(sh, stats, Z, sf2, alpha, beta, N, D, 0.0)
+    else:
+        from oracle import gparml_oracle as O
+        mu, S, sraw = O.effective_embedding(sh["X_mu"], sh["X_S"], None, 0.0, False)
+        gm, gs = O.embedding_grads(sh["Y"], mu, S, Z, sf2, alpha, G1, G2)
+        g = -np.array([gm, gs * O.softplus_grad(sraw)])
     return float(np.abs(g).sum()), time.time() - t
 
 
-class CpuBaseline(object):
+class CpuArm(object):
     def __init__(self, cfg_name, cores, pts_per_worker):
         import multiprocessing
-        from oracle import gparml_oracle as O  # noqa: F401  (the one place bench.py may use oracle/)
+        from oracle import ref_shim  # noqa: F401  (the CPU arm is the one place bench.py may use oracle/)
+        self.kind = "reference" if ref_shim.reference_available() else "port"
+        self.g = block_problem_globals(cfg_name)
         k = CONFIGS[cfg_name]
         self.k, self.cores, self.pts = k, cores, pts_per_worker
         n = cores * pts_per_worker
-        p = make_problem(n, k["M"], k["Q"], k["D"], seed=int(cfg_name[1]), fixed_embeddings=k["fixed_embeddings"])
-        self.p = p
-        self.shards = [dict(Y=p["Y"][lo:hi], X_mu=p["X_mu"][lo:hi], X_S=p["X_S"][lo:hi]) for lo, hi in split_rows(n, cores)]
+        bs = k["N"] // ROW_BLOCKS
+        rows = block_problem_rows(cfg_name, 0, bs * ((n + bs - 1) // bs), with_direction=False)
+        self.n = n
+        self.shards = [dict(Y=rows["Y"][i * pts_per_worker:(i + 1) * pts_per_worker],
+                            X_mu=rows["X_mu"][i * pts_per_worker:(i + 1) * pts_per_worker],
+                            X_S=rows["X_S"][i * pts_per_worker:(i + 1) * pts_per_worker]) for i in range(cores)]
         # spawn (not fork): the parent may already hold a CUDA context; thread env is inherited
         saved = {v: os.environ.get(v) for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}
         _cpu_init()
@@ -100,19 +125,25 @@ class CpuBaseline(object):
 
     def step(self):
         """One evaluation of the sample; returns (wall seconds of the two maps, wall seconds of the master step)."""
-        from oracle import gparml_oracle as O
-        p, k = self.p, self.k
+        g, k = self.g, self.k
+        Z, sf2, alpha, beta, D, fixed = g["Z"], g["sf2"], g["alpha"], g["beta"], k["D"], k["fixed_embeddings"]
         t0 = time.time()
-        res = self.pool.map(_cpu_stats_worker, [(s, p["Z"], p["sf2"], p["alpha"], k["fixed_embeddings"]) for s in self.shards])
+        res = self.pool.map(_cpu_stats_worker, [(self.kind, s, Z, sf2, alpha, beta, self.n, D, fixed) for s in self.shards])
         t_map = time.time() - t0
         t1 = time.time()
-        stats = O.reduce_statistics([r[0] for r in res])
-        g = O.global_step(stats, p["Z"], p["sf2"], p["alpha"], p["beta"], len(p["Y"]))
+        if self.kind == "reference":
+            from oracle import ref_harness as H
+            stats = H.reduce_statistics([r[0] for r in res])
+            gl = H.master_step(stats, Z, sf2, alpha, beta, self.n, D)
+        else:
+            from oracle import gparml_oracle as O
+            stats = O.reduce_statistics([r[0] for r in res])
+            gl = O.global_step(stats, Z, sf2, alpha, beta, self.n)
         t_glob = time.time() - t1
-        if not k["fixed_embeddings"]:
+        if not fixed:
             t2 = time.time()
-            self.pool.map(_cpu_embed_worker, [(s, p["Z"], p["sf2"], p["alpha"], g["dF_dsum_exp_K_miY"],
-                                               g["dF_dsum_exp_K_mi_K_im"]) for s in self.shards])
+            self.pool.map(_cpu_embed_worker, [(self.kind, s, stats, Z, sf2, alpha, beta, self.n, D, gl["dF_dsum_exp_K_miY"],
+                                               gl["dF_dsum_exp_K_mi_K_im"]) for s in self.shards])
             t_map += time.time() - t2
         return t_map, t_glob
 
@@ -123,13 +154,23 @@ class CpuBaseline(object):
     def evals_per_s(self, t_map, t_glob):
         """Linear extrapolation of the maps to the full N (exactly linear: one Python iteration
         per point, partial_terms.py:46,200,278,383,416) plus the master step once."""
-        full = t_map * (self.k["N"] / float(self.cores * self.pts)) + t_glob
+        full = t_map * (self.k["N"] / float(self.n)) + t_glob
         return 1.0 / full
 
     def describe(self):
-        return ("numpy port of the reference maps in a %d-process Pool, %d points per worker (%d of %d points), "
-                "one evaluation, map time extrapolated linearly to N; CSV parsing and .npy transport excluded"
-                % (self.cores, self.pts, self.cores * self.pts, self.k["N"]))
+        what = ("the reference's own partial_terms.py / kernel_exp.py / kernels.py (unmodified, oracle/ref_shim.py), mapper "
+                "bodies of local_MapReduce.py:183-248,310-363 replayed on in-memory arrays" if self.kind == "reference"
+                else "numpy port of the reference maps (oracle/gparml_oracle.py)")
+        return ("%s in a %d-process Pool, %d points per worker (%d of %d points), one evaluation per step, map time "
+                "extrapolated linearly to N; CSV parsing and .npy transport excluded"
+                % (what, self.cores, self.pts, self.n, self.k["N"]))
+
+
+def default_cpu_points(cfg_name, leg):
+    M = CONFIGS[cfg_name]["M"]
+    if M >= 400:
+        return 8
+    return 256
 
 
 def run_reference_arm(args):
@@ -137,9 +178,8 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    k = CONFIGS[args.config]
-    pts = args.cpu_points or (8 if k["M"] >= 400 else 256)
-    cb = CpuBaseline(args.config, cores, pts)
+    pts = args.cpu_points or default_cpu_points(args.config, "arm")
+    cb = CpuArm(args.config, cores, pts)
     for _ in range(args.warmup):
         cb.step()
     t0 = time.time()
@@ -156,7 +196,7 @@ def run_reference_arm(args):
         "warmup": args.warmup, "ms_per_step": 1e3 / val, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.config, args.gpus),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": cb.describe()},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": cb.kind, "sample": cb.describe()},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "sample_wall_s_per_step": wall / args.steps,
     }
@@ -202,20 +242,14 @@ class ClockSampler(object):
         for ln in self.proc.stdout:
             self.lines.append((time.time(), ln.strip()))
 
-    def stop(self, t0=None, t1=None):
-        """Summary of the samples received in the wall-clock window [t0, t1] (the timed regions)."""
+    def window(self, t0, t1):
+        """Summary of the samples received in the wall-clock window [t0, t1] (a timed region)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
+        time.sleep(0.12)          # let the sample that covers the end of the window arrive
         sm, mx, pw, reasons = [], [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        rows = [(t, ln) for t, ln in self.lines if (t0 is None or t >= t0) and (t1 is None or t <= t1 + 0.15)]
-        if not rows:
-            rows = self.lines[-2:]
+        rows = [(t, ln) for t, ln in list(self.lines) if t >= t0 and t <= t1 + 0.15]
         for _, ln in rows:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8 or (self.uuid and self.uuid not in f[0]):
@@ -232,86 +266,120 @@ class ClockSampler(object):
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
                 "samples": len(sm), "reasons": sorted(reasons)}
 
+    def stop(self):
+        if self.proc is None:
+            return
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+
 
 # ----------------------------------------------------------------------------------------
-# our arm
+# one configuration on this rank's GPU
 # ----------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
-    ap.add_argument("--n", type=int, default=0, help="override the total number of points (debug only; marks the line invalid)")
-    ap.add_argument("--cpu-points", type=int, default=0, help="points per CPU worker in the baseline sample")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-chunks", type=int, default=4, help="point ranges of the overlapped gradient download (1..8)")
-    ap.add_argument("--fp32", action="store_true", help="opt-in fp32 map path (psi2_stats / embed_grads in fp32, fp64 sums); "
-                                                        "not the headline configuration")
-    args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "own":
-        args.warmup = 3
-    if args.impl == "reference":
-        return run_reference_arm(args)
+class Env(object):
+    """torch / torch.distributed handles shared by the configurations of one run."""
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- gparml_b200 has no CPU path")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            # NCCL prints its version banner on stdout when the communicator is created; stdout must carry
+            # exactly one JSON line, so file descriptor 1 points at stderr until the first collective is done
+            sys.stdout.flush()
+            saved_fd = os.dup(1)
+            try:
+                os.dup2(2, 1)
+                dist.init_process_group("nccl", device_id=self.dev)
+                warm = torch.zeros(1, device=self.dev)
+                dist.all_reduce(warm)
+                torch.cuda.synchronize()
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved_fd, 1)
+                os.close(saved_fd)
+        uuid = ""
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.local_rank).uuid)
+        except Exception:
+            pass
+        self.sampler = ClockSampler(uuid) if self.rank == 0 else None
+        if self.sampler:
+            self.sampler.start()
 
-    import torch
-    import torch.distributed as dist
+    def timed(self, fn, steps, per_step=None):
+        """K steps bracketed by barrier + synchronize, CUDA events on the launching stream, max over ranks.
+        Returns (ms total, last result, wall-clock window)."""
+        torch, dist = self.torch, self.dist
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.time()
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+            if per_step is not None:
+                per_step()
+        e1.record()
+        torch.cuda.synchronize()
+        w1 = time.time()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), out, (w0, w1)
+
+
+def expected_F(cfg_name):
+    try:
+        v = json.load(open(EXPECTED_F)).get(cfg_name)
+        return float(v) if v is not None else None
+    except Exception:
+        return None
+
+
+def run_config(env, cfg_name, steps, warmup, args, main_line):
+    """Measures one BASELINE configuration; returns the dict of its numbers (rank 0 fills the line with it)."""
+    torch, dist = env.torch, env.dist
     from gparml_b200 import _lib
     from gparml_b200.engine import ShardContext
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- gparml_b200 has no CPU path")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL prints its version banner on stdout when the communicator is created; stdout must carry
-        # exactly one JSON line, so file descriptor 1 points at stderr until the first collective is done
-        sys.stdout.flush()
-        saved_fd = os.dup(1)
-        try:
-            os.dup2(2, 1)
-            dist.init_process_group("nccl", device_id=dev)
-            warm = torch.zeros(1, device=dev)
-            dist.all_reduce(warm)
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved_fd, 1)
-            os.close(saved_fd)
-
-    k = dict(CONFIGS[args.config])
-    if args.n:
-        k["N"] = args.n
-    N, M, Q, D, fixed = k["N"], k["M"], k["Q"], k["D"], k["fixed_embeddings"]
-    p = make_problem(N, M, Q, D, seed=int(args.config[1]), fixed_embeddings=fixed, with_direction=not fixed)
+    from gparml_b200.synthetic import split_rows
+    rank, world = env.rank, env.world
+    g = block_problem_globals(cfg_name)
+    N, M, Q, D, fixed = g["N"], g["M"], g["Q"], g["D"], g["fixed_embeddings"]
     lo, hi = split_rows(N, world)[rank]
     n_loc = hi - lo
+    rows = block_problem_rows(cfg_name, lo, hi, with_direction=not fixed)
 
-    ctx = ShardContext(M, Q, D, N, device=local_rank, fixed_embeddings=fixed, fp32_map=args.fp32)
+    ctx = ShardContext(M, Q, D, N, device=env.local_rank, fixed_embeddings=fixed, fp32_map=args.fp32)
     ctx.use_torch_stream()
     # pinned host copies of the shard (e2e) and of the per-point gradient
-    Yp = torch.from_numpy(np.ascontiguousarray(p["Y"][lo:hi])).pin_memory()
-    MUp = torch.from_numpy(np.ascontiguousarray(p["X_mu"][lo:hi])).pin_memory()
-    Sp = torch.from_numpy(np.ascontiguousarray(p["X_S"][lo:hi])).pin_memory()
+    Yp = torch.from_numpy(rows["Y"]).pin_memory()
+    MUp = torch.from_numpy(rows["X_mu"]).pin_memory()
+    Sp = torch.from_numpy(rows["X_S"]).pin_memory()
     GLp = torch.empty((2, n_loc, Q), dtype=torch.float64).pin_memory()
     ctx.upload_shard_ptrs(Yp.data_ptr(), MUp.data_ptr(), Sp.data_ptr(), n_loc)
     if not fixed:
-        ctx.upload(_lib.A_GRAD_D, p["d"][:, lo:hi])
-    Z, sf2, alpha, beta = p["Z"], p["sf2"], p["alpha"], p["beta"]
-    del p
+        ctx.upload(_lib.A_GRAD_D, rows["d"])
+    Z, sf2, alpha, beta = g["Z"], g["sf2"], g["alpha"], g["beta"]
     stats_view = ctx.stats_torch_view() if world > 1 else None
     step_size = 0.0 if fixed else 1e-4
 
     def evaluation():
         ctx.set_globals(Z, sf2, alpha, beta)
         ctx.set_step(step_size)
-        ctx.statistics()
+        ctx.statistics_launch()          # no host wait: the status word travels with global_step_end
         if world > 1:
             dist.all_reduce(stats_view, op=dist.ReduceOp.SUM)
         if fixed:
@@ -326,7 +394,7 @@ def main():
         ctx.upload_shard_ptrs(Yp.data_ptr(), MUp.data_ptr(), Sp.data_ptr(), n_loc)
         ctx.set_globals(Z, sf2, alpha, beta)
         ctx.set_step(step_size)
-        ctx.statistics()
+        ctx.statistics_launch()
         if world > 1:
             dist.all_reduce(stats_view, op=dist.ReduceOp.SUM)
         if fixed:
@@ -335,60 +403,53 @@ def main():
         ctx.embedding_grads_into(GLp.data_ptr(), chunks=args.e2e_chunks)
         return ctx.global_step_end()
 
-    def timed(fn, steps, collect_phases=False):
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        phases = {}
-        e0.record()
-        for _ in range(steps):
-            out = fn()
-            if collect_phases:
-                for kk, v in ctx.phase_times_ms().items():
-                    phases.setdefault(kk, []).append(v)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), out, phases
-
-    uuid = ""
-    try:
-        uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
-    except Exception:
-        pass
-    sampler = ClockSampler(uuid) if rank == 0 else None
-    if sampler:
-        sampler.start()          # started before the warm-up so that it is sampling when the timed region begins
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         evaluation()
     ctx.enable_timing(True)
     launches0 = ctx.launch_count
-    t_load0 = time.time()
-    ms_total, (F, g), phases = timed(evaluation, args.steps, collect_phases=True)
+    phases = {}
+
+    def collect():
+        for kk, v in ctx.phase_times_ms().items():
+            phases.setdefault(kk, []).append(v)
+    ms_total, (F, gflat), win = env.timed(evaluation, steps, per_step=collect)
     launches = ctx.launch_count - launches0
     ctx.enable_timing(False)
-    ms_per_step = ms_total / args.steps
-    value = 1e3 / ms_per_step
+    ms_per_step = ms_total / steps
+    out = {"config": workload_config(cfg_name, world), "value": 1e3 / ms_per_step, "unit": UNIT, "ms_per_step": ms_per_step,
+           "steps": steps, "warmup": warmup, "gpu_launches": launches, "F": F}
+    out["clocks"] = env.sampler.window(*win) if env.sampler else None
 
-    e2e = None
-    if not args.no_e2e:
+    # the packed all-reduce, timed alone (device events around `steps` back-to-back all-reduces)
+    if world > 1:
+        for _ in range(3):
+            dist.all_reduce(stats_view, op=dist.ReduceOp.SUM)
+        ms_ar, _, _ = env.timed(lambda: dist.all_reduce(stats_view, op=dist.ReduceOp.SUM), 10)
+        out["allreduce"] = {"bytes": int(ctx.stats_count) * 8, "ms": ms_ar / 10}
+        evaluation()                     # the buffer was summed repeatedly: restore a consistent state
+
+    # F against the committed value of this configuration (the data does not depend on the number of ranks)
+    want = expected_F(cfg_name)
+    if want is not None and not args.fp32:
+        rel = abs(F - want) / abs(want)
+        out["F_check"] = {"expected": want, "rel_err": rel, "ok": bool(rel <= 1e-11)}
+        if not rel <= 1e-11:
+            raise SystemExit("bench.py: %s F = %.17g differs from the committed %.17g (rel %.2e) at %d rank(s)"
+                             % (cfg_name, F, want, rel, world))
+
+    if main_line and not args.no_e2e:
         evaluation_e2e()
-        ms_e2e, _, _ = timed(evaluation_e2e, args.steps)
+        ms_e2e, _, _ = env.timed(evaluation_e2e, steps)
         h2d = n_loc * (D + 2 * Q) * 8 + (M * Q + Q + 2) * 8
         d2h = (0 if fixed else 2 * n_loc * Q * 8) + (1 + M * Q + Q + 2) * 8
-        tot = torch.tensor([h2d, d2h], dtype=torch.float64, device=dev)
+        tot = torch.tensor([h2d, d2h], dtype=torch.float64, device=env.dev)
         if world > 1:
             dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        e2e = {"value": 1e3 / (ms_e2e / args.steps), "unit": UNIT, "h2d_bytes_per_step": int(tot[0].item()),
-               "d2h_bytes_per_step": int(tot[1].item()),
-               "api": "upload_shard(Y, X_mu, X_S) from pinned host memory + evaluation + grad_latest back to pinned host, every step"}
+        out["e2e"] = {"value": 1e3 / (ms_e2e / steps), "unit": UNIT, "h2d_bytes_per_step": int(tot[0].item()),
+                      "d2h_bytes_per_step": int(tot[1].item()),
+                      "api": "upload_shard(Y, X_mu, X_S) from pinned host memory + evaluation + grad_latest back to pinned host, every step"}
 
-    clocks = sampler.stop(t_load0, time.time()) if sampler else None   # samples during the two timed loops
-
-    # roofline of the dominant kernel (psi2_stats) on this rank, live CUDA-event durations
+    # ---- rooflines of this rank's kernels, live CUDA-event durations ------------------------------------------
     P = M * (M + 1) // 2
     dfma = ctx.measure_dfma_peak()                       # lane-ops/s, pure DFMA probe on this GPU
     med = {kk: float(np.median(v)) for kk, v in phases.items()}
@@ -421,16 +482,22 @@ def main():
         roofline["note"] = "fp32 map kernels selected: the FP64-pipe roofline above does not describe them"
     total_ops = algorithmic_ops(N, M, Q, D, fixed)
     roofline["whole_evaluation_frac"] = (2.0 * total_ops / world / (ms_per_step * 1e-3) / 1e12) / peak
-    # DRAM traffic of the dominant kernel from the committed ncu --set full capture of the same workload
+    # DRAM traffic from the committed ncu --set full captures of the same workload
+    traffic = {}
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01c.json")))
-        ent = tr.get(args.config, {}).get("psi2_stats_kernel")
-        if ent and int(ent["n_local"]) == n_loc:
-            roofline["traffic"] = ent["dram_bytes"]
-            roofline["traffic_source"] = ent.get("source")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", args.traffic_file))).get(cfg_name, {})
     except Exception:
         pass
-    # the HBM-bound streaming kernel (prep_points): algorithmic bytes against the measured copy bandwidth
+
+    def dram(kernel):
+        ent = traffic.get(kernel)
+        if ent and int(ent["n_local"]) == n_loc:
+            return ent["dram_bytes"], ent.get("source")
+        return None, None
+    roofline["traffic"], src = dram("psi2_stats_kernel")
+    if src:
+        roofline["traffic_source"] = src
+    # the HBM-bound streaming kernels: algorithmic bytes against the measured copy bandwidth
     hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
     try:
         mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -443,36 +510,151 @@ def main():
         gbs = prep_bytes / (med["prep_points"] * 1e-3) / 1e9
         roofline["prep_points_hbm"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                                        "peak_source": hbm_src, "algorithmic_bytes_per_launch": prep_bytes,
-                                       "launch_ms": med["prep_points"]}
+                                       "launch_ms": med["prep_points"], "traffic": dram("prep_points_kernel")[0]}
+    out["roofline"] = roofline
+    out["phase_ms_median"] = med
+
+    # ---- the same evaluation through the reference's interface (parallel_GPLVM protocol on b200_MapReduce) -----
+    if main_line and not args.no_through_driver and not args.fp32:
+        ctx.synchronize()
+        out["through_driver"] = through_driver(env, cfg_name, g, rows, steps, warmup, step_size, F)
+    ctx.close()
+    del Yp, MUp, Sp, GLp, rows
+    return out
+
+
+def through_driver(env, cfg_name, g, rows, steps, warmup, step_size, F_raw):
+    """Times ``parallel_GPLVM.likelihood_and_gradient(x, i, step)`` -- the callback the reference's optimiser calls
+    (parallel_GPLVM.py:222-279) -- on the b200_MapReduce backend: one input file per rank (``.npy`` shards), the
+    ``--load`` path for the initial state (the 'f' checkpoint files are written below), no per-evaluation files."""
+    from gparml_b200 import b200_MapReduce, parallel_GPLVM as drv
+    rank, world = env.rank, env.world
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    work = [tempfile.mkdtemp(prefix="gparml_bench_", dir=base) if rank == 0 else None]
+    if world > 1:
+        env.dist.broadcast_object_list(work, src=0, device=env.dev)
+    work = work[0]
+    dirs = {d: os.path.join(work, d) for d in ("input", "embeddings", "statistics", "tmp")}
+    try:
+        if rank == 0:
+            for d in dirs.values():
+                os.makedirs(d)
+            for key, val in (("Z", g["Z"]), ("sf2", np.array([[g["sf2"]]])), ("alpha", g["alpha"].reshape(1, -1)),
+                             ("beta", np.array([[g["beta"]]]))):
+                np.save(os.path.join(dirs["statistics"], "global_statistics_%s_f.npy" % key), val)
+        if world > 1:
+            env.dist.barrier()
+        name = "shard_%03d.npy" % rank
+        np.save(os.path.join(dirs["input"], name), rows["Y"])
+        np.save(os.path.join(dirs["embeddings"], name + ".embedding.npy"), rows["X_mu"])
+        np.save(os.path.join(dirs["embeddings"], name + ".variance.npy"), rows["X_S"])
+        if "d" in rows:
+            np.save(os.path.join(dirs["embeddings"], name + ".grad_d.npy"), rows["d"])
+        if world > 1:
+            env.dist.barrier()
+        # b200_stream='torch': the shard contexts work on torch's current stream, the one the CUDA events of
+        # Env.timed are recorded on (on their own streams the last step's embeddings map would fall outside e0..e1)
+        opts = drv.default_options(M=g["M"], Q=g["Q"], D=g["D"], load=True, fixed_embeddings=g["fixed_embeddings"],
+                                   b200_write_files=False, b200_stream="torch", display=False, **dirs)
+        opts = b200_MapReduce.init(opts)
+        opts, gs = drv.init_statistics(b200_MapReduce, opts)
+        x0 = drv.flatten_global_statistics(opts, gs)
+        x0 = np.array([drv.sp.transform_back(b, x) for b, x in zip(opts["flat_global_statistics_bounds"], x0)])
+        drv.options, drv.map_reduce = opts, b200_MapReduce
+        it = [0]
+
+        def call():
+            it[0] += 1
+            return drv.likelihood_and_gradient(x0, it[0], step_size)
+        for _ in range(max(warmup, 1)):
+            f, grad = call()
+        ms, (f, grad), _ = env.timed(call, steps)
+        rel = abs(-f - F_raw) / abs(F_raw)
+        if not rel <= 1e-12:
+            raise SystemExit("bench.py: F through the driver (%.17g) differs from the C-ABI loop (%.17g)" % (-f, F_raw))
+        return {"value": 1e3 / (ms / steps), "unit": UNIT, "ms_per_step": ms / steps,
+                "api": "gparml_b200.parallel_GPLVM.likelihood_and_gradient(x, i, step_size) on b200_MapReduce "
+                       "(parallel_GPLVM.py:222-279 protocol, one input shard per rank, b200_write_files=False)",
+                "F_matches_c_abi_loop": True}
+    finally:
+        b200_MapReduce.close()
+        if world > 1:
+            env.dist.barrier()
+        if rank == 0:
+            shutil.rmtree(work, ignore_errors=True)
+
+
+# ----------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
+    ap.add_argument("--other-configs", default="c5,c4,c2", help="comma-separated BASELINE configs measured after the main one "
+                                                                "('' = none); only with the default main config c3")
+    ap.add_argument("--other-steps", type=int, default=3)
+    ap.add_argument("--cpu-points", type=int, default=0, help="points per CPU worker in the baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-through-driver", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="point ranges of the overlapped gradient download (1..8)")
+    ap.add_argument("--traffic-file", default="ncu_traffic_r02.json")
+    ap.add_argument("--fp32", action="store_true", help="opt-in fp32 map path (psi2_stats / embed_grads in fp32, fp64 sums); "
+                                                        "not the headline configuration")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "own":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    env = Env()
+    rank, world = env.rank, env.world
+    res = run_config(env, args.config, args.steps, args.warmup, args, main_line=True)
+    others = []
+    if args.config == "c3" and not args.fp32:
+        for name in [c for c in args.other_configs.split(",") if c]:
+            o = run_config(env, name, args.other_steps, 3, args, main_line=False)
+            r = o["roofline"]
+            others.append({"config": o["config"], "value": o["value"], "unit": UNIT, "ms_per_step": o["ms_per_step"],
+                           "steps": o["steps"], "warmup": o["warmup"], "clocks": o["clocks"], "F": o["F"],
+                           "F_check": o.get("F_check"), "allreduce": o.get("allreduce"),
+                           "psi2_stats": {"frac": r["frac"], "executed_frac": r["executed_frac"], "launch_ms": r["launch_ms"]},
+                           "embed_grads": ({"frac": r["embed_grads"]["frac"], "executed_frac": r["embed_grads"]["executed_frac"],
+                                            "launch_ms": r["embed_grads"]["launch_ms"]} if "embed_grads" in r else None),
+                           "whole_evaluation_frac": r["whole_evaluation_frac"], "phase_ms_median": o["phase_ms_median"]})
+    if env.sampler:
+        env.sampler.stop()
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32 maps, f64 sums and master step (opt-in)" if args.fp32 else "f64",
-        "data": "synthetic", "config": workload_config(args.config, world), "clocks": clocks, "e2e": e2e,
-        "gpu_launches": launches, "roofline": roofline, "phase_ms_median": med,
-        "F": F,
+        "data": "synthetic", "config": res["config"], "clocks": res["clocks"], "e2e": res.get("e2e"),
+        "through_driver": res.get("through_driver"),
+        "gpu_launches": res["gpu_launches"], "roofline": res["roofline"], "phase_ms_median": res["phase_ms_median"],
+        "F": res["F"], "F_check": res.get("F_check"), "allreduce": res.get("allreduce"), "other_configs": others,
     }
-    if args.n:
-        line["config"]["debug_n_override"] = args.n
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             cores = os.cpu_count() or 1
-            pts = args.cpu_points or (16 if M >= 400 else 1024)
-            cb = CpuBaseline(args.config, cores, pts)
+            pts = args.cpu_points or default_cpu_points(args.config, "baseline")
+            cb = CpuArm(args.config, cores, pts)
             tm, tg = cb.step()
             cb.close()
-            line["cpu_baseline"] = {"value": cb.evals_per_s(tm, tg), "unit": UNIT, "cores": cores, "kind": "port",
+            line["cpu_baseline"] = {"value": cb.evals_per_s(tm, tg), "unit": UNIT, "cores": cores, "kind": cb.kind,
                                     "sample": cb.describe(), "sample_wall_s": tm + tg}
         except Exception as e:  # the baseline must never take the GPU line down with it
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
-    ctx.close()
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        env.dist.barrier()
+        env.dist.destroy_process_group()
     return 0
 
 

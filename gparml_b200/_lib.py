@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("GPARML_B200_LIB") or os.path.join(HERE, "libgparml_b2
 OK, ERR_CUDA, ERR_ARG, ERR_NOT_PD, ERR_STATE, ERR_NO_DEVICE, ERR_RANGE = 0, -1, -2, -3, -4, -5, -6
 FLAG_FP32_MAP, FLAG_FIXED_EMBEDDINGS, FLAG_FIXED_BETA = 1, 2, 4
 VARIANCE_UNCONSTRAINED, VARIANCE_POSITIVE = 0, 1
+MAX_PEERS = 16      # GPARML_MAX_PEERS
 
 (A_X_MU, A_X_S, A_GRAD_D, A_GRAD_LATEST, A_GRAD_NEW, A_GRAD_OLD, A_STATS, A_KMM, A_KMM_INV, A_A_INV,
  A_DF_DKMM, A_DF_DPSI1Y, A_DF_DPSI2, A_PSI1, A_GRAD_X_MU, A_GRAD_X_S, A_Y, A_GRAD_GLOBAL) = range(18)
@@ -51,6 +52,8 @@ PROTOTYPES = {
     "gparml_set_globals": (ctypes.c_int, [_vp, _vp, ctypes.c_double, _vp, ctypes.c_double]),
     "gparml_set_step": (ctypes.c_int, [_vp, ctypes.c_double]),
     "gparml_statistics": (ctypes.c_int, [_vp]),
+    "gparml_statistics_launch": (ctypes.c_int, [_vp]),
+    "gparml_status": (ctypes.c_int, [_vp]),
     "gparml_stats_count": (_i64, [_vp]),
     "gparml_stats_device_ptr": (ctypes.c_int, [_vp, ctypes.POINTER(_vp)]),
     "gparml_stats_add": (ctypes.c_int, [_vp, _vp, ctypes.c_double]),
@@ -66,6 +69,8 @@ PROTOTYPES = {
     "gparml_kmm_derivative": (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
     "gparml_grad_contract": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gparml_stats_add_peer": (ctypes.c_int, [_vp, _vp, ctypes.c_double]),
+    "gparml_stats_copy_peer": (ctypes.c_int, [_vp, _vp]),
+    "gparml_stats_allreduce_peers": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_double]),
     "gparml_array_count": (_i64, [_vp, ctypes.c_int]),
     "gparml_download": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _i64]),
     "gparml_upload": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _i64]),

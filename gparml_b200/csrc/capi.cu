@@ -446,7 +446,11 @@ static int prep_if_needed(gparml_ctx *c)
     return GPARML_OK;
 }
 
-extern "C" int gparml_statistics(gparml_ctx *c)
+// The statistics map without any host synchronisation: everything is queued on the context's streams and the
+// call returns.  Device-side failures (unconstrained variance out of range) stay in the device status word, which
+// gparml_status / gparml_global_step_end read back -- so a host thread that drives several GPUs can launch all of
+// its shards before it waits for any of them (the reference forks one mapper per shard, local_MapReduce.py:134).
+extern "C" int gparml_statistics_launch(gparml_ctx *c)
 {
     CHECK_CTX_PIPE(c);
     GP_TRY(finish_pending_gs(c));
@@ -489,6 +493,21 @@ extern "C" int gparml_statistics(gparml_ctx *c)
     GP_TRY(record(c, 3));
     c->have_stats = true;
     c->have_global_step = false;
+    return GPARML_OK;
+}
+
+// Waits for the context's stream and reports (and clears) the device status word.
+extern "C" int gparml_status(gparml_ctx *c)
+{
+    CHECK_CTX(c);
+    return check_status(c, true);
+}
+
+// Blocking form: the statistics map, then -- where a device-side check can fail (unconstrained variances,
+// supporting_functions.py:154) -- the status word, so that the assert surfaces in this call like in the reference.
+extern "C" int gparml_statistics(gparml_ctx *c)
+{
+    GP_TRY(gparml_statistics_launch(c));
     if (!(c->flags & GPARML_FLAG_FIXED_EMBEDDINGS) && c->variance_domain == GPARML_VARIANCE_UNCONSTRAINED)
         GP_TRY(check_status(c, true));
     return GPARML_OK;
@@ -901,19 +920,94 @@ extern "C" int gparml_grad_contract(gparml_ctx *c, int which, const double *dF_d
     return GPARML_OK;
 }
 
-// In-process reduce across devices: stats += packed buffer of a context on ANOTHER device
-// (peer copy into scratch, then the same fixed-order add).
+// ---------------------------------------------------------------------------
+// in-process reduce across the shard contexts of ONE host thread (any mix of devices); no host synchronisation
+// ---------------------------------------------------------------------------
+// order c's stream behind everything queued so far on other's stream (works across devices)
+static int wait_for(gparml_ctx *c, gparml_ctx *other)
+{
+    if (other == c) return GPARML_OK;
+    GP_CUDA(cudaSetDevice(other->device));
+    GP_CUDA(cudaEventRecord(other->ev_main, other->stream));
+    GP_CUDA(cudaSetDevice(c->device));
+    GP_CUDA(cudaStreamWaitEvent(c->stream, other->ev_main, 0));
+    return GPARML_OK;
+}
+
+// stats += packed buffer of a context on ANOTHER device (peer copy into scratch, then the same fixed-order add)
 extern "C" int gparml_stats_add_peer(gparml_ctx *c, gparml_ctx *other, double scale)
 {
     CHECK_CTX(c);
     GP_TRY(finish_pending_gs(c));
     if (!other || other->L.count != c->L.count) { gp_set_error("stats_add_peer: incompatible contexts"); return GPARML_ERR_ARG; }
-    GP_CUDA(cudaSetDevice(other->device));
-    GP_CUDA(cudaStreamSynchronize(other->stream));
-    GP_CUDA(cudaSetDevice(c->device));
     GP_TRY(gp_ensure_ws(c, (size_t)c->L.count * sizeof(double)));
+    GP_TRY(wait_for(c, other));
     GP_CUDA(cudaMemcpyPeerAsync(c->ws, c->device, other->stats, other->device, (size_t)c->L.count * sizeof(double), c->stream));
     GP_TRY(gp_launch_stats_add(c, c->ws, scale));
     c->have_global_step = false;
+    return GPARML_OK;
+}
+
+// stats = packed buffer of `other` (same or another device)
+extern "C" int gparml_stats_copy_peer(gparml_ctx *c, gparml_ctx *other)
+{
+    CHECK_CTX(c);
+    GP_TRY(finish_pending_gs(c));
+    if (!other || other->L.count != c->L.count) { gp_set_error("stats_copy_peer: incompatible contexts"); return GPARML_ERR_ARG; }
+    if (other == c) return GPARML_OK;
+    GP_TRY(wait_for(c, other));
+    GP_CUDA(cudaMemcpyPeerAsync(c->stats, c->device, other->stats, other->device, (size_t)c->L.count * sizeof(double), c->stream));
+    c->have_stats = true;
+    c->have_global_step = false;
+    return GPARML_OK;
+}
+
+int gp_launch_stats_allreduce(gparml_ctx *root, double *const *bufs, int n, double scale);
+
+// The reducer (local_MapReduce.py:250-277) for n shard contexts driven by one host thread: ONE kernel on the first
+// context's device reads every context's packed buffer -- directly over NVLink peer memory when the contexts live on
+// different GPUs -- adds them in list order (deterministic), scales (drop-out, :263-264) and stores the sum back into
+// EVERY context's buffer, so each GPU can run its replicated master step without a second transfer.  Streams are
+// ordered with events; the host never waits.  Falls back to peer copies when a pair of devices has no peer access.
+extern "C" int gparml_stats_allreduce_peers(gparml_ctx **ctxs, int n, double scale)
+{
+    if (!ctxs || n < 1 || n > GPARML_MAX_PEERS) { gp_set_error("stats_allreduce_peers: 1..%d contexts", GPARML_MAX_PEERS); return GPARML_ERR_ARG; }
+    gparml_ctx *root = ctxs[0];
+    for (int g = 0; g < n; ++g) {
+        if (!ctxs[g] || ctxs[g]->L.count != root->L.count) { gp_set_error("stats_allreduce_peers: incompatible contexts"); return GPARML_ERR_ARG; }
+        for (int h = 0; h < g; ++h)
+            if (ctxs[h] == ctxs[g]) { gp_set_error("stats_allreduce_peers: context listed twice"); return GPARML_ERR_ARG; }
+        CHECK_CTX(ctxs[g]);
+        GP_TRY(finish_pending_gs(ctxs[g]));
+    }
+    GP_CUDA(cudaSetDevice(root->device));
+    bool direct = true;
+    for (int g = 1; g < n && direct; ++g) {
+        if (ctxs[g]->device == root->device) continue;
+        int can = 0;
+        GP_CUDA(cudaDeviceCanAccessPeer(&can, root->device, ctxs[g]->device));
+        if (!can) { direct = false; break; }
+        cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[g]->device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else if (e != cudaSuccess) { cudaGetLastError(); direct = false; }
+    }
+    if (direct) {
+        double *bufs[GPARML_MAX_PEERS];
+        for (int g = 0; g < n; ++g) {
+            bufs[g] = ctxs[g]->stats;
+            GP_TRY(wait_for(root, ctxs[g]));
+        }
+        GP_TRY(gp_launch_stats_allreduce(root, bufs, n, scale));
+        GP_CUDA(cudaEventRecord(root->ev_main, root->stream));
+        for (int g = 1; g < n; ++g) {
+            GP_CUDA(cudaSetDevice(ctxs[g]->device));
+            GP_CUDA(cudaStreamWaitEvent(ctxs[g]->stream, root->ev_main, 0));
+        }
+    } else {
+        for (int g = 1; g < n; ++g) GP_TRY(gparml_stats_add_peer(root, ctxs[g], g == n - 1 ? scale : 1.0));
+        if (n == 1 && scale != 1.0) GP_TRY(gp_launch_stats_add(root, root->stats, 0.5 * scale));
+        for (int g = 1; g < n; ++g) GP_TRY(gparml_stats_copy_peer(ctxs[g], root));
+    }
+    for (int g = 0; g < n; ++g) { ctxs[g]->have_stats = true; ctxs[g]->have_global_step = false; }
     return GPARML_OK;
 }

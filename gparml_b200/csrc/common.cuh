@@ -58,7 +58,9 @@ struct StatLayout {
     int64_t off_ta;   // (Q, P)   sum_n Psi2_n ((w (mu - zbar))^2 + alpha S w)
     int64_t count;
 };
-enum { ST_YYT = 0, ST_PSI0 = 1, ST_KL = 2, ST_NLOCAL = 3, ST_HEAD = 4 };
+// ST_FLAGS: number of shards whose input check failed (unconstrained variance out of range); it is summed by the
+// reducer / all-reduce like everything else, so EVERY rank's master step reports GPARML_ERR_RANGE together.
+enum { ST_YYT = 0, ST_PSI0 = 1, ST_KL = 2, ST_NLOCAL = 3, ST_FLAGS = 4, ST_HEAD = 6 };
 
 __host__ __device__ inline int64_t gp_pair_index(int M, int a, int b)  // a <= b
 {

@@ -21,9 +21,14 @@
 // failed pivot reports GPARML_ERR_NOT_PD (the caller raises LinAlgError, which the reference's
 // optimiser wrapper turns into f = inf, scg_adapted.py:55).
 //
-// Two M x M work matrices (X, W) live in shared memory when 2 M^2 doubles fit (M <= 118);
-// larger M runs the same code on L2-resident global scratch.  The kernel is replicated on
+// Two M x M work matrices (X, W) live in shared memory when 2 M^2 doubles fit (M <= 116);
+// larger M takes the multi-kernel path of global_step_large.cu.  The kernels are replicated on
 // every GPU after the all-reduce, so no second broadcast is needed.
+//
+// Three launches per evaluation: kmm_only (Kmm, Kmm^-1: side stream at set_globals), the head
+// (A^-1, dF/dPsi1Y, dF/dPsi2, pair tables: everything embed_grads waits for -- one inversion, no
+// M x M x M product) and the tail (dF/dKmm with its two products, the bound and the hyper-parameter
+// gradients: side stream, concurrent with embed_grads).
 #include <math.h>
 
 #include "gs_common.cuh"
@@ -209,24 +214,29 @@ __global__ void __launch_bounds__(GS_THREADS, 1) global_step_kernel(GsParams p)
         if (tid == 0) ldk_slot[0] = ldK;
         return;
     }
+    if (tid == 0 && p.stats[ST_FLAGS] != 0.0) atomicOr(p.status, 4);      // some shard (any rank) failed its input check
     if (*p.status & 1) return;                 // Kmm was not positive definite
     ldK = ldk_slot[0];
-    for (size_t idx = tid; idx < MM; idx += GS_THREADS) {
-        const int i = (int)(idx / M), j = (int)(idx % M);
-        W[idx] = p.kmm_inv[idx];               // Kmm^-1
-        P2[idx] = S0[pidx(M, i, j)];           // full Psi2
-    }
-    __syncthreads();
 
-    // ---- A = Kmm + beta Psi2, A^-1 (partial_terms.py:60) ---------------------------------------
-    for (size_t idx = tid; idx < MM; idx += GS_THREADS) X[idx] = fma(beta, P2[idx], p.kmm[idx]);
+    // ---- head of the master step: what the embeddings map waits for (dF/dPsi1Y, dF/dPsi2 -> pair tables) --------
+    // Neither needs an M x M x M product: dF/dPsi2 = 1/2 beta D (Kmm^-1 - A^-1) - 1/2 beta^3 C C^T
+    // (partial_terms.py:123-131).  The two products behind dF/dKmm (Kmm^-1 Psi2 Kmm^-1, :102-113) only feed the
+    // gradients of Z / alpha / sf2 and run in global_step_tail_kernel on the side stream, next to embed_grads.
+    // full Psi2 and A = Kmm + beta Psi2 (partial_terms.py:60); row loops, no integer division
+    for (int i = wid; i < M; i += GS_THREADS / 32) {
+        const size_t ro = (size_t)i * M;
+        for (int j = lane; j < M; j += 32) {
+            const double ps = S0[pidx(M, i, j)];
+            P2[ro + j] = ps;
+            X[ro + j] = fma(beta, ps, p.kmm[ro + j]);
+        }
+    }
     __syncthreads();
     if (!gs_sweep_invert(X, M, tmp, piv, red, &ldA)) {
         if (tid == 0) atomicOr(p.status, 2);
         return;
     }
-    for (size_t idx = tid; idx < MM; idx += GS_THREADS) p.a_inv[idx] = -X[idx];
-    __syncthreads();
+    // X = -A^-1 from here on
 
     // ---- C = A^-1 Psi1Y, G1 = beta^2 C (partial_terms.py:115-121) -----------------------------
     for (int idx = tid; idx < M * D; idx += GS_THREADS) {
@@ -235,72 +245,82 @@ __global__ void __launch_bounds__(GS_THREADS, 1) global_step_kernel(GsParams p)
         for (int k = 0; k < M; ++k) s = fma(-X[(size_t)i * M + k], P1Y[(size_t)k * D + d], s);
         p.c_mat[idx] = s;
         p.g_1[idx] = beta * beta * s;
+        if (D <= M) W[idx] = s;               // shared copy for the C C^T loop below (W is free in the head)
     }
     __syncthreads();
+    const double *Cs = (D <= M) ? W : p.c_mat;
     double v = 0.0;
-    for (int idx = tid; idx < M * D; idx += GS_THREADS) v = fma(P1Y[idx], p.c_mat[idx], v);
+    for (int idx = tid; idx < M * D; idx += GS_THREADS) v = fma(P1Y[idx], Cs[idx], v);
     const double tr1 = gp_block_sum(v, red);               // tr(Psi1Y^T A^-1 Psi1Y)
 
-    // ---- U = Psi2 Kmm^-1 -> X  (X no longer needed: A^-1 lives in p.a_inv) ---------------------
+    // ---- dF/dPsi2 (partial_terms.py:123-131) and the scalar contractions that need A^-1 only ----
+    double s_ap = 0.0, s_cpc = 0.0, s_22 = 0.0;
+    const double hD = 0.5 * (double)D, b3 = 0.5 * beta * beta * beta;
+    for (int i = wid; i < M; i += GS_THREADS / 32) {
+        const size_t ro = (size_t)i * M;
+        for (int j = lane; j < M; j += 32) {
+            double e = 0.0;
+            for (int d = 0; d < D; ++d) e = fma(Cs[i * D + d], Cs[j * D + d], e);     // (C C^T)[i,j]
+            const double ai = -X[ro + j], ps = P2[ro + j];
+            const double g2 = hD * beta * (p.kmm_inv[ro + j] - ai) - b3 * e;
+            p.a_inv[ro + j] = ai;
+            p.g_2[ro + j] = g2;
+            s_ap = fma(ai, ps, s_ap);
+            s_cpc = fma(ps, e, s_cpc);
+            s_22 = fma(g2, ps, s_22);
+        }
+    }
+    s_ap = gp_block_sum(s_ap, red);      // tr(A^-1 Psi2)
+    s_cpc = gp_block_sum(s_cpc, red);    // tr(C^T Psi2 C)
+    s_22 = gp_block_sum(s_22, red);      // <dF/dPsi2, Psi2>
+    if (tid == 0) {
+        double *extra = p.out + 1 + M * Q + Q + 2;
+        extra[0] = ldK; extra[1] = ldA; extra[3] = tr1;
+        extra[4] = s_ap; extra[5] = s_cpc; extra[7] = s_22;
+    }
+    __syncthreads();                     // publishes g_2 to the whole CTA
+    gs_pair_tables(p, p.g_2);
+}
+
+// Tail of the master step: dF/dKmm (partial_terms.py:102-113) with its two M x M x M products, then the bound
+// and the hyper-parameter gradients (gs_tail).  One CTA; independent of embed_grads, so it runs concurrently with
+// it on the side stream (capi.cu gparml_global_step_begin).
+__global__ void __launch_bounds__(GS_THREADS, 1) global_step_tail_kernel(GsParams p)
+{
+    extern __shared__ __align__(16) double sm[];
+    __shared__ double red[33];
+    __shared__ double qred[32 * GP_MAX_Q];
+    __shared__ double ia2[GP_MAX_Q];
+    if (*p.status & 3) return;
+    const int M = p.M, D = p.D;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const size_t MM = (size_t)M * M;
+    double *X = sm, *W = sm + MM;
+    const double beta = p.glob->beta;
+    const double *P2 = p.psi2_full;
+    for (size_t idx = tid; idx < MM; idx += GS_THREADS) W[idx] = p.kmm_inv[idx];
+    __syncthreads();
+    // U = Psi2 Kmm^-1 -> X
     gs_matmul(P2, W, M, [&](int i, int j, double val) { X[(size_t)i * M + j] = val; });
     __syncthreads();
-    v = 0.0;
+    double v = 0.0;
     for (int i = tid; i < M; i += GS_THREADS) v += X[(size_t)i * M + i];
     const double trKP = gp_block_sum(v, red);              // tr(Kmm^-1 Psi2)
-
-    // ---- dF/dKmm, dF/dPsi2 (partial_terms.py:102-131) and the scalar contractions ------------
-    double s_ap = 0.0, s_cpc = 0.0, s_kk = 0.0, s_22 = 0.0;
+    double s_kk = 0.0;
     const double hD = 0.5 * (double)D;
     gs_matmul(W, X, M, [&](int i, int j, double t) {       // t = (Kinv Psi2 Kinv)[i,j]
         const size_t idx = (size_t)i * M + j;
         double e = 0.0;
         for (int d = 0; d < D; ++d) e = fma(p.c_mat[i * D + d], p.c_mat[j * D + d], e);     // (C C^T)[i,j]
-        const double ai = p.a_inv[idx], wi = W[idx], ps = P2[idx];
-        const double gk = hD * wi - hD * ai - hD * beta * t - 0.5 * beta * beta * e;
-        const double g2 = hD * beta * (wi - ai) - 0.5 * beta * beta * beta * e;
+        const double gk = hD * W[idx] - hD * p.a_inv[idx] - hD * beta * t - 0.5 * beta * beta * e;
         p.g_k[idx] = gk;
-        p.g_2[idx] = g2;
-        s_ap = fma(ai, ps, s_ap);
-        s_cpc = fma(ps, e, s_cpc);
         s_kk = fma(gk, p.kmm[idx], s_kk);
-        s_22 = fma(g2, ps, s_22);
     });
-    s_ap = gp_block_sum(s_ap, red);      // tr(A^-1 Psi2)
-    s_cpc = gp_block_sum(s_cpc, red);    // tr(C^T Psi2 C)
     s_kk = gp_block_sum(s_kk, red);      // <dF/dKmm, Kmm>
-    s_22 = gp_block_sum(s_22, red);      // <dF/dPsi2, Psi2>
     __syncthreads();
-    if (p.phase == 1) {
-        // embed_grads needs dF/dPsi1Y (g_1) and the pair tables only: publish them and the scalars of the
-        // tail, which runs as its own kernel (global_step_tail_kernel) next to the embeddings map
-        if (tid == 0) {
-            double *extra = p.out + 1 + M * Q + Q + 2;
-            extra[0] = ldK; extra[1] = ldA; extra[2] = trKP; extra[3] = tr1;
-            extra[4] = s_ap; extra[5] = s_cpc; extra[6] = s_kk; extra[7] = s_22;
-        }
-        gs_pair_tables(p, p.g_2);
-        return;
-    }
-    // the work matrices are free now: keep dF/dKmm in X and dF/dPsi2 in W for the contractions
-    for (size_t idx = tid; idx < MM; idx += GS_THREADS) {
-        X[idx] = p.g_k[idx];
-        W[idx] = p.g_2[idx];
-    }
-    __syncthreads();
-
-    gs_tail(p, X, W, P2, ldK, ldA, tr1, trKP, s_ap, s_cpc, s_kk, s_22, qred, ia2);
-    gs_pair_tables(p, W);
-}
-
-// phase 2: bound and hyper-parameter gradients from the partial derivatives left in global memory by
-// phase 1 (O(M^2 Q) work of one CTA; independent of embed_grads, so it runs concurrently with it)
-__global__ void __launch_bounds__(GS_THREADS, 1) global_step_tail_kernel(GsParams p)
-{
-    __shared__ double qred[32 * GP_MAX_Q];
-    __shared__ double ia2[GP_MAX_Q];
-    if (*p.status & 3) return;
+    (void)lane; (void)wid;
     const double *extra = p.out + 1 + p.M * p.Q + p.Q + 2;
-    gs_tail(p, p.g_k, p.g_2, p.psi2_full, extra[0], extra[1], extra[3], extra[2], extra[4], extra[5], extra[6], extra[7], qred, ia2);
+    gs_tail(p, p.g_k, p.g_2, P2, extra[0], extra[1], extra[3], trKP, extra[4], extra[5], s_kk, extra[7], qred, ia2);
 }
 
 int gp_launch_global_step_large(gparml_ctx *c, GsParams &p);
@@ -371,12 +391,20 @@ static int launch_gs(gparml_ctx *c, bool kmm_only, int phase)
         return gp_launch_global_step_large(c, p);
     }
     if (phase == 2) {
-        global_step_tail_kernel<<<1, GS_THREADS, 0, c->stream>>>(p);
+        const size_t smem_tail = 2 * MM * sizeof(double);
+        GP_CUDA(cudaFuncSetAttribute(global_step_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tail));
+        global_step_tail_kernel<<<1, GS_THREADS, smem_tail, c->stream>>>(p);
         GP_LAUNCH_CHECK(c);
         return GPARML_OK;
     }
     GP_CUDA(cudaFuncSetAttribute(global_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     global_step_kernel<<<1, GS_THREADS, smem, c->stream>>>(p);
     GP_LAUNCH_CHECK(c);
+    if (!kmm_only && phase == 0) {          // whole master step on one stream: head, then tail
+        const size_t smem_tail = 2 * MM * sizeof(double);
+        GP_CUDA(cudaFuncSetAttribute(global_step_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tail));
+        global_step_tail_kernel<<<1, GS_THREADS, smem_tail, c->stream>>>(p);
+        GP_LAUNCH_CHECK(c);
+    }
     return GPARML_OK;
 }

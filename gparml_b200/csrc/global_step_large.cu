@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(256) gsl_build_kernel(GsParams p, double *__re
 {
     const int M = p.M, Q = p.Q;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx == 0 && !p.kmm_only && p.stats[ST_FLAGS] != 0.0) atomicOr(p.status, 4);      // see common.cuh ST_FLAGS
     if (idx >= (size_t)M * M) return;
     const int i = (int)(idx / M), j = (int)(idx % M);
     double s = 0.0;

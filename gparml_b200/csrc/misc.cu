@@ -105,6 +105,48 @@ int gp_launch_stats_add(gparml_ctx *c, const double *src, double scale)
     return GPARML_OK;
 }
 
+// One-kernel all-reduce over the packed buffers of up to GPARML_MAX_PEERS contexts (the buffers of contexts on
+// other GPUs are addressed directly: NVLink peer loads and stores).  Each thread owns two consecutive elements of
+// every buffer: it reads them from all n buffers (all loads in flight before the first add), sums in list order,
+// scales, and writes the result back to all n buffers -- element-wise, so reading and writing the same buffers in
+// one kernel is race-free.
+struct PeerBufs { double *p[GPARML_MAX_PEERS]; };
+
+__global__ void __launch_bounds__(256) stats_allreduce_kernel(PeerBufs b, int n, int64_t count, double scale)
+{
+    const int64_t i = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    if (i >= count) return;
+    if (i + 1 < count) {        // packed buffers are cudaMalloc'ed: 16-byte aligned
+        double2 v[GPARML_MAX_PEERS];
+#pragma unroll
+        for (int g = 0; g < GPARML_MAX_PEERS; ++g)
+            if (g < n) v[g] = __ldcg(reinterpret_cast<const double2 *>(b.p[g] + i));      // L2 only: never a stale L1 line
+        double2 a = v[0];
+#pragma unroll
+        for (int g = 1; g < GPARML_MAX_PEERS; ++g)
+            if (g < n) { a.x += v[g].x; a.y += v[g].y; }
+        a.x *= scale; a.y *= scale;
+#pragma unroll
+        for (int g = 0; g < GPARML_MAX_PEERS; ++g)
+            if (g < n) *reinterpret_cast<double2 *>(b.p[g] + i) = a;
+    } else {
+        double a = __ldcg(b.p[0] + i);
+        for (int g = 1; g < n; ++g) a += __ldcg(b.p[g] + i);
+        a *= scale;
+        for (int g = 0; g < n; ++g) b.p[g][i] = a;
+    }
+}
+
+int gp_launch_stats_allreduce(gparml_ctx *root, double *const *bufs, int n, double scale)
+{
+    PeerBufs b;
+    for (int g = 0; g < GPARML_MAX_PEERS; ++g) b.p[g] = g < n ? bufs[g] : nullptr;
+    const int64_t count = root->L.count, threads = (count + 1) / 2;
+    stats_allreduce_kernel<<<(int)((threads + 255) / 256), 256, 0, root->stream>>>(b, n, count, scale);
+    GP_LAUNCH_CHECK(root);
+    return GPARML_OK;
+}
+
 // ---------------------------------------------------------------------------
 // K6: optimiser local state (scg_adapted_local_MapReduce.py:29-243) on the device-resident
 // (2, n, Q) vectors.  HBM-bound streaming; reductions are two-stage and deterministic.

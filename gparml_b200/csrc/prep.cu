@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_points_kernel(PrepParams p)
         __syncthreads();
     }
     if (bad) atomicOr(p.status, 4);
-    kl = gp_block_sum(0.5 * kl, sh);
+    kl = gp_block_sum(bad ? NAN : 0.5 * kl, sh);      // NaN marks the failed input check for prep_finish (ST_FLAGS)
     zeros = gp_block_sum(zeros, sh);
     if (tid == 0) {
         p.kl_partials[2 * blockIdx.x] = kl;
@@ -188,7 +188,10 @@ __global__ void __launch_bounds__(256) prep_finish_kernel(const double *__restri
     z = gp_block_sum(z, sh);
     if (threadIdx.x == 0) {
         double kl;
-        if (mode == 2 || z == n_local * (double)Q) kl = 0.0;        // all variances zero: fixed embeddings (partial_terms.py:86-87)
+        stats[ST_FLAGS] = (a != a) ? 1.0 : 0.0;
+        stats[ST_FLAGS + 1] = 0.0;
+        if (a != a) kl = 0.0;                                         // input check failed: the evaluation raises
+        else if (mode == 2 || z == n_local * (double)Q) kl = 0.0;        // all variances zero: fixed embeddings (partial_terms.py:86-87)
         else if (z > 0.0) kl = INFINITY;                              // -log(0) for some but not all entries, as numpy would give
         else kl = a;
         stats[ST_PSI0] = sf2 * n_local;                               // partial_terms.py:81 (ST_YYT: set_yyt_kernel)

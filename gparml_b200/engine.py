@@ -44,6 +44,7 @@ class ShardContext(object):
         _lib.check(self._lib.gparml_create(ctypes.byref(h), self.device, self.M, self.Q, self.D, self.n_total, flags))
         self._h = h
         self._torch_view = None
+        self.last_F = None           # bound of the last finished master step
 
     # -- lifetime -----------------------------------------------------------------
     def close(self):
@@ -143,7 +144,18 @@ class ShardContext(object):
 
     # -- map 1 ---------------------------------------------------------------------------
     def statistics(self):
+        """The statistics map; blocks until the device-side input check (variances in range) is known."""
         _lib.check(self._lib.gparml_statistics(self._h))
+
+    def statistics_launch(self):
+        """Queue the statistics map and return at once (no host synchronisation); a failed input check is
+        raised by the next :meth:`status` or :meth:`global_step_end`."""
+        _lib.check(self._lib.gparml_statistics_launch(self._h))
+
+    def status(self):
+        """Wait for the context's stream and raise what the device status word holds (AssertionError for a
+        variance out of range, LinAlgError for a failed pivot)."""
+        _lib.check(self._lib.gparml_status(self._h))
 
     @property
     def stats_count(self):
@@ -168,18 +180,13 @@ class ShardContext(object):
         _lib.check(self._lib.gparml_stats_add(self._h, ctypes.c_void_p(other.stats_device_ptr()), float(scale)))
 
     def stats_add_any(self, other, scale=1.0):
-        """stats_add that also works when ``other`` lives on a different GPU of this process."""
-        if other.device == self.device:
-            return self.stats_add(other, scale)
+        """stats_add that also works when ``other`` lives on a different GPU of this process
+        (stream-ordered, the host does not wait)."""
         _lib.check(self._lib.gparml_stats_add_peer(self._h, other._h, float(scale)))
 
     def stats_copy_from(self, other):
-        if other.device != self.device:
-            # zero-copy is impossible across devices: go through the peer add on a cleared buffer
-            self.upload(_lib.A_STATS, np.zeros(self.stats_count))
-            return self.stats_add_any(other, 1.0)
-        other.synchronize()
-        _lib.check(self._lib.gparml_stats_copy(self._h, ctypes.c_void_p(other.stats_device_ptr())))
+        """stats = other's packed buffer (any device of this process; stream-ordered, asynchronous)."""
+        _lib.check(self._lib.gparml_stats_copy_peer(self._h, other._h))
 
     def kmm_derivative(self, which):
         shape = {0: (self.M, self.Q, self.M), 1: (self.Q, self.M, self.M), 2: (self.M, self.M)}[which]
@@ -255,6 +262,7 @@ class ShardContext(object):
         g = np.zeros(self.M * self.Q + self.Q + 2)
         _lib.check(self._lib.gparml_global_step(self._h, _lib.ptr(F), _lib.ptr(g)))
         mq = self.M * self.Q
+        self.last_F = float(F[0])
         return float(F[0]), {"Z": g[:mq].reshape(self.M, self.Q).copy(), "sf2": float(g[mq]),
                              "alpha": g[mq + 1:mq + 1 + self.Q].copy(), "beta": float(g[mq + 1 + self.Q]),
                              "flat": g}
@@ -271,6 +279,7 @@ class ShardContext(object):
         g = np.zeros(self.M * self.Q + self.Q + 2)
         _lib.check(self._lib.gparml_global_step_end(self._h, _lib.ptr(F), _lib.ptr(g)))
         mq = self.M * self.Q
+        self.last_F = float(F[0])
         return float(F[0]), {"Z": g[:mq].reshape(self.M, self.Q).copy(), "sf2": float(g[mq]),
                              "alpha": g[mq + 1:mq + 1 + self.Q].copy(), "beta": float(g[mq + 1 + self.Q]),
                              "flat": g}
@@ -366,6 +375,25 @@ class ShardContext(object):
         return t[:, 0].copy(), t[:, 1:].copy(), float(out[-1])
 
 
+def allreduce_contexts(contexts, scale=1.0):
+    """The reducer for shard contexts driven by this host thread (any mix of GPUs): afterwards EVERY
+    context's packed buffer holds ``scale`` * the sum over all of them (``gparml_stats_allreduce_peers``:
+    one kernel over NVLink peer memory, no host synchronisation)."""
+    lib = _lib.load()
+    n = len(contexts)
+    if n > _lib.MAX_PEERS:               # two levels: groups of MAX_PEERS, then the group heads, then hand the sum back
+        groups = [contexts[i:i + _lib.MAX_PEERS] for i in range(0, n, _lib.MAX_PEERS)]
+        for g in groups:
+            allreduce_contexts(g, 1.0)
+        allreduce_contexts([g[0] for g in groups], scale)
+        for g in groups:
+            for c in g[1:]:
+                c.stats_copy_from(g[0])
+        return
+    arr = (ctypes.c_void_p * n)(*[c._h for c in contexts])
+    _lib.check(lib.gparml_stats_allreduce_peers(arr, n, float(scale)))
+
+
 def evaluate(contexts, Z, sf2, alpha, beta, step_size=0.0, reduce_fn=None):
     """One ELBO + gradient evaluation over shard contexts living in THIS process
     (SURVEY.md 3.2 steps 4-9).  ``contexts`` share one device unless ``reduce_fn`` is
@@ -375,29 +403,26 @@ def evaluate(contexts, Z, sf2, alpha, beta, step_size=0.0, reduce_fn=None):
 
     Returns (F, grad dict).  Per-point gradients stay on device (``ctx.grad_latest()``).
     """
-    for c in contexts:
+    for c in contexts:                      # every shard's map is queued before the host waits for any
         c.set_globals(Z, sf2, alpha, beta)
         c.set_step(step_size)
-        c.statistics()
+        c.statistics_launch()
     root = contexts[0]
-    for c in contexts[1:]:
-        root.stats_add_any(c)
+    if len(contexts) > 1:
+        allreduce_contexts(contexts)        # every context now holds the sum (local_MapReduce.py:250-277)
     if reduce_fn is not None:
         reduce_fn(root)
-    if len(contexts) == 1 and not root.fixed_embeddings:
-        # the embeddings map only waits for the partial derivatives; F and the global gradients are
-        # finished and downloaded concurrently with it
-        root.global_step_begin()
-        root.embedding_grads()
-        return root.global_step_end()
-    F, grad = root.global_step()
-    if not root.fixed_embeddings:
-        if len(contexts) > 1:
-            for c in contexts[1:]:
-                # every shard needs the reduced sums and the partial derivatives
-                # (local_MapReduce.py:315-321,350-354): replicate the global step
-                c.stats_copy_from(root)
-                c.global_step()
-        for c in contexts:
-            c.embedding_grads()
-    return F, grad
+        for c in contexts[1:]:
+            c.stats_copy_from(root)
+    if root.fixed_embeddings:
+        return root.global_step()
+    # the embeddings map only waits for the partial derivatives; F and the global gradients are finished
+    # and downloaded concurrently with it.  The master step is replicated on every context (identical
+    # inputs, identical outputs: local_MapReduce.py:315-321,350-354 read the same files in every mapper)
+    for c in contexts:
+        c.global_step_begin()
+        c.embedding_grads()
+    out = root.global_step_end()
+    for c in contexts[1:]:
+        c.global_step_end()
+    return out

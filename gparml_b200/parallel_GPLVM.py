@@ -5,6 +5,11 @@ per-evaluation sequence cache -> statistics_MR -> global statistics/derivatives 
 embeddings_MR, timing dictionary and the final ``'f'`` evaluation are kept as in the
 reference so that the ``b200_MapReduce`` backend is exercised exactly the way
 ``local_MapReduce`` is.  ``options['parallel']`` selects the backend ('b200' here).
+
+Launched as ``python -m torch.distributed.run --nproc-per-node G -m gparml_b200.parallel_GPLVM ...`` (or by
+calling :func:`main` from every rank) the same code runs one process per GPU: every rank maps its own input
+files, the backend all-reduces the packed statistics, and all ranks step the same optimiser with identical
+scalars (``b200_MapReduce`` module docstring).  Rank 0 owns the statistics folder.
 """
 import os
 import pickle
@@ -51,21 +56,24 @@ def main(opt_param):
     options, global_statistics = init_statistics(map_reduce, options)
     x0 = flatten_global_statistics(options, global_statistics)
     x0 = numpy.array([sp.transform_back(b, x) for b, x in zip(options['flat_global_statistics_bounds'], x0)])
+    rank = map_reduce.dist_info(options)[0]
     if options['optimiser'] != 'SCG_adapted':
         raise Exception("only the SCG_adapted optimiser is replayed here")
     x_opt = SCG_adapted(likelihood_and_gradient, x0, options['embeddings'], options['fixed_embeddings'],
                         display=options.get('display', True), maxiters=options['iterations'], xtol=0, ftol=0, gtol=0)
     flat_array = x_opt[0]
     options['iteration'] = len(x_opt[1]) - 1
-    clean(options)
+    if rank == 0:
+        clean(options)
     likelihood_and_gradient(flat_array, 'f')          # parallel_GPLVM.py:120: the checkpoint evaluation
-    map_reduce.flush(options)
-    with open(options['statistics'] + '/time_acc.obj', 'wb') as f:
-        pickle.dump(time_acc, f)
-    with open(options['statistics'] + '/nlml_acc.obj', 'wb') as f:
-        pickle.dump(x_opt[1], f)
-    with open(options['statistics'] + '/time_acc_SCG_adapted.obj', 'wb') as f:
-        pickle.dump(x_opt[4], f)
+    map_reduce.flush(options)                         # every rank writes the embeddings of its own shards
+    if rank == 0:
+        with open(options['statistics'] + '/time_acc.obj', 'wb') as f:
+            pickle.dump(time_acc, f)
+        with open(options['statistics'] + '/nlml_acc.obj', 'wb') as f:
+            pickle.dump(x_opt[1], f)
+        with open(options['statistics'] + '/time_acc_SCG_adapted.obj', 'wb') as f:
+            pickle.dump(x_opt[4], f)
     return x_opt
 
 
@@ -81,8 +89,9 @@ def init_statistics(map_reduce, options):
     options['partial_derivatives_names'] = ['F', 'dF_dsum_exp_K_ii', 'dF_dKmm', 'dF_dsum_exp_K_miY',
                                             'dF_dsum_exp_K_mi_K_im']
     options['cache_names'] = ['Kmm', 'Kmm_inv']
-    if not options['load']:
-        names = sorted(os.listdir(options['input'] + '/'))
+    rank, world, _ = map_reduce.dist_info(options) if hasattr(map_reduce, 'dist_info') else (0, 1, None)
+    if not options['load'] and rank == 0:
+        names = sorted(os.listdir(options['input'] + '/'))[::world]      # the shards rank 0 maps (all of them in one process)
         fid = 0
         embeddings = map_reduce.load(options['embeddings'] + '/' + names[fid] + '.embedding.npy')
         while embeddings.shape[0] < options['M']:
@@ -102,28 +111,57 @@ def init_statistics(map_reduce, options):
         Z = Z + numpy.random.randn(options['M'], options['Q']) * 0.05
         global_statistics = {'Z': Z, 'sf2': numpy.array([[1.0]]), 'alpha': numpy.ones((1, options['Q'])),
                              'beta': numpy.array([[1.0]])}
+    elif not options['load']:
+        global_statistics = None                                          # rank 0's initial values arrive below
     else:
         global_statistics = {}
         for key in options['global_statistics_names']:
             global_statistics[key] = map_reduce.load(options['statistics'] + '/global_statistics_' + key + '_f.npy')
+    if world > 1:
+        global_statistics = map_reduce._bcast(global_statistics, options)
     bounds = {'Z': [(None, None)] * (options['M'] * options['Q']), 'sf2': [(0, None)],
               'alpha': [(0, None)] * options['Q'], 'beta': [(0, None)]}
     flat = []
     for key in options['global_statistics_names']:
         flat = flat + bounds[key]
     options['flat_global_statistics_bounds'] = flat
+    options['flat_positive'] = numpy.array([b == (0, None) for b in flat])      # vectorised transforms below
     return options, global_statistics
+
+
+def _transform_vec(options, x):
+    """supporting_functions.py:131-136 over the flat vector: softplus where the bound is (0, None)."""
+    pos = options['flat_positive']
+    assert numpy.all(numpy.abs(x[pos]) < sp.lim_val)
+    out = numpy.array(x, dtype=float)
+    out[pos] = numpy.log(1 + numpy.exp(x[pos]))
+    return out
+
+
+def _transform_grad_vec(options, x):
+    """supporting_functions.py:143-148: sigmoid where the bound is (0, None), 1 elsewhere."""
+    pos = options['flat_positive']
+    out = numpy.ones(len(x))
+    out[pos] = 1 / (numpy.exp(-x[pos]) + 1)
+    return out
 
 
 def likelihood_and_gradient(flat_array, iteration, step_size=0):
     """parallel_GPLVM.py:222-279: returns (-F, -grad * transform_grad)."""
     global options, map_reduce, time_acc
-    flat_t = numpy.array([sp.transform(b, x) for b, x in zip(options['flat_global_statistics_bounds'], flat_array)])
+    flat_array = numpy.asarray(flat_array, dtype=float)
+    flat_t = _transform_vec(options, flat_array)
     global_statistics = rebuild_global_statistics(options, flat_t)
     options['i'] = iteration
     options['step_size'] = step_size
-    clean(options)
-    write = options.get('b200_write_files', True)
+    rank, world, _ = map_reduce.dist_info(options) if hasattr(map_reduce, 'dist_info') else (0, 1, None)
+    if rank == 0:
+        clean(options)
+    want_files = options.get('b200_write_files', True) or iteration == 'f'      # the 'f' checkpoint is always written
+    # the reference's file protocol (cache -> statistics_MR -> partial_terms -> embeddings_MR through .npy files)
+    # in one process; several ranks must stay bit-identical, so they all take the file-less evaluation and rank 0
+    # writes the same files from the device state afterwards
+    write = want_files and world == 1 and options.get('b200_write_files', True)
     if write:
         for key in global_statistics:
             map_reduce.save(options['statistics'] + '/global_statistics_' + key + '_' + str(options['i']) + '.npy',
@@ -149,6 +187,8 @@ def likelihood_and_gradient(flat_array, iteration, step_size=0):
                     'beta': numpy.array([[g['beta']]])}
         mapper_time, reducer_time, embeddings_time = [], [], []
         t1 = t2 = t3 = time.time()
+        if want_files:
+            map_reduce.write_evaluation_files(options, global_statistics)
     time_acc['time_acc_statistics_map_reduce'] += [t1 - t0]
     time_acc['time_acc_statistics_mapper'] += [mapper_time]
     time_acc['time_acc_statistics_reducer'] += [reducer_time]
@@ -156,9 +196,7 @@ def likelihood_and_gradient(flat_array, iteration, step_size=0):
     if not options['fixed_embeddings']:
         time_acc['time_acc_embeddings_MR'] += [t3 - t2]
         time_acc['time_acc_embeddings_MR_mapper'] += [embeddings_time]
-    gradient = flatten_global_statistics(options, gradient)
-    gradient = numpy.array([g * sp.transform_grad(b, x) for b, x, g in
-                            zip(options['flat_global_statistics_bounds'], flat_array, gradient)])
+    gradient = flatten_global_statistics(options, gradient) * _transform_grad_vec(options, flat_array)
     return -1 * likelihood, -1 * gradient
 
 
@@ -226,3 +264,42 @@ def clean(options):
         for key in names:
             for it in (-1, options['i'] - 1, options['i']):
                 map_reduce.remove(options['statistics'] + '/' + prefix + key + '_' + str(it) + '.npy')
+
+
+def _parse_args(argv=None):
+    """The reference's command line (parallel_GPLVM.py:407-516), reduced to the options this replay supports."""
+    import argparse
+    ap = argparse.ArgumentParser(description="Bayesian GPLVM / sparse GP on B200 (replay of parallel_GPLVM.py)")
+    ap.add_argument("-i", "--input", required=True, help="folder of input shards (one CSV or .npy file per shard)")
+    ap.add_argument("-e", "--embeddings", required=True, help="folder of the embeddings / variances / local gradients")
+    ap.add_argument("-s", "--statistics", help="statistics folder (default: <tmp>/statistics)")
+    ap.add_argument("--tmp", default="/tmp")
+    ap.add_argument("-p", "--parallel", default="b200", choices=["b200"])
+    ap.add_argument("-T", "--iterations", type=int, default=5)
+    ap.add_argument("-M", type=int, default=2, dest="M")
+    ap.add_argument("-Q", type=int, default=2, dest="Q")
+    ap.add_argument("-D", type=int, default=4, dest="D")
+    ap.add_argument("--init", default="PCA", choices=["PCA", "random"])
+    ap.add_argument("--load", action="store_true", help="resume from the 'f' checkpoint in the statistics / embeddings folders")
+    ap.add_argument("-k", "--keep", action="store_true", help="keep the per-iteration files")
+    ap.add_argument("--fixed_embeddings", action="store_true")
+    ap.add_argument("--fixed_beta", action="store_true")
+    ap.add_argument("--drop_out_fraction", type=float, default=0)
+    ap.add_argument("--no_files", action="store_true", help="no per-evaluation files (only the 'f' checkpoint)")
+    ap.add_argument("--quiet", action="store_true")
+    a = ap.parse_args(argv)
+    o = dict(DEFAULTS)
+    o.update(input=a.input, embeddings=a.embeddings, tmp=a.tmp, statistics=a.statistics or os.path.join(a.tmp, "statistics"),
+             parallel=a.parallel, iterations=a.iterations, M=a.M, Q=a.Q, D=a.D, init=a.init, load=a.load, keep=a.keep,
+             fixed_embeddings=a.fixed_embeddings, fixed_beta=a.fixed_beta, drop_out_fraction=a.drop_out_fraction,
+             b200_write_files=not a.no_files, display=not a.quiet)
+    return o
+
+
+if __name__ == '__main__':
+    opts = _parse_args()
+    if int(os.environ.get("RANK", "0")) != 0:
+        opts['display'] = False
+    for d in ('statistics',):
+        os.makedirs(opts[d], exist_ok=True)
+    main(default_options(**opts))

@@ -33,10 +33,20 @@ def _ctx(folder):
 
 
 def _sum(folder, method):
+    """Partial inner products of this process's shards, added in shard order and -- under
+    torch.distributed.run -- summed over the ranks, so that every rank's optimiser sees the same scalar."""
     total = 0
     for c in _ctx(folder):
         total += getattr(c, method)()
-    return total
+    return _over_ranks(folder, total, "sum")
+
+
+def _over_ranks(folder, value, op):
+    s = b200_MapReduce.session_of(folder)
+    if s.world == 1:
+        return value
+    from . import distributed as gd
+    return gd.allreduce_scalars([value], op, s.tdev)[0]
 
 
 def embeddings_set_grads(folder):                       # :29-55
@@ -64,7 +74,7 @@ def embeddings_get_grads_gamma(folder):                 # :126-141
 
 
 def embeddings_get_grads_max_d(folder, alpha):          # :143-156
-    return _timed('embeddings_get_grads_max_d', lambda: max([0] + [c.scg_get_max_d(alpha) for c in _ctx(folder)]))
+    return _timed('embeddings_get_grads_max_d', lambda: _over_ranks(folder, max([0] + [c.scg_get_max_d(alpha) for c in _ctx(folder)]), "max"))
 
 
 def embeddings_set_grads_reset_d(folder):               # :161-174

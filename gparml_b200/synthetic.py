@@ -79,3 +79,57 @@ def split_rows(n, parts):
         out.append((lo, hi))
         lo = hi
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# the same kind of problem generated in independent row blocks (bench.py): a rank builds only the
+# rows it owns, and the data -- hence the bound F -- is identical for 1, 2, 4 or 8 ranks
+# ------------------------------------------------------------------------------------------------
+ROW_BLOCKS = 8
+
+
+def block_problem_globals(cfg_name):
+    """Everything that does not depend on a row: hyper-parameters (the reference's initial values sf2 = alpha =
+    beta = 1, parallel_GPLVM.py:189-194), the inducing inputs (M draws from the distribution of the means; the
+    reference takes k-means centres of the embeddings plus 0.05 noise, :180-186) and the output maps."""
+    k = CONFIGS[cfg_name]
+    M, Q, D = k["M"], k["Q"], k["D"]
+    rng = np.random.default_rng([BASE_SEED, int(cfg_name[1]), 0])
+    lin = rng.standard_normal((D, Q))
+    proj = rng.standard_normal((D, Q))
+    phase = 5.0 * rng.standard_normal(D)
+    Z = rng.standard_normal((M, Q)) * np.sqrt(1.0 + 0.05 ** 2) + 0.05 * rng.standard_normal((M, Q))
+    return dict(lin=lin, proj=proj, phase=phase, Z=np.ascontiguousarray(Z), sf2=1.0, alpha=np.ones(Q), beta=1.0,
+                N=k["N"], M=M, Q=Q, D=D, fixed_embeddings=k["fixed_embeddings"])
+
+
+def block_problem_rows(cfg_name, lo, hi, with_direction=True):
+    """Rows [lo, hi) of the block-generated problem of BASELINE config ``cfg_name``: dict with Y, X_mu, X_S
+    (unconstrained; zeros with fixed embeddings) and optionally d (2, n, Q).  [lo, hi) must be a union of whole
+    blocks (N / ROW_BLOCKS rows each), which every split over 1, 2, 4 or 8 ranks is."""
+    g = block_problem_globals(cfg_name)
+    N, Q, D = g["N"], g["Q"], g["D"]
+    assert N % ROW_BLOCKS == 0
+    bs = N // ROW_BLOCKS
+    assert lo % bs == 0 and hi % bs == 0 and 0 <= lo <= hi <= N, (lo, hi, bs)
+    scale = 1.0 / np.sqrt(1.03 ** 2 * np.sum(g["lin"] ** 2, axis=1) / Q + 0.125 + 0.05 ** 2)     # unit variance columns
+    Ys, MUs, Ss, Ds = [], [], [], []
+    for b in range(lo // bs, hi // bs):
+        rng = np.random.default_rng([BASE_SEED, int(cfg_name[1]), 1 + b])
+        Xs = rng.standard_normal((bs, Q))
+        Y = 1.03 * (Xs @ g["lin"].T) / np.sqrt(Q) + 0.5 * np.sin(2.0 * (Xs @ g["proj"].T) / np.sqrt(Q) + g["phase"])
+        Y += 0.05 * rng.standard_normal((bs, D))
+        Ys.append(Y * scale)
+        if g["fixed_embeddings"]:
+            MUs.append(Xs)
+            Ss.append(np.zeros((bs, Q)))
+        else:
+            MUs.append(Xs + 0.05 * rng.standard_normal((bs, Q)))
+            Ss.append(softplus_inv(np.clip(0.5 + 0.01 * rng.standard_normal((bs, Q)), 0.001, 1.0)))
+            if with_direction:
+                Ds.append(rng.standard_normal((2, bs, Q)))
+    cat = lambda parts, axis=0: np.ascontiguousarray(np.concatenate(parts, axis=axis)) if parts else None   # noqa: E731
+    out = dict(Y=cat(Ys), X_mu=cat(MUs), X_S=cat(Ss))
+    if Ds:
+        out["d"] = cat(Ds, 1)
+    return out

@@ -132,8 +132,16 @@ int gparml_set_globals(gparml_ctx *ctx, const double *Z, double sf2, const doubl
 int gparml_set_step(gparml_ctx *ctx, double step_size);
 
 /* ---- map 1: statistics_mapper (local_MapReduce.py:183-248) --------------- */
-/* prep_points + psi1_stats + psi2_stats -> packed partial sums of THIS shard on device. */
+/* prep_points + psi1_stats + psi2_stats -> packed partial sums of THIS shard on device.
+ * gparml_statistics blocks until a device-side input check can be reported: with unconstrained variances
+ * it returns GPARML_ERR_RANGE where supporting_functions.py:154 asserts.
+ * gparml_statistics_launch only queues the work and returns (no host synchronisation): one host thread can
+ * start the map on every shard / GPU before it waits for any (the reference forks one mapper per shard,
+ * local_MapReduce.py:134-137).  The check result stays in the device status word and is reported by the next
+ * gparml_status (waits for the context's stream) or gparml_global_step_end. */
 int gparml_statistics(gparml_ctx *ctx);
+int gparml_statistics_launch(gparml_ctx *ctx);
+int gparml_status(gparml_ctx *ctx);
 int64_t gparml_stats_count(const gparml_ctx *ctx);            /* doubles in the packed buffer */
 /* Device pointer of the packed buffer: the caller sum-reduces it in place across
  * shards (NCCL all-reduce, replacing statistics_reducer local_MapReduce.py:250-277). */
@@ -200,8 +208,18 @@ int gparml_kmm_derivative(gparml_ctx *ctx, int which, double *out);
 int gparml_grad_contract(gparml_ctx *ctx, int which, const double *dF_dKmm, const double *dKmm_dx,
                          const double *dF_dPsi1Y, const double *dPsi1Y_dx, const double *dF_dPsi2,
                          const double *dPsi2_dx, double *out);
-/* stats = (stats + packed buffer of a context on ANOTHER device) * scale (peer copy + add). */
+/* stats = (stats + packed buffer of a context on ANOTHER device) * scale (peer copy + add); stream-ordered
+ * behind the other context's queued work, no host synchronisation. */
 int gparml_stats_add_peer(gparml_ctx *ctx, gparml_ctx *other, double scale);
+/* stats = packed buffer of another context on any device of this process (stream-ordered, asynchronous). */
+int gparml_stats_copy_peer(gparml_ctx *ctx, gparml_ctx *other);
+/* statistics_reducer (local_MapReduce.py:250-277) for n shard contexts driven by ONE host thread, on any mix of
+ * GPUs: every context's packed buffer becomes scale * (sum over the n buffers, added in list order).  One kernel
+ * on ctxs[0]'s device reads and writes the other GPUs' buffers directly through NVLink peer memory; streams are
+ * ordered with events and the host never waits.  scale: 1.0, or total/kept shards for --drop_out_fraction
+ * (local_MapReduce.py:263-264).  n <= GPARML_MAX_PEERS. */
+#define GPARML_MAX_PEERS 16
+int gparml_stats_allreduce_peers(gparml_ctx **ctxs, int n, double scale);
 
 /* ---- generic transfers ---------------------------------------------------- */
 int64_t gparml_array_count(const gparml_ctx *ctx, int array_id);

@@ -7,8 +7,9 @@ imported, so the bodies of ``statistics_mapper`` (local_MapReduce.py:183-248),
 ``calculate_global_derivatives`` (parallel_GPLVM.py:302-369) and
 ``embeddings_mapper`` (local_MapReduce.py:310-363) are replayed here on
 in-memory arrays, every arithmetic call going to the reference object.
-Used by ``oracle/gen_golden.py`` and ``tests/test_oracle.py``; only
-works where ``/root/reference`` exists.
+Used by ``oracle/gen_golden.py``, ``tests/test_oracle.py`` and -- as the CPU arm of ``bench.py``
+(``--impl reference`` / ``cpu_baseline``) -- timed on the GPU box's host cores, where the three reference
+files are present as the git-ignored staging copy ``oracle/_ref/`` (``oracle/stage_ref.py``).
 """
 import numpy as np
 
@@ -53,35 +54,61 @@ def _effective(shard, step_size, fixed_embeddings):
     return mu, s_raw, s_raw
 
 
-def reference_evaluate(shards, Z, sf2, alpha, beta, step_size=0.0, fixed_embeddings=False,
-                       fixed_beta=False):
-    N = sum(s["Y"].shape[0] for s in shards)
-    D = shards[0]["Y"].shape[1]
-    parts = []
-    for s in shards:
-        mu, S, _ = _effective(s, step_size, fixed_embeddings)
-        o = _new_pt(Z, sf2, alpha, beta, N, D)
-        o.set_data(s["Y"], mu, S, is_set_statistics=True)
-        t = o.get_local_statistics()
-        parts.append({
-            "sum_YYT": t["sum_YYT"], "sum_exp_K_ii": t["sum_exp_K_ii"],
-            "sum_exp_K_mi_K_im": t["sum_exp_K_mi_K_im"], "sum_exp_K_miY": t["exp_K_miY"],
-            "sum_KL": t["KL"],
-            "sum_d_exp_K_miY_d_Z": o.dexp_K_miY_dZ(),
-            "sum_d_exp_K_mi_K_im_d_Z": o.dexp_K_mi_K_im_dZ(),
-            "sum_d_exp_K_miY_d_alpha": o.dexp_K_miY_dalpha(),
-            "sum_d_exp_K_mi_K_im_d_alpha": o.dexp_K_mi_K_im_dalpha(),
-            "sum_d_exp_K_ii_d_sf2": o.dexp_K_ii_dsf2(),
-            "sum_d_exp_K_miY_d_sf2": o.dexp_K_miY_dsf2(),
-            "sum_d_exp_K_mi_K_im_d_sf2": o.dexp_K_mi_K_im_dsf2(),
-        })
+def map_statistics(s, Z, sf2, alpha, beta, N, D, step_size=0.0, fixed_embeddings=False):
+    """Body of statistics_mapper (local_MapReduce.py:183-248) for one shard, on in-memory arrays: the 12 partial
+    sums, every arithmetic call going to the reference's own partial_terms object."""
+    mu, S, _ = _effective(s, step_size, fixed_embeddings)
+    o = _new_pt(Z, sf2, alpha, beta, N, D)
+    o.set_data(s["Y"], mu, S, is_set_statistics=True)
+    t = o.get_local_statistics()
+    return {
+        "sum_YYT": t["sum_YYT"], "sum_exp_K_ii": t["sum_exp_K_ii"],
+        "sum_exp_K_mi_K_im": t["sum_exp_K_mi_K_im"], "sum_exp_K_miY": t["exp_K_miY"],
+        "sum_KL": t["KL"],
+        "sum_d_exp_K_miY_d_Z": o.dexp_K_miY_dZ(),
+        "sum_d_exp_K_mi_K_im_d_Z": o.dexp_K_mi_K_im_dZ(),
+        "sum_d_exp_K_miY_d_alpha": o.dexp_K_miY_dalpha(),
+        "sum_d_exp_K_mi_K_im_d_alpha": o.dexp_K_mi_K_im_dalpha(),
+        "sum_d_exp_K_ii_d_sf2": o.dexp_K_ii_dsf2(),
+        "sum_d_exp_K_miY_d_sf2": o.dexp_K_miY_dsf2(),
+        "sum_d_exp_K_mi_K_im_d_sf2": o.dexp_K_mi_K_im_dsf2(),
+    }
+
+
+def reduce_statistics(parts):
+    """statistics_reducer (local_MapReduce.py:250-277): per-key sum over the shards."""
     stats = {}
     for k in STAT_NAMES:
         acc = parts[0][k]
         for p in parts[1:]:
             acc = acc + p[k]
         stats[k] = acc
+    return stats
 
+
+def map_embeddings(s, stats, Z, sf2, alpha, beta, N, D, step_size=0.0):
+    """Body of embeddings_mapper (local_MapReduce.py:310-363) for one shard: grad_latest (2, n, Q)."""
+    mu, S, s_raw = _effective(s, step_size, False)
+    o = _new_pt(Z, sf2, alpha, beta, N, D)
+    o.set_data(s["Y"], mu, S, is_set_statistics=False)
+    o.set_local_statistics(stats["sum_YYT"], stats["sum_exp_K_mi_K_im"], stats["sum_exp_K_miY"],
+                           stats["sum_exp_K_ii"], stats["sum_KL"])
+    gm = o.grad_X_mu()
+    gs = o.grad_X_S() * _sigmoid(s_raw)
+    return -1 * np.array([gm, gs])
+
+
+def reference_evaluate(shards, Z, sf2, alpha, beta, step_size=0.0, fixed_embeddings=False,
+                       fixed_beta=False):
+    N = sum(s["Y"].shape[0] for s in shards)
+    D = shards[0]["Y"].shape[1]
+    parts = [map_statistics(s, Z, sf2, alpha, beta, N, D, step_size, fixed_embeddings) for s in shards]
+    stats = reduce_statistics(parts)
+    return master_and_embeddings(shards, stats, Z, sf2, alpha, beta, N, D, step_size, fixed_embeddings, fixed_beta)
+
+
+def master_step(stats, Z, sf2, alpha, beta, N, D, fixed_beta=False):
+    """calculate_global_statistics / calculate_global_derivatives (parallel_GPLVM.py:302-369)."""
     g = _new_pt(Z, sf2, alpha, beta, N, D)
     g.set_local_statistics(stats["sum_YYT"], stats["sum_exp_K_mi_K_im"], stats["sum_exp_K_miY"],
                            stats["sum_exp_K_ii"], stats["sum_KL"])
@@ -104,15 +131,13 @@ def reference_evaluate(shards, Z, sf2, alpha, beta, step_size=0.0, fixed_embeddi
                  "grad_Z": grad_Z, "grad_alpha": grad_alpha, "grad_sf2": float(grad_sf2),
                  "grad_beta": float(grad_beta), "F": float(pd["F"]),
                  "cond_Kmm": float(np.linalg.cond(g.Kmm))})
+    return glob
+
+
+def master_and_embeddings(shards, stats, Z, sf2, alpha, beta, N, D, step_size, fixed_embeddings, fixed_beta):
+    glob = master_step(stats, Z, sf2, alpha, beta, N, D, fixed_beta)
     out = {"stats": stats, "global": glob, "grad_latest": []}
     if not fixed_embeddings:
         for s in shards:
-            mu, S, s_raw = _effective(s, step_size, fixed_embeddings)
-            o = _new_pt(Z, sf2, alpha, beta, N, D)
-            o.set_data(s["Y"], mu, S, is_set_statistics=False)
-            o.set_local_statistics(stats["sum_YYT"], stats["sum_exp_K_mi_K_im"], stats["sum_exp_K_miY"],
-                                   stats["sum_exp_K_ii"], stats["sum_KL"])
-            gm = o.grad_X_mu()
-            gs = o.grad_X_S() * _sigmoid(s_raw)
-            out["grad_latest"].append(-1 * np.array([gm, gs]))
+            out["grad_latest"].append(map_embeddings(s, stats, Z, sf2, alpha, beta, N, D, step_size))
     return out

@@ -143,3 +143,17 @@ def test_numpy_oracle_matches_live_reference(shape):
             assert relerr(a["global"][k], b["global"][k]) < 1e-10, k
         for x, y in zip(a["grad_latest"], b["grad_latest"]):
             assert relerr(x, y) < 1e-11
+
+
+def test_bench_expected_F_c2():
+    """bench.py asserts F against tests/golden/bench_expected_F.json at every rank count; the c2 value (N = 100k,
+    M = 50, Q = 4, D = 1, fixed embeddings) is small enough for the C oracle at its full size."""
+    import json
+    import os
+    from gparml_b200.synthetic import block_problem_globals, block_problem_rows
+    from oracle import c_oracle
+    want = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bench_expected_F.json")))["c2"]
+    g = block_problem_globals("c2")
+    rows = block_problem_rows("c2", 0, g["N"], with_direction=False)
+    ref = c_oracle.evaluate([rows], g["Z"], g["sf2"], g["alpha"], g["beta"], fixed_embeddings=True)
+    assert abs(ref["global"]["F"] - want) <= 1e-9 * abs(want), (ref["global"]["F"], want)
