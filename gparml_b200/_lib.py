@@ -49,6 +49,7 @@ PROTOTYPES = {
     "gparml_set_n_total": (ctypes.c_int, [_vp, _i64]),
     "gparml_upload_shard": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, ctypes.c_int]),
     "gparml_n_local": (_i64, [_vp]),
+    "gparml_jitter_events": (_i64, [_vp]),
     "gparml_set_globals": (ctypes.c_int, [_vp, _vp, ctypes.c_double, _vp, ctypes.c_double]),
     "gparml_set_step": (ctypes.c_int, [_vp, ctypes.c_double]),
     "gparml_statistics": (ctypes.c_int, [_vp]),

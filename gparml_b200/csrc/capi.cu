@@ -209,6 +209,7 @@ extern "C" int gparml_set_n_total(gparml_ctx *c, int64_t n_total)
 extern "C" int64_t gparml_n_local(const gparml_ctx *c) { return c ? c->n : -1; }
 extern "C" int64_t gparml_stats_count(const gparml_ctx *c) { return c ? c->L.count : -1; }
 extern "C" int64_t gparml_launch_count(const gparml_ctx *c) { return c ? c->launches : -1; }
+extern "C" int64_t gparml_jitter_events(const gparml_ctx *c) { return c ? c->jitter_events : -1; }
 
 static int ensure_shard_capacity(gparml_ctx *c, int64_t n)
 {
@@ -423,9 +424,10 @@ static int check_status(gparml_ctx *c, bool sync_needed)
     (void)sync_needed;
     if (st) {
         GP_CUDA(cudaMemsetAsync(c->d_status, 0, sizeof(int), c->stream));
+        if (st & 24) c->jitter_events++;        // a factorisation needed the reference's 1e-7 jitter: not an error
         if (st & 4) { gp_set_error("unconstrained variance outside (-36.04, 36.04) (supporting_functions.py:154 assert)"); return GPARML_ERR_RANGE; }
-        if (st & 1) { gp_set_error("Kmm is not positive definite (Cholesky pivot <= 0)"); return GPARML_ERR_NOT_PD; }
-        if (st & 2) { gp_set_error("Kmm + beta*Psi2 is not positive definite (Cholesky pivot <= 0)"); return GPARML_ERR_NOT_PD; }
+        if (st & 1) { gp_set_error("Kmm is not positive definite, also with 1e-7 jitter (pivot <= 0)"); return GPARML_ERR_NOT_PD; }
+        if (st & 2) { gp_set_error("Kmm + beta*Psi2 is not positive definite, also with 1e-7 jitter (pivot <= 0)"); return GPARML_ERR_NOT_PD; }
     }
     return GPARML_OK;
 }
@@ -590,10 +592,10 @@ extern "C" int gparml_global_step_end(gparml_ctx *c, double *F, double *grad)
     memcpy(&st, c->glob_host + 1 + ng, sizeof(int));           // device status word as of the end of the head
     if (st) {
         GP_CUDA(cudaMemsetAsync(c->d_status, 0, sizeof(int), c->stream));
+        if (st & 24) c->jitter_events++;
         if (st & 4) { gp_set_error("unconstrained variance outside (-36.04, 36.04) (supporting_functions.py:154 assert)"); return GPARML_ERR_RANGE; }
-        if (st & 1) { gp_set_error("Kmm is not positive definite (Cholesky pivot <= 0)"); return GPARML_ERR_NOT_PD; }
-        gp_set_error("Kmm + beta*Psi2 is not positive definite (Cholesky pivot <= 0)");
-        return GPARML_ERR_NOT_PD;
+        if (st & 1) { gp_set_error("Kmm is not positive definite, also with 1e-7 jitter (pivot <= 0)"); return GPARML_ERR_NOT_PD; }
+        if (st & 2) { gp_set_error("Kmm + beta*Psi2 is not positive definite, also with 1e-7 jitter (pivot <= 0)"); return GPARML_ERR_NOT_PD; }
     }
     if (F) *F = c->glob_host[0];
     if (grad) memcpy(grad, c->glob_host + 1, ng * sizeof(double));

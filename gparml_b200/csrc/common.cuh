@@ -102,6 +102,7 @@ struct gparml_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
+    int64_t jitter_events = 0;  // evaluations whose Kmm or Kmm + beta Psi2 needed the 1e-7 jitter retry
 
     // shard
     int64_t n = 0;         // points in this shard

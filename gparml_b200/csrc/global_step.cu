@@ -33,6 +33,7 @@
 
 #include "gs_common.cuh"
 
+#define GS_JITTER 1e-7   // partial_terms.py:454,456
 #define GS_TI 2          // register tile of the two M x M x M products: 2 x 5 outputs per thread
 #define GS_TJ 5
 
@@ -206,7 +207,18 @@ __global__ void __launch_bounds__(GS_THREADS, 1) global_step_kernel(GsParams p)
             p.kmm[idx] = k;
         }
         __syncthreads();
-        if (!gs_sweep_invert(X, M, tmp, piv, red, &ldK)) {
+        bool ok = gs_sweep_invert(X, M, tmp, piv, red, &ldK);
+        if (!ok) {
+            // The reference retries once with 1e-7 on the diagonal when the factorisation says "not positive
+            // definite" (partial_terms.py:453-454; there only the log-determinant is recomputed, here Kmm^-1 is
+            // taken from the same jittered matrix).  Status bit 8 records the event; it is not an error.
+            __syncthreads();
+            for (size_t idx = tid; idx < MM; idx += GS_THREADS) X[idx] = p.kmm[idx] + ((idx / M == idx % M) ? GS_JITTER : 0.0);
+            __syncthreads();
+            ok = gs_sweep_invert(X, M, tmp, piv, red, &ldK);
+            if (ok && tid == 0) atomicOr(p.status, 8);
+        }
+        if (!ok) {
             if (tid == 0) atomicOr(p.status, 1);
             return;
         }
@@ -232,7 +244,18 @@ __global__ void __launch_bounds__(GS_THREADS, 1) global_step_kernel(GsParams p)
         }
     }
     __syncthreads();
-    if (!gs_sweep_invert(X, M, tmp, piv, red, &ldA)) {
+    bool ok = gs_sweep_invert(X, M, tmp, piv, red, &ldA);
+    if (!ok) {                                  // partial_terms.py:455-457: one retry with A + 1e-7 I (status bit 16)
+        __syncthreads();
+        for (int i = wid; i < M; i += GS_THREADS / 32) {
+            const size_t ro = (size_t)i * M;
+            for (int j = lane; j < M; j += 32) X[ro + j] = fma(beta, P2[ro + j], p.kmm[ro + j]) + (i == j ? GS_JITTER : 0.0);
+        }
+        __syncthreads();
+        ok = gs_sweep_invert(X, M, tmp, piv, red, &ldA);
+        if (ok && tid == 0) atomicOr(p.status, 16);
+    }
+    if (!ok) {
         if (tid == 0) atomicOr(p.status, 2);
         return;
     }

@@ -90,6 +90,11 @@ class ShardContext(object):
         return int(self._lib.gparml_n_local(self._h))
 
     @property
+    def jitter_events(self):
+        """Evaluations whose Kmm / Kmm + beta Psi2 needed the reference's 1e-7 jitter (partial_terms.py:453-457)."""
+        return int(self._lib.gparml_jitter_events(self._h))
+
+    @property
     def launch_count(self):
         return int(self._lib.gparml_launch_count(self._h))
 

@@ -122,6 +122,10 @@ int gparml_set_n_total(gparml_ctx *ctx, int64_t n_total);
 int gparml_upload_shard(gparml_ctx *ctx, const double *Y, const double *X_mu, const double *X_S,
                         int64_t n_local, int variance_domain);
 int64_t gparml_n_local(const gparml_ctx *ctx);
+/* Number of evaluations so far in which Kmm or Kmm + beta Psi2 only factorised after the reference's jitter
+ * retry (+1e-7 on the diagonal, partial_terms.py:453-457; single-CTA master step, M <= 116).  A matrix that is
+ * not positive definite even then gives GPARML_ERR_NOT_PD. */
+int64_t gparml_jitter_events(const gparml_ctx *ctx);
 
 /* ---- per-evaluation globals --------------------------------------------- */
 /* Z (M,Q), alpha (Q,), sf2, beta: the `global_statistics_*_<i>.npy` broadcast

@@ -139,7 +139,7 @@ def test_in_process_multi_gpu_shards_run_concurrently(tmp_path):
     from gparml_b200.synthetic import make_problem, split_rows
     ndev = torch.cuda.device_count()
     parts = max(2, min(ndev, 4))
-    N, M, Q, D = 40000 * parts, 40, 6, 4
+    N, M, Q, D = 400000 * parts, 40, 6, 4        # ~4 ms of map per shard: well above launch latencies
     p = make_problem(N, M, Q, D, seed=31, generic_hypers=True)
     one = ShardContext(M, Q, D, N)
     one.upload_shard(p["Y"], p["X_mu"], p["X_S"])

@@ -169,29 +169,118 @@ def test_main_runs_fixed_embeddings_sparse_gp(tmp_path):
 
 
 def test_dropout_rescales_like_reference(tmp_path):
-    """--drop_out_fraction (local_MapReduce.py:121-129,263-264): kept-shard sums scaled by total/kept."""
+    """--drop_out_fraction (local_MapReduce.py:121-129,263-264): every accumulated statistic is the sum over the
+    kept shards divided by kept / (kept + dropped) -- checked on all 12 tensors against the oracle's per-shard
+    sums -- including the reference's fallback when every node is dropped (one node drawn with random.randint,
+    the dropped list left untouched, so the factor is (1 + n) / 1)."""
+    import random
     from gparml_b200 import b200_MapReduce, parallel_GPLVM as drv
     from gparml_b200.synthetic import make_problem
-    p = make_problem(400, 5, 2, 3, seed=3)
+    from oracle import gparml_oracle as O
+    p = make_problem(403, 5, 2, 3, seed=3)
     dirs = _write_problem(tmp_path, p, 4)
     np.random.seed(5)
     opts = drv.default_options(M=5, Q=2, D=3, iterations=1, init="random", display=False, **dirs)
     opts = b200_MapReduce.init(opts)
     opts, gs = drv.init_statistics(b200_MapReduce, opts)
+    names = sorted(os.listdir(dirs["input"]))
+    Z, sf2 = gs["Z"], float(np.squeeze(gs["sf2"]))
+    alpha = np.atleast_1d(np.squeeze(gs["alpha"]))
+    per_shard = []
+    for n in names:
+        Y = np.genfromtxt(os.path.join(dirs["input"], n), delimiter=",")
+        mu = np.load(os.path.join(dirs["embeddings"], n + ".embedding.npy"))
+        S = O.softplus(np.load(os.path.join(dirs["embeddings"], n + ".variance.npy")))
+        per_shard.append(O.shard_statistics(Y, mu, S, Z, sf2, alpha))
     try:
         opts["i"], opts["step_size"] = 0, 0
         b200_MapReduce.cache(opts, gs)
-        files, _, _ = b200_MapReduce.statistics_MR(opts)
-        full = {k: np.load(f) for k, f in files}
-        opts["drop_out_fraction"] = 0.5
-        np.random.seed(11)
-        files, _, _ = b200_MapReduce.statistics_MR(opts)
-        kept = list(b200_MapReduce.non_dropped_out_nodes)
-        assert 1 <= len(kept) <= 4
-        part = {k: np.load(f) for k, f in files}
-        # N-proportional statistic: kept points * (4 / kept shards) (equal shard sizes here)
-        assert part["sum_d_exp_K_ii_d_sf2"] == pytest.approx(full["sum_d_exp_K_ii_d_sf2"])
-        assert part["sum_exp_K_mi_K_im"].shape == (5, 5)
+        for frac, seed in ((0.5, 11), (0.5, 12), (1.0, 13)):
+            opts["drop_out_fraction"] = frac
+            np.random.seed(seed)
+            random.seed(seed)
+            files, _, _ = b200_MapReduce.statistics_MR(opts)
+            kept = list(b200_MapReduce.non_dropped_out_nodes)
+            dropped = list(b200_MapReduce.dropped_out_nodes)
+            if frac == 1.0:
+                assert len(kept) == 1 and len(dropped) == 4          # the reference's fallback branch
+            else:
+                assert sorted(kept + dropped) == [0, 1, 2, 3] and 1 <= len(kept) <= 4
+            scale = float(len(kept) + len(dropped)) / len(kept)
+            got = {k: np.load(f) for k, f in files}
+            want = O.reduce_statistics([per_shard[i] for i in kept])
+            for k in got:
+                assert relerr(got[k], np.asarray(want[k]) * scale) < 1e-11, (frac, seed, k)
+            # the embeddings map still runs on every shard, dropped or not (local_MapReduce.py:292-294)
+            F, _ = b200_MapReduce.session_contexts(opts["embeddings"])[kept[0]].global_step()
+            assert np.isfinite(F)
+            b200_MapReduce.embeddings_MR(opts)
+            for c in b200_MapReduce.session_contexts(opts["embeddings"]):
+                assert np.all(np.isfinite(c.grad_latest()))
+    finally:
+        b200_MapReduce.close()
+
+
+def test_load_resumes_from_checkpoint_and_keep_keeps_files(tmp_path):
+    """--load (parallel_GPLVM.py:195-200, local_MapReduce.py:49): a second main() started from the 'f' checkpoint
+    and the flushed embeddings continues where the first one stopped; --keep (parallel_GPLVM.py:373-404) leaves the
+    per-iteration files in place, without it they are cleaned."""
+    from gparml_b200 import b200_MapReduce, parallel_GPLVM as drv
+    from gparml_b200.synthetic import make_problem
+    p = make_problem(600, 6, 2, 3, seed=12)
+    dirs = _write_problem(tmp_path, p, 3)
+    st = dirs["statistics"]
+    np.random.seed(2)
+    try:
+        x1 = drv.main(drv.default_options(M=6, Q=2, D=3, iterations=3, init="PCA", display=False, **dirs))
+    finally:
+        b200_MapReduce.close()
+    flog1 = x1[1]
+    assert not [f for f in os.listdir(st) if f.startswith("global_statistics_Z_") and not f.endswith("_f.npy")
+                and f not in ("global_statistics_Z_%d.npy" % k for k in (len(flog1) - 1, len(flog1) - 2))]
+    Z_f = np.load(os.path.join(st, "global_statistics_Z_f.npy"))
+    F_f = float(np.load(os.path.join(st, "partial_derivatives_F_f.npy")))
+    assert -F_f == pytest.approx(flog1[-1], rel=1e-12)
+    emb1 = np.load(os.path.join(dirs["embeddings"], "easy_0.embedding.npy"))
+    try:
+        x2 = drv.main(drv.default_options(M=6, Q=2, D=3, iterations=2, load=True, keep=True, display=False, **dirs))
+    finally:
+        b200_MapReduce.close()
+    flog2 = x2[1]
+    # the resumed run starts at the checkpoint: same parameters, same embeddings, hence the same objective
+    assert flog2[0] == pytest.approx(flog1[-1], rel=1e-11)
+    assert flog2[-1] < flog2[0]
+    assert not np.array_equal(np.load(os.path.join(st, "global_statistics_Z_f.npy")), Z_f)       # a new checkpoint
+    assert not np.array_equal(np.load(os.path.join(dirs["embeddings"], "easy_0.embedding.npy")), emb1)
+    # keep=True: the per-iteration files of the second run are all still there
+    for k in range(0, 3):
+        assert os.path.exists(os.path.join(st, "global_statistics_Z_%d.npy" % k)), k
+        assert os.path.exists(os.path.join(st, "accumulated_statistics_sum_exp_K_mi_K_im_%d.npy" % k)), k
+
+
+def test_checkpoint_written_without_per_evaluation_files(tmp_path):
+    """b200_write_files=False skips the per-evaluation file transport but the final 'f' evaluation still writes the
+    checkpoint predict.py / --load need (global statistics, accumulated statistics, cache, partial derivatives)."""
+    from gparml_b200 import b200_MapReduce, parallel_GPLVM as drv
+    from gparml_b200.synthetic import make_problem
+    p = make_problem(300, 4, 2, 3, seed=14)
+    dirs = _write_problem(tmp_path, p, 2)
+    st = dirs["statistics"]
+    np.random.seed(6)
+    try:
+        x1 = drv.main(drv.default_options(M=4, Q=2, D=3, iterations=2, init="PCA", display=False, b200_write_files=False, **dirs))
+        files = sorted(os.listdir(st))
+        assert not [f for f in files if f.endswith(".npy") and not f.endswith("_f.npy")], files
+        for f in ("global_statistics_Z_f.npy", "global_statistics_beta_f.npy", "accumulated_statistics_sum_exp_K_mi_K_im_f.npy",
+                  "accumulated_statistics_sum_KL_f.npy", "cache_Kmm_f.npy", "cache_Kmm_inv_f.npy",
+                  "partial_derivatives_F_f.npy", "partial_derivatives_dF_dKmm_f.npy"):
+            assert f in files, f
+        assert -float(np.load(os.path.join(st, "partial_derivatives_F_f.npy"))) == pytest.approx(x1[1][-1], rel=1e-12)
+    finally:
+        b200_MapReduce.close()
+    try:        # and that checkpoint is loadable
+        x2 = drv.main(drv.default_options(M=4, Q=2, D=3, iterations=1, load=True, display=False, b200_write_files=False, **dirs))
+        assert x2[1][0] == pytest.approx(x1[1][-1], rel=1e-11)
     finally:
         b200_MapReduce.close()
 

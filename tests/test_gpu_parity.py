@@ -186,6 +186,45 @@ def test_error_mapping_not_pd_and_range():
             c.statistics()
 
 
+def test_jitter_retry_follows_reference_branch():
+    """partial_terms.py:453-457: when a factorisation says "not positive definite" the reference retries with 1e-7
+    on the diagonal and only gives up (assert) if that fails too.  The device does the same (single-CTA master
+    step): a Kmm + beta Psi2 with one eigenvalue of -1e-9 evaluates to the bound of the reference's jitter branch
+    (the oracle restates it: oracle/gparml_oracle.py global_step), the event is counted, and a matrix that is
+    indefinite beyond the jitter still raises LinAlgError (test_error_mapping_not_pd_and_range)."""
+    from gparml_b200.engine import ShardContext
+    from gparml_b200.synthetic import make_problem
+    from oracle import gparml_oracle as O
+    M, Q, D, n = 12, 3, 2, 300
+    p = make_problem(n, M, Q, D, seed=91, generic_hypers=True)
+    rng = np.random.default_rng(91)
+    V, _ = np.linalg.qr(rng.standard_normal((M, M)))
+    lam = np.concatenate([[-1.0e-9], rng.uniform(0.5, 2.0, M - 1)])
+    E = (V * lam) @ V.T
+    E = 0.5 * (E + E.T)
+    K = O.kmm(p["Z"], p["sf2"], p["alpha"])
+    P2 = (E - K) / p["beta"]                      # Kmm + beta Psi2 = E: indefinite by 1e-9
+    with ShardContext(M, Q, D, n) as c:
+        c.upload_shard(p["Y"], p["X_mu"], p["X_S"])
+        c.set_globals(p["Z"], p["sf2"], p["alpha"], p["beta"])
+        c.statistics()
+        F0, _ = c.global_step()
+        assert c.jitter_events == 0 and np.isfinite(F0)
+        c.set_stats_named({"sum_exp_K_mi_K_im": P2})
+        stats = c.stats_named()
+        F, g = c.global_step()
+        assert c.jitter_events == 1
+        ref = O.global_step(stats, p["Z"], p["sf2"], p["alpha"], p["beta"], n)
+        assert np.linalg.slogdet(K + p["beta"] * stats["sum_exp_K_mi_K_im"])[0] < 0      # the reference's trigger (:455)
+        print("jitter branch: F %.12g  oracle %.12g  rel %.2e" % (F, ref["F"], abs(F - ref["F"]) / abs(ref["F"])))
+        assert abs(F - ref["F"]) <= 1e-7 * abs(ref["F"])
+        assert np.all(np.isfinite(g["flat"]))
+        # the next evaluation with healthy statistics is not affected
+        c.statistics()
+        F1, _ = c.global_step()
+        assert F1 == F0 and c.jitter_events == 1
+
+
 def test_scg_local_ops_match_numpy():
     from gparml_b200 import _lib
     from gparml_b200.engine import ShardContext

@@ -103,8 +103,9 @@ def test_world_size_2_gloo_reduce(tmp_path):
 
 
 def test_bench_reference_arm_line_on_cpu():
-    """`bench.py --impl reference` needs no GPU: it times the oracle port of the reference's maps in a
-    Pool on the host cores and prints ONE JSON line with the contract's keys."""
+    """`bench.py --impl reference` needs no GPU: it times the reference's own maps (staged oracle/_ref or
+    /root/reference; the oracle port where neither exists) in a Pool on the host cores and prints ONE JSON line with
+    the contract's keys."""
     import json
     import subprocess
     import sys
@@ -117,7 +118,9 @@ def test_bench_reference_arm_line_on_cpu():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "ELBO+grad evals/sec" and d["unit"] == "evals/s"
     assert d["higher_is_better"] is True and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    from oracle import ref_shim
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_shim.reference_available() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     # ranks other than 0 exit without work
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
