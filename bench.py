@@ -439,7 +439,14 @@ def run_config(env, cfg_name, steps, warmup, args, main_line):
 
     if main_line and not args.no_e2e:
         evaluation_e2e()
-        ms_e2e, _, _ = env.timed(evaluation_e2e, steps)
+        ctx.enable_timing(True)
+        ph_e2e = {}
+
+        def collect_e2e():
+            for kk, v in ctx.phase_times_ms().items():
+                ph_e2e.setdefault(kk, []).append(v)
+        ms_e2e, _, _ = env.timed(evaluation_e2e, steps, per_step=collect_e2e)
+        ctx.enable_timing(False)
         h2d = n_loc * (D + 2 * Q) * 8 + (M * Q + Q + 2) * 8
         d2h = (0 if fixed else 2 * n_loc * Q * 8) + (1 + M * Q + Q + 2) * 8
         tot = torch.tensor([h2d, d2h], dtype=torch.float64, device=env.dev)
@@ -447,7 +454,22 @@ def run_config(env, cfg_name, steps, warmup, args, main_line):
             dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         out["e2e"] = {"value": 1e3 / (ms_e2e / steps), "unit": UNIT, "h2d_bytes_per_step": int(tot[0].item()),
                       "d2h_bytes_per_step": int(tot[1].item()),
-                      "api": "upload_shard(Y, X_mu, X_S) from pinned host memory + evaluation + grad_latest back to pinned host, every step"}
+                      "api": "upload_shard(Y, X_mu, X_S) from pinned host memory + evaluation + grad_latest back to pinned host, every step",
+                      # same phases as phase_ms_median, here including the waits for the row-range uploads / chunked downloads
+                      "phase_ms_median": {kk: float(np.median(v)) for kk, v in ph_e2e.items()}}
+        # what the host link gives each rank while ALL ranks copy at once (the copies the e2e step hides behind kernels)
+        dY = torch.empty_like(Yp, device=env.dev)
+        dG = torch.empty((2, n_loc, Q), dtype=torch.float64, device=env.dev)
+        for _ in range(2):
+            dY.copy_(Yp, non_blocking=True)
+            GLp.copy_(dG, non_blocking=True)
+        ms_h2d, _, _ = env.timed(lambda: dY.copy_(Yp, non_blocking=True), 5)
+        ms_d2h, _, _ = env.timed(lambda: GLp.copy_(dG, non_blocking=True), 5)
+        out["e2e"]["host_link_all_ranks_copying"] = {
+            "h2d_gbs_per_rank": Yp.numel() * 8 / (ms_h2d / 5 * 1e-3) / 1e9,
+            "d2h_gbs_per_rank": GLp.numel() * 8 / (ms_d2h / 5 * 1e-3) / 1e9,
+            "note": "slowest rank (max over ranks of the copy time), pinned host memory, %d-rank concurrent copies" % world}
+        del dY, dG
 
     # ---- rooflines of this rank's kernels, live CUDA-event durations ------------------------------------------
     P = M * (M + 1) // 2

@@ -18,7 +18,7 @@ VARIANCE_UNCONSTRAINED, VARIANCE_POSITIVE = 0, 1
 MAX_PEERS = 16      # GPARML_MAX_PEERS
 
 (A_X_MU, A_X_S, A_GRAD_D, A_GRAD_LATEST, A_GRAD_NEW, A_GRAD_OLD, A_STATS, A_KMM, A_KMM_INV, A_A_INV,
- A_DF_DKMM, A_DF_DPSI1Y, A_DF_DPSI2, A_PSI1, A_GRAD_X_MU, A_GRAD_X_S, A_Y, A_GRAD_GLOBAL) = range(18)
+ A_DF_DKMM, A_DF_DPSI1Y, A_DF_DPSI2, A_PSI1, A_GRAD_X_MU, A_GRAD_X_S, A_Y, A_GRAD_GLOBAL, A_GS_EXTRA) = range(19)
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _vp = ctypes.c_void_p

@@ -7,6 +7,8 @@
 #include "../../include/gparml_b200.h"
 
 #define GP_MAX_Q 16
+#define GP_MAX_RANGES 8        // row ranges of one shard upload
+#define GP_RANGE_ROWS 16384    // aim: one range per this many points (only the first range's transfer is exposed)
 
 // ---------------------------------------------------------------------------
 // error plumbing
@@ -129,11 +131,11 @@ struct gparml_ctx {
     cudaEvent_t ev_gs_head = nullptr, ev_gs_tail = nullptr;
     bool gs_pending = false;           // gparml_global_step_begin without its _end
     double *glob_host = nullptr;       // pinned staging of [F, grad]
-    // gparml_upload_shard sends X_mu / X_S in up to 4 row ranges; gparml_statistics consumes them range by
-    // range (prep_points + psi2_stats of range k overlap the transfer of range k+1)
-    cudaEvent_t ev_x[4] = {nullptr, nullptr, nullptr, nullptr};
+    // gparml_upload_shard sends X_mu / X_S in up to GP_MAX_RANGES row ranges; gparml_statistics consumes them range
+    // by range (prep_points + psi2_stats of range k overlap the transfer of range k+1)
+    cudaEvent_t ev_x[GP_MAX_RANGES] = {};
     int x_pending = 0;                 // ranges of the last upload the main stream has not been ordered behind yet
-    int64_t x_bounds[5] = {0, 0, 0, 0, 0};
+    int64_t x_bounds[GP_MAX_RANGES + 1] = {};
     cudaEvent_t ev_main = nullptr, ev_y = nullptr, ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     // globals

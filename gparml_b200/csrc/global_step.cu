@@ -67,61 +67,80 @@ __device__ bool gs_sweep_invert_mem(double *A, int M, double *tmp, double *piv, 
     return true;
 }
 
-// Register-resident version for M <= 128: thread (ty, tx) owns the elements (ty + 32 a, tx + 32 b),
-// a, b < 4, for the whole sweep; only the pivot column travels through shared memory (double
-// buffered, one barrier per pivot).  Per pivot: 8 shared-memory reads and 16 FMAs per thread
-// instead of 3 shared-memory accesses per element.
-__device__ bool gs_sweep_invert_reg(double *A, int M, double *tmp2 /* 2 x 128 */, double *piv, double *red, double *logdet)
+// Register-resident version for M <= 128: thread (ty, tx) owns the elements (ty + 32 a, tx + 32 b), a, b < NS =
+// ceil(M / 32), for the whole sweep; only the pivot column travels through shared memory (double buffered, one
+// barrier per pivot) together with the reciprocal pivot, which its owner thread alone computes.
+// The rank-1 update is issued unconditionally for all NS x NS elements and row k / column k are repaired in two
+// rare branches: the first version selected per element ((tx + 32 b == k) ? ... : fma) and spent ~250 issue slots
+// per warp and pivot on 16 FMAs -- 2400 cycles per pivot whatever M was (tools/micro/sweep_probe.cu; B200:
+// M = 100 121 -> 75 us, M = 50 61 -> 25 us).
+template <int NS>
+__device__ __forceinline__ bool gs_sweep_invert_reg(double *A, int M, double *tmp2 /* 2 x 128 + 2 */, double *piv, double *red,
+                                                    double *logdet)
 {
     const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-    double e[4][4];
+    double *pv = tmp2 + 256;
+    double e[NS][NS];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < NS; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
+        for (int b = 0; b < NS; ++b) {
             const int i = ty + 32 * a, j = tx + 32 * b;
             e[a][b] = (i < M && j < M) ? A[(size_t)i * M + j] : 0.0;
         }
     for (int k = 0; k < M; ++k) {
-        double *tmp = tmp2 + (k & 1) * 128;
-        // owners of column k publish it: elements (i, k) live in threads with tx == k % 32, slot b == k / 32
-        if (tx == (k & 31)) {
-            const int kb = k >> 5;
+        double *buf = tmp2 + (k & 1) * 128;
+        const int kx = k & 31, ks = k >> 5;          // column k: lanes tx == kx, slot ks; row k: warp ty == kx, slot ks
+        const bool rowk_warp = (ty == kx), colk_lane = (tx == kx);
+        if (colk_lane) {                             // owners of column k publish it (and the reciprocal pivot)
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const double v = (kb == 0) ? e[a][0] : ((kb == 1) ? e[a][1] : ((kb == 2) ? e[a][2] : e[a][3]));
-                tmp[ty + 32 * a] = v;
-            }
+            for (int b = 0; b < NS; ++b)
+                if (b == ks) {
+#pragma unroll
+                    for (int a = 0; a < NS; ++a) buf[ty + 32 * a] = e[a][b];
+                    if (rowk_warp) {
+#pragma unroll
+                        for (int a = 0; a < NS; ++a)
+                            if (a == ks) pv[k & 1] = 1.0 / e[a][b];
+                    }
+                }
         }
         __syncthreads();
-        const double d = tmp[k];
-        if (!(d > 0.0) || !isfinite(d)) return false;          // uniform
-        // one division per warp instead of one per thread: the single SM's FP64 pipe is the limit here
-        double pinv = 0.0;
-        if (tx == 0) pinv = 1.0 / d;
-        pinv = __shfl_sync(0xffffffffu, pinv, 0);
+        const double d = buf[k];
+        if (!(d > 0.0) || !isfinite(d)) return false;          // uniform: every thread reads the same pivot
+        const double pinv = pv[k & 1];
         if (tid == 0) piv[k] = d;
-        double tj[4];
+        double ti[NS], tj[NS];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) tj[b] = tmp[tx + 32 * b];
+        for (int b = 0; b < NS; ++b) tj[b] = buf[tx + 32 * b];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int i = ty + 32 * a;                          // warp-uniform
-            if (i == k) {
+        for (int a = 0; a < NS; ++a) ti[a] = buf[ty + 32 * a] * pinv;
 #pragma unroll
-                for (int b = 0; b < 4; ++b) e[a][b] = (tx + 32 * b == k) ? -pinv : tj[b] * pinv;
-            } else {
-                const double ti = tmp[i] * pinv;
+        for (int a = 0; a < NS; ++a)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) e[a][b] = (tx + 32 * b == k) ? ti : fma(-ti, tj[b], e[a][b]);
-            }
+            for (int b = 0; b < NS; ++b) e[a][b] = fma(-ti[a], tj[b], e[a][b]);
+        if (rowk_warp) {                             // row k: A[k][j] = c_j / d
+#pragma unroll
+            for (int a = 0; a < NS; ++a)
+                if (a == ks) {
+#pragma unroll
+                    for (int b = 0; b < NS; ++b) e[a][b] = tj[b] * pinv;
+                }
+        }
+        if (colk_lane) {                             // column k: A[i][k] = c_i / d, A[k][k] = -1 / d
+#pragma unroll
+            for (int b = 0; b < NS; ++b)
+                if (b == ks) {
+#pragma unroll
+                    for (int a = 0; a < NS; ++a) e[a][b] = (rowk_warp && a == ks) ? -pinv : ti[a];
+                }
         }
     }
     __syncthreads();
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < NS; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
+        for (int b = 0; b < NS; ++b) {
             const int i = ty + 32 * a, j = tx + 32 * b;
             if (i < M && j < M) A[(size_t)i * M + j] = e[a][b];
         }
@@ -133,7 +152,11 @@ __device__ bool gs_sweep_invert_reg(double *A, int M, double *tmp2 /* 2 x 128 */
 
 __device__ __forceinline__ bool gs_sweep_invert(double *A, int M, double *tmp, double *piv, double *red, double *logdet)
 {
-    return (M <= 128) ? gs_sweep_invert_reg(A, M, tmp, piv, red, logdet) : gs_sweep_invert_mem(A, M, tmp, piv, red, logdet);
+    if (M <= 32) return gs_sweep_invert_reg<1>(A, M, tmp, piv, red, logdet);
+    if (M <= 64) return gs_sweep_invert_reg<2>(A, M, tmp, piv, red, logdet);
+    if (M <= 96) return gs_sweep_invert_reg<3>(A, M, tmp, piv, red, logdet);
+    if (M <= 128) return gs_sweep_invert_reg<4>(A, M, tmp, piv, red, logdet);
+    return gs_sweep_invert_mem(A, M, tmp, piv, red, logdet);
 }
 
 // C[i][j] = sum_k A[i][k] B[k][j] for a GS_TI x GS_TJ register tile per thread; `emit` consumes
@@ -179,8 +202,8 @@ __global__ void __launch_bounds__(GS_THREADS, 1) global_step_kernel(GsParams p)
     const size_t MM = (size_t)M * M;
     double *X = p.use_smem ? sm : p.X;
     double *W = p.use_smem ? sm + MM : p.W;
-    double *tmp = p.use_smem ? sm + 2 * MM : sm;          // max(M, 256) doubles: pivot column (double buffered when M <= 128)
-    double *piv = tmp + (M > 256 ? M : 256);              // M doubles: the pivots
+    double *tmp = p.use_smem ? sm + 2 * MM : sm;          // max(M, 258) doubles: pivot column, double buffered, + 2 reciprocal pivots
+    double *piv = tmp + (M > 258 ? M : 258);              // M doubles: the pivots
     const GlobalsDev g = *p.glob;
     const double sf2 = g.sf2, beta = g.beta;
     const double *S0 = p.stats + p.off_s0;
@@ -235,6 +258,8 @@ __global__ void __launch_bounds__(GS_THREADS, 1) global_step_kernel(GsParams p)
     // (partial_terms.py:123-131).  The two products behind dF/dKmm (Kmm^-1 Psi2 Kmm^-1, :102-113) only feed the
     // gradients of Z / alpha / sf2 and run in global_step_tail_kernel on the side stream, next to embed_grads.
     // full Psi2 and A = Kmm + beta Psi2 (partial_terms.py:60); row loops, no integer division
+    long long clk[6];
+    clk[0] = clock64();
     for (int i = wid; i < M; i += GS_THREADS / 32) {
         const size_t ro = (size_t)i * M;
         for (int j = lane; j < M; j += 32) {
@@ -244,6 +269,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1) global_step_kernel(GsParams p)
         }
     }
     __syncthreads();
+    clk[1] = clock64();
     bool ok = gs_sweep_invert(X, M, tmp, piv, red, &ldA);
     if (!ok) {                                  // partial_terms.py:455-457: one retry with A + 1e-7 I (status bit 16)
         __syncthreads();
@@ -260,30 +286,50 @@ __global__ void __launch_bounds__(GS_THREADS, 1) global_step_kernel(GsParams p)
         return;
     }
     // X = -A^-1 from here on
+    clk[2] = clock64();
 
     // ---- C = A^-1 Psi1Y, G1 = beta^2 C (partial_terms.py:115-121) -----------------------------
-    for (int idx = tid; idx < M * D; idx += GS_THREADS) {
-        const int i = idx / D, d = idx % D;
+    // M D dot products of length M: four lanes per output (k strided by 4, fixed-order shuffle tree), Psi1Y staged
+    // in shared memory behind the shared copy of C when both fit into W
+    const int DS = D | 1;                      // odd row stride of the shared copy of C: conflict-free column reads
+    const bool cs_smem = (size_t)M * DS <= MM; // W is free in the head: C (M x D) fits there unless D > M
+    const bool py_smem = (size_t)M * (DS + D) <= MM;
+    double *Ps = W + (size_t)M * DS;
+    if (py_smem)
+        for (int idx = tid; idx < M * D; idx += GS_THREADS) Ps[idx] = P1Y[idx];
+    __syncthreads();
+    const double *Pk = py_smem ? Ps : P1Y;
+    const int ntask = ((4 * M * D + 31) / 32) * 32;
+    for (int t = tid; t < ntask; t += GS_THREADS) {
+        const int idx = t >> 2, part = t & 3;
+        const bool valid = idx < M * D;
+        const int i = valid ? idx / D : 0, d = valid ? idx - i * D : 0;
         double s = 0.0;
-        for (int k = 0; k < M; ++k) s = fma(-X[(size_t)i * M + k], P1Y[(size_t)k * D + d], s);
-        p.c_mat[idx] = s;
-        p.g_1[idx] = beta * beta * s;
-        if (D <= M) W[idx] = s;               // shared copy for the C C^T loop below (W is free in the head)
+        for (int k = part; k < M; k += 4) s = fma(-X[(size_t)i * M + k], Pk[(size_t)k * D + d], s);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (valid && part == 0) {
+            p.c_mat[idx] = s;
+            p.g_1[idx] = beta * beta * s;
+            if (cs_smem) W[i * DS + d] = s;
+        }
     }
     __syncthreads();
-    const double *Cs = (D <= M) ? W : p.c_mat;
+    const double *Cs = cs_smem ? W : p.c_mat;
+    const int cst = cs_smem ? DS : D;
     double v = 0.0;
-    for (int idx = tid; idx < M * D; idx += GS_THREADS) v = fma(P1Y[idx], Cs[idx], v);
+    for (int idx = tid; idx < M * D; idx += GS_THREADS) v = fma(P1Y[idx], p.c_mat[idx], v);
     const double tr1 = gp_block_sum(v, red);               // tr(Psi1Y^T A^-1 Psi1Y)
 
     // ---- dF/dPsi2 (partial_terms.py:123-131) and the scalar contractions that need A^-1 only ----
+    clk[3] = clock64();
     double s_ap = 0.0, s_cpc = 0.0, s_22 = 0.0;
     const double hD = 0.5 * (double)D, b3 = 0.5 * beta * beta * beta;
     for (int i = wid; i < M; i += GS_THREADS / 32) {
         const size_t ro = (size_t)i * M;
         for (int j = lane; j < M; j += 32) {
             double e = 0.0;
-            for (int d = 0; d < D; ++d) e = fma(Cs[i * D + d], Cs[j * D + d], e);     // (C C^T)[i,j]
+            for (int d = 0; d < D; ++d) e = fma(Cs[i * cst + d], Cs[j * cst + d], e);     // (C C^T)[i,j]
             const double ai = -X[ro + j], ps = P2[ro + j];
             const double g2 = hD * beta * (p.kmm_inv[ro + j] - ai) - b3 * e;
             p.a_inv[ro + j] = ai;
@@ -302,7 +348,14 @@ __global__ void __launch_bounds__(GS_THREADS, 1) global_step_kernel(GsParams p)
         extra[4] = s_ap; extra[5] = s_cpc; extra[7] = s_22;
     }
     __syncthreads();                     // publishes g_2 to the whole CTA
+    clk[4] = clock64();
     gs_pair_tables(p, p.g_2);
+    __syncthreads();
+    clk[5] = clock64();
+    if (tid == 0) {                      // probe: SM cycles per section (GPARML_A_GS_EXTRA[8..12])
+        double *extra = p.out + 1 + M * Q + Q + 2;
+        for (int k = 0; k < 5; ++k) extra[8 + k] = (double)(clk[k + 1] - clk[k]);
+    }
 }
 
 // Tail of the master step: dF/dKmm (partial_terms.py:102-113) with its two M x M x M products, then the bound
@@ -366,7 +419,7 @@ int gp_launch_global_step(gparml_ctx *c, bool kmm_only, cudaStream_t s)
 int gp_launch_global_step_head(gparml_ctx *c, cudaStream_t s, bool *split)
 {
     const size_t MM = (size_t)c->M * c->M;
-    const size_t vec = (size_t)(c->M > 256 ? c->M : 256) + c->M;
+    const size_t vec = (size_t)(c->M > 258 ? c->M : 258) + c->M;
     *split = (2 * MM + vec) * sizeof(double) <= (size_t)216 * 1024;      // single-CTA path only
     cudaStream_t saved = c->stream;
     c->stream = s;
@@ -393,7 +446,7 @@ static int launch_gs(gparml_ctx *c, bool kmm_only, int phase)
     p.fixed_beta = (c->flags & GPARML_FLAG_FIXED_BETA) ? 1 : 0;
     p.kmm_only = kmm_only ? 1 : 0;
     const size_t MM = (size_t)c->M * c->M;
-    const size_t vec = (size_t)(c->M > 256 ? c->M : 256) + c->M;      // pivot column buffers + pivots
+    const size_t vec = (size_t)(c->M > 258 ? c->M : 258) + c->M;      // pivot column buffers + pivots
     const size_t smem_full = (2 * MM + vec) * sizeof(double);
     p.use_smem = smem_full <= (size_t)216 * 1024 ? 1 : 0;
     const size_t smem = p.use_smem ? smem_full : vec * sizeof(double);

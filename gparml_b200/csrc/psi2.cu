@@ -330,7 +330,7 @@ static int plan_q(gparml_ctx *c, int64_t cnt, int *splits_out)
     const int64_t slots = (int64_t)c->sm_count * occ;
     const int64_t rows_x_P = (int64_t)(1 + 2 * Q) * P;
     int64_t max_splits = (cnt + 4 * PSI2_TN - 1) / (4 * PSI2_TN);
-    const int64_t ws_cap = ((int64_t)256 << 20) / (rows_x_P * (int64_t)sizeof(double)) / 4;   // up to 4 ranges per evaluation
+    const int64_t ws_cap = ((int64_t)512 << 20) / (rows_x_P * (int64_t)sizeof(double)) / GP_MAX_RANGES;   // all ranges of an evaluation share the workspace
     if (max_splits > ws_cap) max_splits = ws_cap;
     if (max_splits > 65535) max_splits = 65535;
     if (max_splits < 1) max_splits = 1;

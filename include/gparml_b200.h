@@ -71,7 +71,10 @@ enum gparml_array {
     GPARML_A_GRAD_X_MU = 14,  /* (n, Q)    dF/dX_mu, positive domain   (partial_terms.py:367-398)       */
     GPARML_A_GRAD_X_S = 15,   /* (n, Q)    dF/dX_S,  positive domain   (partial_terms.py:400-431)       */
     GPARML_A_Y = 16,          /* (n, D)    the shard's outputs                                           */
-    GPARML_A_GRAD_GLOBAL = 17 /* (M*Q + Q + 2) dF/d[Z, sf2, alpha, beta], positive domain               */
+    GPARML_A_GRAD_GLOBAL = 17, /* (M*Q + Q + 2) dF/d[Z, sf2, alpha, beta], positive domain              */
+    GPARML_A_GS_EXTRA = 18    /* (13) scalars of the master step: log det Kmm, log det A, tr(Kmm^-1 Psi2),
+                                 tr(Psi1Y^T A^-1 Psi1Y), four contractions, then (probe) SM clock cycles of the
+                                 head kernel's sections: form A, inversion, C / tr, dF/dPsi2, pair tables   */
 };
 
 /* the 12 accumulated statistics in the reference's layouts (parallel_GPLVM.py:142-151),
@@ -114,7 +117,7 @@ int gparml_set_n_total(gparml_ctx *ctx, int64_t n_total);
 /* Copies Y (n,D), X_mu (n,Q), X_S (n,Q) host -> device; replaces the per-evaluation
  * genfromtxt + load of local_MapReduce.py:195-201 / 323-329.  Also computes
  * sum_n y_n.y_n (partial_terms.py:40).  May be called again with a different n.
- * Asynchronous: the copies run on the context's copy stream (X_mu / X_S in up to four row ranges,
+ * Asynchronous: the copies run on the context's copy stream (X_mu / X_S in up to eight row ranges,
  * then Y) and the next gparml_statistics starts on the first range while the others are still in
  * flight; every other entry point waits for them.  Pageable host arrays may be reused when the call
  * returns, pinned ones must stay valid until the next call that synchronises (gparml_statistics with
