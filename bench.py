@@ -533,6 +533,20 @@ def run_config(env, cfg_name, steps, warmup, args, main_line):
         roofline["prep_points_hbm"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                                        "peak_source": hbm_src, "algorithmic_bytes_per_launch": prep_bytes,
                                        "launch_ms": med["prep_points"], "traffic": dram("prep_points_kernel")[0]}
+    # K6, the optimiser's local-state passes (scg_adapted_local_MapReduce.py:29-243 on device-resident vectors): pure streams
+    if not fixed and main_line:
+        vec_bytes = 2 * n_loc * Q * 8
+        for _ in range(2):
+            ctx.scg_update_d(0.5)
+            ctx.scg_update_grad_old()
+        ms_axpy, _, _ = env.timed(lambda: ctx.scg_update_d(0.5), 10)          # d = g d - new: 2 reads + 1 write
+        ms_copy, _, _ = env.timed(lambda: ctx.scg_update_grad_old(), 10)      # old = new: 1 read + 1 write
+        roofline["scg_local_state_hbm"] = {
+            "bound": "hbm", "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src,
+            "update_d": {"achieved": 3 * vec_bytes / (ms_axpy / 10 * 1e-3) / 1e9, "frac": 3 * vec_bytes / (ms_axpy / 10 * 1e-3) / 1e9 / hbm_peak,
+                         "algorithmic_bytes_per_launch": 3 * vec_bytes, "launch_ms": ms_axpy / 10, "traffic": dram("scg_update_kernel<2>")[0]},
+            "update_grad_old": {"achieved": 2 * vec_bytes / (ms_copy / 10 * 1e-3) / 1e9, "frac": 2 * vec_bytes / (ms_copy / 10 * 1e-3) / 1e9 / hbm_peak,
+                                "algorithmic_bytes_per_launch": 2 * vec_bytes, "launch_ms": ms_copy / 10}}
     out["roofline"] = roofline
     out["phase_ms_median"] = med
 

@@ -130,6 +130,7 @@ extern "C" int gparml_create(gparml_ctx **out, int device, int M, int Q, int D, 
     A_(c->pair_lk, (size_t)c->L.P);
     A_(c->pair_g, (size_t)c->L.P);
     A_(c->pair_zz, (size_t)c->L.P * Q);
+    A_(c->pair_zc, (size_t)c->L.P * ((Q + 1) & ~1));
     A_(c->pair_h, (size_t)c->L.P);
     A_(c->stats, (size_t)c->L.count);
     A_(c->red_ws, 4096);
@@ -154,7 +155,7 @@ extern "C" int gparml_destroy(gparml_ctx *c)
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     void *ptrs[] = {c->Y, c->x_mu, c->x_s, c->grad_d, c->grad_latest, c->grad_new, c->grad_old, c->rec1, c->rec2, c->s_pos, c->s_sig,
-                    c->gx_mu, c->gx_s, c->psi1, c->Z, c->d_glob, c->pair_idx, c->pair_lk, c->pair_g, c->pair_zz, c->pair_h, c->stats, c->ws, c->red_ws,
+                    c->gx_mu, c->gx_s, c->psi1, c->Z, c->d_glob, c->pair_idx, c->pair_lk, c->pair_g, c->pair_zz, c->pair_zc, c->pair_h, c->stats, c->ws, c->red_ws,
                     c->d_status, c->kmm, c->kmm_inv, c->a_inv, c->g_k, c->g_1, c->g_2, c->scratch_x, c->scratch_w, c->c_mat,
                     c->glob_out, c->named_tmp, c->psi2_full, c->gsl_ws, c->rec2f, c->d_yyt};
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);

@@ -148,6 +148,7 @@ struct gparml_ctx {
     double2 *pair_g = nullptr;  // (P) (lk, Gs) for embed_grads
     double2 *pair_h = nullptr;  // (P) (lk + log|Gs|, sign(Gs)) for the expanded-basis embed_grads kernel
     double2 *pair_zz = nullptr; // (P, Q) (zbar_q - center_q, (zbar_q - center_q)^2) for embed_grads
+    double *pair_zc = nullptr;  // (P, Q rounded up to even) zbar_q - center_q alone: the exponent of embed_psi2x reads only this
 
     // statistics
     StatLayout L;

@@ -57,7 +57,7 @@
 // ---------------------------------------------------------------------------------------------
 
 // Psi1 side (partial_terms.py:388-390, 421-423): h1 = B[n,m] Psi1[n,m], B = Y G1^T;
-//   out[q] = sum_m h1 ad_q,  out[Q+q] = sum_m h1 ad_q^2,  out[2Q] = sum_m h1
+//   out[q] = sum_m h1 ad_q,  out[Q+q] = sum_m h1 (ad_q^2 - a_q),  out[2Q] = sum_m h1
 // DR > 0: D <= DR, the point's Y row lives in registers and G1 (zero-padded to DR columns) in shared
 // memory next to Z (B200, c3: 1.39 -> see DESIGN.md); DR = 0: any D, Y and G1 read through L1.
 template <int Q, int DR>
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(128) embed_psi1_kernel(EmbedParams p)
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
         out[q] = s1[q];
-        out[Q + q] = s2[q];
+        out[Q + q] = fma(-a[q], s0, s2[q]);      // sum_m h1 (ad_q^2 - a_q): the finish needs no Psi1 record
     }
     out[2 * Q] = s0;
 }
@@ -146,10 +146,11 @@ static int launch_psi1_part(gparml_ctx *c, const EmbedParams &p, int64_t cnt)
 }
 
 // Combine the split partials and the Psi1 part, add the KL terms (partial_terms.py:385,418),
-// apply the softplus chain and the sign flip (local_MapReduce.py:357-360).
+// apply the softplus chain and the sign flip (local_MapReduce.py:357-360).  Runs when the pair range was split over
+// several CTAs (or on the fp32 path); with one split the epilogue of embed_psi2x does this itself.
 __global__ void __launch_bounds__(256) embed_finish_kernel(const double *__restrict__ partial, int splits,
                                                            const double *__restrict__ psi1_part, int64_t n, int64_t i0, int64_t cnt, int Q, int R,
-                                                           const double *__restrict__ rec1, const double *__restrict__ rec2,
+                                                           const double *__restrict__ rec2,
                                                            const double *__restrict__ s_pos, const double *__restrict__ s_sig,
                                                            double *__restrict__ gx_mu, double *__restrict__ gx_s,
                                                            double *__restrict__ grad_latest, int basis,
@@ -169,23 +170,18 @@ __global__ void __launch_bounds__(256) embed_finish_kernel(const double *__restr
         ah += pr[2 * Q];
     }
     const double *p1 = psi1_part + (size_t)i * W;
-    const double mu = rec2[i * R + 2 * q], w = rec2[i * R + 2 * q + 1], a = rec1[i * R + 2 * q + 1];
-    const double S = s_pos[idx];
-    double t1, t2;     // sum_p h wd_q,  sum_p h wd_q^2
-    if (basis == 0) {  // sqrt(w) basis: am = sum_p h u_q, as = sum_p h u_q^2
-        t1 = sqrt(w) * am;
-        t2 = w * as;
-    } else {           // expanded basis: am = sum_p h zc_q, as = sum_p h zc_q^2
-        const double mc = mu - glob->center[q];
-        t1 = w * fma(mc, ah, -am);
-        t2 = w * (w * fma(mc, fma(mc, ah, -2.0 * am), as));
+    const double2 mw = *reinterpret_cast<const double2 *>(rec2 + i * R + 2 * q);
+    const double mu = mw.x, w = mw.y;
+    double mc = mu - glob->center[q];
+    if (basis == 0) {  // sqrt(w) basis (fp32 kernel): am = sum_p h u_q, as = sum_p h u_q^2 with u = sqrt(w) (mu - zbar);
+        // in the shared formula t1 = w (mc ah - am'), t2 = w^2 (mc^2 ah - 2 mc am' + as') this is mc = 0, am' = -am / sqrt(w), as' = as / w
+        mc = 0.0;
+        const double rw = w > 0.0 ? 1.0 / sqrt(w) : 0.0;
+        am = -am * rw;
+        as = as * rw * rw;
     }
-    const double gmu = -mu - p1[q] - 2.0 * t1;
-    const double gs = -0.5 * (1.0 - 1.0 / S) + 0.5 * (p1[Q + q] - a * p1[2 * Q]) + (2.0 * t2 - w * ah);
-    gx_mu[idx] = gmu;
-    gx_s[idx] = gs;
-    grad_latest[idx] = -gmu;
-    grad_latest[n * Q + idx] = -(gs * s_sig[idx]);
+    gp_embed_finish_one(mu, w, mc, am, as, ah, p1[q], p1[Q + q], s_pos[idx], s_sig[idx], gx_mu + idx, gx_s + idx, grad_latest + idx,
+                        grad_latest + n * Q + idx);
 }
 
 int gp_launch_embed_psi2_f32(gparml_ctx *c, const int *m_bounds, int splits, double *partial, int64_t i0, int64_t i1);
@@ -225,7 +221,7 @@ static int launch_q(gparml_ctx *c, int64_t i0, int64_t i1)
     const int splits = pick_splits(ntiles, slots, max_splits);
     EmbedParams p;
     p.rec1 = c->rec1; p.rec2 = c->rec2; p.Y = c->Y; p.Z = c->Z; p.G1 = c->g_1; p.pair_g = c->pair_g;
-    p.pair_zz = c->pair_zz; p.pair_h = c->pair_h; p.glob = c->d_glob;
+    p.pair_zz = c->pair_zz; p.pair_zc = c->pair_zc; p.pair_h = c->pair_h; p.glob = c->d_glob;
     p.n = c->n; p.i0 = i0; p.i1 = i1; p.M = c->M; p.D = c->D;
     // row splits (fp32 kernel): every split owns about P / splits pairs (row m has M - m pairs)
     const double P = (double)c->L.P;
@@ -244,6 +240,12 @@ static int launch_q(gparml_ctx *c, int64_t i0, int64_t i1)
     GP_TRY(gp_ensure_ws(c, (size_t)(splits + 1) * c->n * W * sizeof(double)));
     p.partial = c->ws;
     p.psi1_part = c->ws + (size_t)splits * c->n * W;
+#ifdef EMB_NO_FUSE
+    p.fuse_finish = 0;
+#else
+    p.fuse_finish = (!fp32 && splits == 1) ? 1 : 0;
+#endif
+    p.s_pos = c->s_pos; p.s_sig = c->s_sig; p.gx_mu = c->gx_mu; p.gx_s = c->gx_s; p.grad_latest = c->grad_latest;
     {   // Psi1 side: Y row in registers / G1 in shared memory when they fit
         const bool fits = (size_t)c->M * (Q + 16) * sizeof(double) <= (size_t)96 * 1024;
         if (fits && c->D <= 4) GP_TRY((launch_psi1_part<Q, 4>(c, p, cnt)));
@@ -254,7 +256,8 @@ static int launch_q(gparml_ctx *c, int64_t i0, int64_t i1)
     if (fp32) GP_TRY(gp_launch_embed_psi2_f32(c, p.m_bounds, splits, p.partial, i0, i1));   // opt-in fp32 evaluation of the Psi2 part
     else GP_TRY(gp_launch_embed_psi2x(c, p, (int)ntiles, splits));
     const int64_t total = cnt * Q;
-    embed_finish_kernel<<<(int)((total + 255) / 256), 256, 0, c->stream>>>(c->ws, splits, p.psi1_part, c->n, i0, cnt, Q, gp_rec_len(Q), c->rec1,
+    if (p.fuse_finish) return GPARML_OK;          // the epilogue of embed_psi2x wrote the gradients
+    embed_finish_kernel<<<(int)((total + 255) / 256), 256, 0, c->stream>>>(c->ws, splits, p.psi1_part, c->n, i0, cnt, Q, gp_rec_len(Q),
                                                                            c->rec2, c->s_pos, c->s_sig, c->gx_mu, c->gx_s,
                                                                            c->grad_latest, fp32 ? 0 : 1, c->d_glob);
     GP_LAUNCH_CHECK(c);

@@ -12,6 +12,7 @@ struct EmbedParams {
     const double2 *pair_g;
     const double2 *pair_h;     // (P) (lk + log|Gs|, sign Gs)
     const double2 *pair_zz;    // (P, Q) (zc, zc^2), zc = zbar - center
+    const double *pair_zc;     // (P, Q rounded up to even) zc alone
     const GlobalsDev *glob;
     int64_t n;           // points in the shard (stride of the partial buffers)
     int64_t i0, i1;      // this launch covers points [i0, i1)
@@ -19,8 +20,29 @@ struct EmbedParams {
     int m_bounds[EMB_MAX_SPLITS + 1];   // row splits (sqrt(w)-basis kernels)
     int p_bounds[EMB_MAX_SPLITS + 1];   // pair splits (expanded-basis kernel)
     double *partial;     // [splits][n][2Q + 1]  (AM, AS, AH) resp. (BZ, BZZ, AH)
-    double *psi1_part;   // [n][2Q + 1]          (sum_m h1 ad, sum_m h1 ad^2, sum_m h1),  h1 = B Psi1
+    double *psi1_part;   // [n][2Q + 1]          (sum_m h1 ad_q, sum_m h1 (ad_q^2 - a_q), -),  h1 = B Psi1
+    // fused finish (expanded-basis kernel with ONE pair split): the epilogue of embed_psi2x writes the gradients itself
+    int fuse_finish;
+    const double *s_pos, *s_sig;
+    double *gx_mu, *gx_s, *grad_latest;
 };
+
+// The last step of the embeddings map for one (point, q): combine the Psi2 sums (expanded basis: am = sum_p h zc_q,
+// as = sum_p h zc_q^2, ah = sum_p h) with the Psi1 part and the KL terms (partial_terms.py:385,418), apply the softplus
+// chain and the sign flip (local_MapReduce.py:357-360).  Shared by embed_finish_kernel and the fused epilogue.
+__device__ __forceinline__ void gp_embed_finish_one(double mu, double w, double mc, double am, double as, double ah, double p1_q,
+                                                    double p1_Qq, double S, double sig, double *gmu, double *gs, double *gl_mu,
+                                                    double *gl_s)
+{
+    const double t1 = w * fma(mc, ah, -am);                                 // sum_p h wd_q
+    const double t2 = w * (w * fma(mc, fma(mc, ah, -2.0 * am), as));        // sum_p h wd_q^2
+    const double g_m = -mu - p1_q - 2.0 * t1;
+    const double g_s = -0.5 * (1.0 - 1.0 / S) + 0.5 * p1_Qq + (2.0 * t2 - w * ah);
+    *gmu = g_m;
+    *gs = g_s;
+    *gl_mu = -g_m;
+    *gl_s = -(g_s * sig);
+}
 
 // embed_x.cu: hand-scheduled expanded-basis Psi2 part (compiled with ptxas -O1 so that the
 // instruction order written in the source is the order that is issued)

@@ -52,14 +52,24 @@ struct ExpState {
 };
 #define GPX_SHIFT 6755399441055744.0
 
+#ifndef EMBX_HORNER
+#define EMBX_HORNER 1          // exponent form: 0 = (zc, zc^2) dot product, 1 = Horner on zc, 2 = Horner + register prefetch
+#endif
+
+// zn: (zc, zc^2) record of the next pair; cn: its zc-only record; cnn: the zc-only record of the pair after it
+// (EMBX_HORNER 2 loads it into zr during block XA); zc: (zc, zc^2) record of the current pair
 template <int Q, int NP, bool DO_E, bool DO_A>
-__device__ __forceinline__ void embx_step(const double2 *__restrict__ zn, const double2 gn, const double2 *__restrict__ zc,
+__device__ __forceinline__ void embx_step(const double2 *__restrict__ zn, const double2 *__restrict__ cn,
+                                          const double2 *__restrict__ cnn, double2 (&zr)[(Q + 1) / 2], const double2 gn,
+                                          const double2 *__restrict__ zc,
                                           const double (&hc)[NP], double (&hn)[NP], const double (&kn)[NP],
                                           const double (&A)[NP][Q], const double (&nW)[NP][Q], double (&bz)[NP][Q],
                                           double (&bzz)[NP][Q], double (&ah)[NP], const double *exp_tab)
 {
     constexpr int PF = EMBX_PF;
     ExpState es[NP];
+    constexpr int QP2 = (Q + 1) / 2;
+#if EMBX_HORNER == 0
     if (DO_E) {
         // ---- block E: exponent of the next pair -------------------------------------------------
         constexpr int NC = (NP == 1) ? 2 : 1;      // sub-chains per sum: always >= 4 independent chains
@@ -87,6 +97,41 @@ __device__ __forceinline__ void embx_step(const double2 *__restrict__ zn, const 
             else es[v].x = gp_exp_clamp(e0[v][0] + e1[v][0]);
         }
     }
+#else
+    if (DO_E) {
+        // ---- block E: exponent of the next pair, in Horner form ---------------------------------
+        //   kn + sum_q zc_q (A_q + nW_q zc_q):  t = fma(nW, zc, A), e = fma(t, zc, e)
+        // -- still 2 FMAs per (point, q) but only zc is read (half the shared-memory bytes of the (zc, zc^2)
+        // form: Q/2 16-byte loads from the zc-only ring), software-pipelined by one latent dimension so that e(q)
+        // issues four instructions after the t(q) it depends on.
+#if EMBX_HORNER == 1
+#pragma unroll
+        for (int k = 0; k < QP2; ++k) zr[k] = cn[k];
+#endif
+        double e[NP][2], t[NP], tn[NP];
+#pragma unroll
+        for (int v = 0; v < NP; ++v) {
+            e[v][0] = gn.x;
+            e[v][1] = kn[v];
+            t[v] = fma(nW[v][0], zr[0].x, A[v][0]);
+        }
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const double zq = (q & 1) ? zr[q >> 1].y : zr[q >> 1].x;
+            if (q + 1 < Q) {
+                const double zq1 = ((q + 1) & 1) ? zr[(q + 1) >> 1].y : zr[(q + 1) >> 1].x;
+#pragma unroll
+                for (int v = 0; v < NP; ++v) tn[v] = fma(nW[v][(q + 1) < Q ? (q + 1) : 0], zq1, A[v][(q + 1) < Q ? (q + 1) : 0]);
+            }
+#pragma unroll
+            for (int v = NP - 1; v >= 0; --v) e[v][q & 1] = fma(t[v], zq, e[v][q & 1]);
+#pragma unroll
+            for (int v = 0; v < NP; ++v) t[v] = tn[v];
+        }
+#pragma unroll
+        for (int v = 0; v < NP; ++v) es[v].x = gp_exp_clamp(e[v][0] + e[v][1]);
+    }
+#endif
     // ---- block XA: exp steps of the next pair, each followed by one group of accumulations ---------
     double2 zz[Q];
     if (DO_A) {
@@ -96,7 +141,13 @@ __device__ __forceinline__ void embx_step(const double2 *__restrict__ zn, const 
         for (int v = 0; v < NP; ++v) ah[v] += hc[v];
     }
     const int sg = DO_E ? (__double2hiint(gn.y) & 0x80000000) : 0;
+#if EMBX_HORNER == 2
+#define EMBX_PREF(q) if (DO_E && (q) < QP2) zr[(q) < QP2 ? (q) : 0] = cnn[(q) < QP2 ? (q) : 0];
+#else
+#define EMBX_PREF(q)
+#endif
 #define EMBX_GROUP(q)                                                                        \
+    EMBX_PREF(q)                                                                             \
     if (DO_A && (q) < Q) {                                                                   \
         if ((q) + PF < Q) zz[((q) + PF) < Q ? ((q) + PF) : 0] = zc[((q) + PF) < Q ? ((q) + PF) : 0]; \
         _Pragma("unroll") for (int v = 0; v < NP; ++v) bz[v][(q) < Q ? (q) : 0] = fma(hc[v], zz[(q) < Q ? (q) : 0].x, bz[v][(q) < Q ? (q) : 0]); \
@@ -161,6 +212,7 @@ __device__ __forceinline__ void embx_step(const double2 *__restrict__ zn, const 
     EMBX_GROUP(14)
     EMBX_GROUP(15)
 #undef EMBX_GROUP
+#undef EMBX_PREF
     if (DO_E) {
 #pragma unroll
         for (int v = 0; v < NP; ++v) {
@@ -177,8 +229,12 @@ embed_psi2x_kernel(EmbedParams p)
 {
     constexpr int R = (3 * Q + 2) & ~1;
     constexpr int NP = EmbXCfg<Q>::NP;
-    constexpr int CP = EMBX_CP, ST = EMBX_STAGES;
-    __shared__ __align__(16) double2 ring_z[ST][CP * Q];
+    constexpr int CP = (EMBX_HORNER && Q > 12) ? EMBX_CP / 2 : EMBX_CP, ST = EMBX_STAGES;      // static shared memory <= 48 kB
+    constexpr int QP = (Q + 1) & ~1;
+    __shared__ __align__(16) double2 ring_z[ST][CP * Q];          // (zc, zc^2): the accumulations
+#if EMBX_HORNER
+    __shared__ __align__(16) double ring_c[ST][CP * QP];          // zc alone: the exponent
+#endif
     __shared__ __align__(16) double2 ring_g[ST][CP];
     __shared__ __align__(8) uint64_t bar[ST];
     __shared__ double exp_tab[GP_EXP_TAB];
@@ -197,7 +253,13 @@ embed_psi2x_kernel(EmbedParams p)
         const int64_t base = p_lo + (int64_t)t * CP;
         const int cnt = (int)((p_hi - base < CP) ? (p_hi - base) : CP);
         const uint32_t bz_ = (uint32_t)cnt * Q * sizeof(double2), bg = (uint32_t)cnt * sizeof(double2);
+#if EMBX_HORNER
+        const uint32_t bc = (uint32_t)cnt * QP * sizeof(double);
+        gp_mbar_expect_tx(&bar[s], bz_ + bg + bc);
+        gp_bulk_g2s(&ring_c[s][0], p.pair_zc + base * QP, bc, &bar[s]);
+#else
         gp_mbar_expect_tx(&bar[s], bz_ + bg);
+#endif
         gp_bulk_g2s(&ring_z[s][0], p.pair_zz + base * Q, bz_, &bar[s]);
         gp_bulk_g2s(&ring_g[s][0], p.pair_h + base, bg, &bar[s]);
     };
@@ -234,18 +296,52 @@ embed_psi2x_kernel(EmbedParams p)
         const int cnt = (int)((p_hi - base < CP) ? (p_hi - base) : CP);
         gp_mbar_wait(&bar[s], (uint32_t)((t / ST) & 1));
         const double2 *zt = &ring_z[s][0];
+#if EMBX_HORNER
+        const double2 *ct = reinterpret_cast<const double2 *>(&ring_c[s][0]);      // QP / 2 pairs of zc per pair record
+#else
+        const double2 *ct = &ring_z[s][0];                                         // unused
+#endif
         const double2 *gt = &ring_g[s][0];
         double hc[NP], hn[NP];
-        embx_step<Q, NP, true, false>(zt, gt[0], zt, hc, hc, kn, A, nW, bz, bzz, ah, exp_tab);      // h of pair 0
+        double2 zr[(Q + 1) / 2];
+        constexpr int CS = QP / 2;                 // double2 per zc-only record
+#if EMBX_HORNER == 2
+#pragma unroll
+        for (int k = 0; k < (Q + 1) / 2; ++k) zr[k] = ct[k];                                        // zc of pair 0
+#endif
+        // h of pair 0 (prefetches the zc of pair 1)
+        embx_step<Q, NP, true, false>(zt, ct, ct + (cnt > 1 ? 1 : 0) * CS, zr, gt[0], zt, hc, hc, kn, A, nW, bz, bzz, ah, exp_tab);
 #pragma unroll 1
         for (int j = 0; j + 1 < cnt; ++j) {
-            embx_step<Q, NP, true, true>(zt + (j + 1) * Q, gt[j + 1], zt + j * Q, hc, hn, kn, A, nW, bz, bzz, ah, exp_tab);
+            const int j2 = j + 2 < cnt ? j + 2 : cnt - 1;
+            embx_step<Q, NP, true, true>(zt + (j + 1) * Q, ct + (j + 1) * CS, ct + j2 * CS, zr, gt[j + 1], zt + j * Q, hc, hn, kn, A,
+                                         nW, bz, bzz, ah, exp_tab);
 #pragma unroll
             for (int v = 0; v < NP; ++v) hc[v] = hn[v];
         }
-        embx_step<Q, NP, false, true>(zt, gt[0], zt + (cnt - 1) * Q, hc, hn, kn, A, nW, bz, bzz, ah, exp_tab);   // last pair
+        embx_step<Q, NP, false, true>(zt, ct, ct, zr, gt[0], zt + (cnt - 1) * Q, hc, hn, kn, A, nW, bz, bzz, ah, exp_tab);   // last pair
         __syncthreads();      // every thread is done reading stage s
         if (tid == 0 && t + ST < nchunks) issue(t + ST);
+    }
+    if (p.fuse_finish) {
+        // one pair split: this thread holds the complete sums of its points -- finish here instead of a round trip
+        // of (2Q + 1) doubles per point through HBM and a second kernel (embed.cu embed_finish_kernel, same arithmetic)
+#pragma unroll
+        for (int v = 0; v < NP; ++v) {
+            if (valid[v]) {
+                const double2 *r2 = reinterpret_cast<const double2 *>(p.rec2 + i[v] * R);
+                const double *p1 = p.psi1_part + (size_t)i[v] * (2 * Q + 1);
+                const int64_t o = i[v] * Q;
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const double2 mw = r2[q];
+                    gp_embed_finish_one(mw.x, mw.y, mw.x - p.glob->center[q], bz[v][q], bzz[v][q], ah[v], p1[q], p1[Q + q],
+                                        p.s_pos[o + q], p.s_sig[o + q], p.gx_mu + o + q, p.gx_s + o + q, p.grad_latest + o + q,
+                                        p.grad_latest + p.n * Q + o + q);
+                }
+            }
+        }
+        return;
     }
 #pragma unroll
     for (int v = 0; v < NP; ++v) {

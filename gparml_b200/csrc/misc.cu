@@ -156,23 +156,41 @@ int gp_launch_stats_allreduce(gparml_ctx *root, double *const *bufs, int n, doub
 //               2 update_d (d = scale * d - new)   3 update_X (X += scale * d)
 //               4 grad_old = grad_new   5 grad_new = grad_latest
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) scg_reduce_kernel(int op, double scale, int64_t len, const double *__restrict__ latest,
+// element-wise term of reduce op `OP`
+template <int OP>
+__device__ __forceinline__ double scg_term(double acc, double scale, double latest, double gnew, double gold, double d)
+{
+    switch (OP) {
+        case 0: return fma(gnew, d, acc);
+        case 1: return fma(d, d, acc);
+        case 2: return fma(d, latest - gnew, acc);
+        case 3: return fma(gnew, gnew, acc);
+        case 4: return fma(gnew, gold, acc);
+        default: return fmax(acc, fabs(scale * d));
+    }
+}
+
+// 16-byte loads, two independent partial sums per thread, only the vectors an op needs are read
+template <int OP>
+__global__ void __launch_bounds__(256) scg_reduce_kernel(double scale, int64_t len, const double *__restrict__ latest,
                                                          const double *__restrict__ gnew, const double *__restrict__ gold,
                                                          const double *__restrict__ d, double *__restrict__ partials)
 {
     __shared__ double sh[33];
-    double acc = 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
-        switch (op) {
-            case 0: acc = fma(gnew[i], d[i], acc); break;
-            case 1: acc = fma(d[i], d[i], acc); break;
-            case 2: acc = fma(d[i], latest[i] - gnew[i], acc); break;
-            case 3: acc = fma(gnew[i], gnew[i], acc); break;
-            case 4: acc = fma(gnew[i], gold[i], acc); break;
-            default: acc = fmax(acc, fabs(scale * d[i])); break;
-        }
+    constexpr bool need_l = OP == 2, need_n = OP == 0 || OP == 2 || OP == 3 || OP == 4, need_o = OP == 4,
+                   need_d = OP == 0 || OP == 1 || OP == 2 || OP == 5;
+    double acc0 = 0.0, acc1 = 0.0;
+    const int64_t len2 = len >> 1;           // len = 2 n Q is even, the vectors are cudaMalloc'ed (16-byte aligned)
+    const double2 *l2 = reinterpret_cast<const double2 *>(latest), *n2 = reinterpret_cast<const double2 *>(gnew),
+                  *o2 = reinterpret_cast<const double2 *>(gold), *d2 = reinterpret_cast<const double2 *>(d);
+    const double2 z = make_double2(0.0, 0.0);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len2; i += (int64_t)gridDim.x * blockDim.x) {
+        const double2 vl = need_l ? l2[i] : z, vn = need_n ? n2[i] : z, vo = need_o ? o2[i] : z, vd = need_d ? d2[i] : z;
+        acc0 = scg_term<OP>(acc0, scale, vl.x, vn.x, vo.x, vd.x);
+        acc1 = scg_term<OP>(acc1, scale, vl.y, vn.y, vo.y, vd.y);
     }
-    if (op == 5) {
+    double acc = (OP == 5) ? fmax(acc0, acc1) : acc0 + acc1;
+    if (OP == 5) {
         // block max (order independent, exact)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc = fmax(acc, __shfl_xor_sync(0xffffffffu, acc, o));
@@ -212,8 +230,17 @@ int gp_scg_reduce(gparml_ctx *c, int op, double scale, double *host_out)
     const int64_t len = 2 * c->n * c->Q;
     int blocks = (int)((len + 256 * 8 - 1) / (256 * 8));
     if (blocks < 1) blocks = 1;
-    if (blocks > 1024) blocks = 1024;
-    scg_reduce_kernel<<<blocks, 256, 0, c->stream>>>(op, scale, len, c->grad_latest, c->grad_new, c->grad_old, c->grad_d, c->red_ws);
+    if (blocks > c->sm_count * 8) blocks = c->sm_count * 8;       // <= 1184 partials (red_ws holds 2048), 8 CTAs per SM resident
+#define SCG_RED(OP) scg_reduce_kernel<OP><<<blocks, 256, 0, c->stream>>>(scale, len, c->grad_latest, c->grad_new, c->grad_old, c->grad_d, c->red_ws)
+    switch (op) {
+        case 0: SCG_RED(0); break;
+        case 1: SCG_RED(1); break;
+        case 2: SCG_RED(2); break;
+        case 3: SCG_RED(3); break;
+        case 4: SCG_RED(4); break;
+        default: SCG_RED(5); break;
+    }
+#undef SCG_RED
     GP_LAUNCH_CHECK(c);
     scg_final_kernel<<<1, 256, 0, c->stream>>>(op, c->red_ws, blocks, c->red_ws + 2048);
     GP_LAUNCH_CHECK(c);
@@ -222,22 +249,43 @@ int gp_scg_reduce(gparml_ctx *c, int op, double scale, double *host_out)
     return GPARML_OK;
 }
 
-__global__ void __launch_bounds__(256) scg_update_kernel(int op, double scale, int64_t len, int64_t half, double *__restrict__ latest,
-                                                         double *__restrict__ gnew, double *__restrict__ gold, double *__restrict__ d,
-                                                         double *__restrict__ x_mu, double *__restrict__ x_s)
+__global__ void __launch_bounds__(256) scg_update_x_scalar_kernel(double scale, int64_t half, const double *__restrict__ d,
+                                                                  double *__restrict__ x_mu, double *__restrict__ x_s)
 {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
-        switch (op) {
-            case 0: { const double g = latest[i]; gnew[i] = g; gold[i] = g; d[i] = -g; } break;
-            case 1: d[i] = -gnew[i]; break;
-            case 2: d[i] = __dsub_rn(__dmul_rn(scale, d[i]), gnew[i]); break;   // no FMA contraction: bit-equal to numpy
-            case 3:
-                if (i < half) x_mu[i] = __dadd_rn(x_mu[i], __dmul_rn(scale, d[i]));
-                else x_s[i - half] = __dadd_rn(x_s[i - half], __dmul_rn(scale, d[i]));
-                break;
-            case 4: gold[i] = gnew[i]; break;
-            default: gnew[i] = latest[i]; break;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * half; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i < half) x_mu[i] = __dadd_rn(x_mu[i], __dmul_rn(scale, d[i]));
+        else x_s[i - half] = __dadd_rn(x_s[i - half], __dmul_rn(scale, d[i]));
+    }
+}
+
+// update ops on 16-byte pairs; op 3 (X += scale d) runs on the mean and the variance half separately
+template <int OP>
+__global__ void __launch_bounds__(256) scg_update_kernel(double scale, int64_t len, double *__restrict__ latest,
+                                                         double *__restrict__ gnew, double *__restrict__ gold, double *__restrict__ d,
+                                                         double *__restrict__ x)
+{
+    const int64_t len2 = len >> 1;
+    double2 *l2 = reinterpret_cast<double2 *>(latest), *n2 = reinterpret_cast<double2 *>(gnew), *o2 = reinterpret_cast<double2 *>(gold),
+            *d2 = reinterpret_cast<double2 *>(d), *x2 = reinterpret_cast<double2 *>(x);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len2; i += (int64_t)gridDim.x * blockDim.x) {
+        switch (OP) {
+            case 0: { const double2 g = l2[i]; n2[i] = g; o2[i] = g; d2[i] = make_double2(-g.x, -g.y); } break;
+            case 1: { const double2 g = n2[i]; d2[i] = make_double2(-g.x, -g.y); } break;
+            case 2: {   // no FMA contraction: bit-equal to numpy
+                const double2 v = d2[i], g = n2[i];
+                d2[i] = make_double2(__dsub_rn(__dmul_rn(scale, v.x), g.x), __dsub_rn(__dmul_rn(scale, v.y), g.y));
+            } break;
+            case 3: {
+                const double2 v = d2[i], xx = x2[i];
+                x2[i] = make_double2(__dadd_rn(xx.x, __dmul_rn(scale, v.x)), __dadd_rn(xx.y, __dmul_rn(scale, v.y)));
+            } break;
+            case 4: o2[i] = n2[i]; break;
+            default: n2[i] = l2[i]; break;
         }
+    }
+    if ((len & 1) && blockIdx.x == 0 && threadIdx.x == 0) {      // odd tail (op 3 with n Q odd)
+        const int64_t i = len - 1;
+        if (OP == 3) x[i] = __dadd_rn(x[i], __dmul_rn(scale, d[i]));
     }
 }
 
@@ -245,10 +293,29 @@ int gp_scg_update(gparml_ctx *c, int op, double scale)
 {
     const int64_t half = c->n * c->Q, len = 2 * half;
     if (len == 0) return GPARML_OK;
-    int blocks = (int)((len + 256 * 4 - 1) / (256 * 4));
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    scg_update_kernel<<<blocks, 256, 0, c->stream>>>(op, scale, len, half, c->grad_latest, c->grad_new, c->grad_old, c->grad_d,
-                                                     c->x_mu, c->x_s);
+    int blocks = (int)((len + 256 * 8 - 1) / (256 * 8));
+    if (blocks > c->sm_count * 8) blocks = c->sm_count * 8;
+    if (blocks < 1) blocks = 1;
+#define SCG_UPD(OP, LEN, D, X) scg_update_kernel<OP><<<blocks, 256, 0, c->stream>>>(scale, LEN, c->grad_latest, c->grad_new, c->grad_old, D, X)
+    switch (op) {
+        case 0: SCG_UPD(0, len, c->grad_d, nullptr); break;
+        case 1: SCG_UPD(1, len, c->grad_d, nullptr); break;
+        case 2: SCG_UPD(2, len, c->grad_d, nullptr); break;
+        case 3:
+            if (half % 2 == 0) {
+                // x_mu and x_s are separate allocations: two launches over 16-byte pairs
+                SCG_UPD(3, half, c->grad_d, c->x_mu);
+                GP_LAUNCH_CHECK(c);
+                SCG_UPD(3, half, c->grad_d + half, c->x_s);
+            } else {
+                // n Q odd: the variance half of grad_d starts 8 bytes off a 16-byte boundary -> scalar kernel
+                scg_update_x_scalar_kernel<<<blocks, 256, 0, c->stream>>>(scale, half, c->grad_d, c->x_mu, c->x_s);
+            }
+            break;
+        case 4: SCG_UPD(4, len, c->grad_d, nullptr); break;
+        default: SCG_UPD(5, len, c->grad_d, nullptr); break;
+    }
+#undef SCG_UPD
     GP_LAUNCH_CHECK(c);
     return GPARML_OK;
 }

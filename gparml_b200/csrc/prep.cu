@@ -84,29 +84,33 @@ struct PrepParams {
 
 #define PREP_TP 128        // points per tile
 #define PREP_THREADS 256
+#define PREP_MINB 5        // resident CTAs per SM the register budget is capped for (48 registers)
 
-// Three phases per tile of 128 points so that every global access is coalesced:
-//   A  thread per (point, q) element: reads mu / S_raw / direction, writes S and sigmoid, puts the
-//      record fields into shared-memory tiles;
-//   B  thread per point: log-prefactors from the products over q;
-//   C  the two record tiles leave as contiguous 16-byte stores.
-// (The first version, one thread per point writing its own 256-byte records, reached 1.05 TB/s.)
-__global__ void __launch_bounds__(PREP_THREADS) prep_points_kernel(PrepParams p)
+// Two phases per tile of 128 points:
+//   A  thread per (point, q) element: reads mu / S_raw / direction, evaluates the per-element quantities and stores
+//      them where they live in the records -- (mu_q, a_q) and (mu_q, w_q) are 16-byte pairs at offset 2q of a
+//      256-byte-aligned record, so the 10 consecutive lanes of a point write 160 contiguous bytes (five full
+//      sectors), the v_q 80 contiguous bytes -- plus S, sigmoid and the two denominators (shared memory);
+//   B  thread per point: log-prefactors from the products over q, one 16-byte store per record.
+// History (B200, c3, 992 B/point): one thread per point writing its own 256-byte records 1.05 TB/s; records
+// staged through 77 kB of shared memory per CTA (2 CTAs/SM, 3 barriers per tile, 50 % bank conflicts) 2.6 TB/s;
+// this version (20 kB, direct stores, one exp less per element): see DESIGN.md.
+__global__ void __launch_bounds__(PREP_THREADS, PREP_MINB) prep_points_kernel(PrepParams p)
 {
-    extern __shared__ __align__(16) double psm[];
+    extern __shared__ __align__(16) double dens[];      // [tile parity][den1 | den2][PREP_TP * Q]
     __shared__ double sh[33];
     __shared__ GlobalsDev g;
     const int Q = p.Q, R = p.R, tid = threadIdx.x;
-    double *r1t = psm, *r2t = r1t + PREP_TP * R, *d1s = r2t + PREP_TP * R, *d2s = d1s + PREP_TP * Q;
-    float *rft = reinterpret_cast<float *>(d2s + PREP_TP * Q);     // [TP][RF], only with rec2f
     const int RF = p.RF;
     if (tid == 0) g = *p.glob;
     __syncthreads();
     double kl = 0.0, zeros = 0.0;
     bool bad = false;
     const bool stepping = p.mode == 0 && p.grad_d != nullptr && p.step != 0.0;
-    for (int64_t base = p.i0 + (int64_t)blockIdx.x * PREP_TP; base < p.i1; base += (int64_t)gridDim.x * PREP_TP) {
+    int parity = 0;
+    for (int64_t base = p.i0 + (int64_t)blockIdx.x * PREP_TP; base < p.i1; base += (int64_t)gridDim.x * PREP_TP, parity ^= 1) {
         const int cnt = (int)((p.i1 - base < PREP_TP) ? (p.i1 - base) : PREP_TP);
+        double *d1s = dens + (size_t)parity * 2 * PREP_TP * Q, *d2s = d1s + PREP_TP * Q;
         for (int e = tid; e < cnt * Q; e += PREP_THREADS) {
             const int pt = e / Q, q = e - pt * Q;
             const int64_t gi = base * Q + e;
@@ -117,8 +121,9 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_points_kernel(PrepParams p)
                     sr = fma(p.grad_d[p.n * Q + gi], p.step, sr);
                 }
                 if (!(fabs(sr) < LIM_VAL)) bad = true;                      // supporting_functions.py:154
-                S = log(1.0 + exp(sr));                                    // supporting_functions.py:155 (same naive form)
-                sig = 1.0 / (exp(-sr) + 1.0);                              // supporting_functions.py:167
+                const double t = exp(sr), u = 1.0 + t;
+                S = log(u);                                                // supporting_functions.py:155 (same naive form)
+                sig = t / u;                                               // = 1 / (exp(-sr) + 1), supporting_functions.py:167
             } else {
                 S = sr;
                 sig = 1.0;
@@ -126,12 +131,15 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_points_kernel(PrepParams p)
             const double al = g.alpha[q];
             const double den1 = fma(al, S, 1.0), den2 = fma(2.0 * al, S, 1.0);
             const double a = al / den1, w = al / den2;
-            double *r1 = r1t + pt * R, *r2 = r2t + pt * R;
-            r1[2 * q] = mu;  r1[2 * q + 1] = a;  r1[2 * Q + q] = al * S * a;
-            r2[2 * q] = mu;  r2[2 * q + 1] = w;  r2[2 * Q + q] = al * S * w;
+            double *r1 = p.rec1 + (base + pt) * R, *r2 = p.rec2 + (base + pt) * R;
+            *reinterpret_cast<double2 *>(r1 + 2 * q) = make_double2(mu, a);
+            *reinterpret_cast<double2 *>(r2 + 2 * q) = make_double2(mu, w);
+            r1[2 * Q + q] = al * S * a;
+            r2[2 * Q + q] = al * S * w;
             if (p.rec2f) {
-                float *rf = rft + pt * RF;
-                rf[2 * q] = (float)(mu - g.center[q]);  rf[2 * q + 1] = (float)w;  rf[2 * Q + q] = (float)(al * S * w);
+                float *rf = p.rec2f + (base + pt) * RF;
+                *reinterpret_cast<float2 *>(rf + 2 * q) = make_float2((float)(mu - g.center[q]), (float)w);
+                rf[2 * Q + q] = (float)(al * S * w);
             }
             d1s[e] = den1;
             d2s[e] = den2;
@@ -146,24 +154,22 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_points_kernel(PrepParams p)
         for (int pt = tid; pt < cnt; pt += PREP_THREADS) {
             double prod1 = 1.0, prod2 = 1.0;
             for (int q = 0; q < Q; ++q) { prod1 *= d1s[pt * Q + q]; prod2 *= d2s[pt * Q + q]; }
-            r1t[pt * R + 3 * Q] = g.log_sf2 - 0.5 * log(prod1);
-            r2t[pt * R + 3 * Q] = 2.0 * g.log_sf2 - 0.5 * log(prod2);
-            if (3 * Q + 1 < R) { r1t[pt * R + 3 * Q + 1] = 0.0; r2t[pt * R + 3 * Q + 1] = 0.0; }
+            const double l1 = g.log_sf2 - 0.5 * log(prod1), l2 = 2.0 * g.log_sf2 - 0.5 * log(prod2);
+            double *r1 = p.rec1 + (base + pt) * R + 3 * Q, *r2 = p.rec2 + (base + pt) * R + 3 * Q;
+            if (3 * Q + 1 < R) {          // even Q: prefactor and the padding double are one aligned 16-byte store
+                *reinterpret_cast<double2 *>(r1) = make_double2(l1, 0.0);
+                *reinterpret_cast<double2 *>(r2) = make_double2(l2, 0.0);
+            } else {
+                *r1 = l1;
+                *r2 = l2;
+            }
             if (p.rec2f) {
-                rft[pt * RF + 3 * Q] = (float)r2t[pt * R + 3 * Q];
-                for (int k = 3 * Q + 1; k < RF; ++k) rft[pt * RF + k] = 0.f;
+                float *rf = p.rec2f + (base + pt) * RF;
+                rf[3 * Q] = (float)l2;
+                for (int k = 3 * Q + 1; k < RF; ++k) rf[k] = 0.f;
             }
         }
-        __syncthreads();
-        if (p.rec2f) {
-            float4 *of = reinterpret_cast<float4 *>(p.rec2f + base * RF);
-            const float4 *inf = reinterpret_cast<const float4 *>(rft);
-            for (int e = tid; e < cnt * (RF / 4); e += PREP_THREADS) of[e] = inf[e];
-        }
-        double2 *o1 = reinterpret_cast<double2 *>(p.rec1 + base * R), *o2 = reinterpret_cast<double2 *>(p.rec2 + base * R);
-        const double2 *i1 = reinterpret_cast<const double2 *>(r1t), *i2 = reinterpret_cast<const double2 *>(r2t);
-        for (int e = tid; e < cnt * (R / 2); e += PREP_THREADS) { o1[e] = i1[e]; o2[e] = i2[e]; }
-        __syncthreads();
+        // no second barrier: the next tile writes the other half of the denominator buffer
     }
     if (bad) atomicOr(p.status, 4);
     kl = gp_block_sum(bad ? NAN : 0.5 * kl, sh);      // NaN marks the failed input check for prep_finish (ST_FLAGS)
@@ -223,8 +229,7 @@ int gp_launch_prep_range(gparml_ctx *c, int64_t i0, int64_t i1, double *kl_parti
     int blocks = (int)((i1 - i0 + PREP_TP - 1) / PREP_TP);
     if (blocks > max_blocks) blocks = max_blocks;
     if (blocks < 1) blocks = 1;
-    const size_t smem = ((size_t)2 * PREP_TP * p.R + (size_t)2 * PREP_TP * p.Q) * sizeof(double) +
-                        (p.rec2f ? (size_t)PREP_TP * p.RF * sizeof(float) : 0);
+    const size_t smem = (size_t)4 * PREP_TP * p.Q * sizeof(double);
     GP_CUDA(cudaFuncSetAttribute(prep_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     p.kl_partials = kl_partials;
     prep_points_kernel<<<blocks, PREP_THREADS, smem, c->stream>>>(p);
@@ -244,8 +249,9 @@ int gp_launch_prep_finish(gparml_ctx *c, const double *kl_partials, int blocks)
 int gp_launch_prep(gparml_ctx *c)
 {
     int blocks = 1;
-    GP_TRY(gp_ensure_ws(c, (size_t)c->sm_count * 8 * 2 * sizeof(double)));
-    GP_TRY(gp_launch_prep_range(c, 0, c->n, c->ws, c->sm_count * 8, &blocks));
+    // persistent grid: every CTA resident (PREP_MINB per SM), tiles dealt grid-stride
+    GP_TRY(gp_ensure_ws(c, (size_t)c->sm_count * PREP_MINB * 2 * sizeof(double)));
+    GP_TRY(gp_launch_prep_range(c, 0, c->n, c->ws, c->sm_count * PREP_MINB, &blocks));
     return gp_launch_prep_finish(c, c->ws, blocks);
 }
 
@@ -256,7 +262,7 @@ int gp_launch_prep(gparml_ctx *c)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pair_table_kernel(const double *__restrict__ Z, int M, int Q, const GlobalsDev *__restrict__ glob,
                                                          int2 *__restrict__ pair_idx, double *__restrict__ pair_lk,
-                                                         double2 *__restrict__ pair_zz)
+                                                         double2 *__restrict__ pair_zz, double *__restrict__ pair_zc)
 {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)M * M) return;
@@ -268,18 +274,21 @@ __global__ void __launch_bounds__(256) pair_table_kernel(const double *__restric
         s = fma(glob->alpha[q] * dz, dz, s);
     }
     const int64_t p = gp_pair_index(M, a, b);
+    const int QP = (Q + 1) & ~1;
     pair_idx[p] = make_int2(a, b);
     pair_lk[p] = -0.25 * s;
     for (int q = 0; q < Q; ++q) {
         const double zc = 0.5 * (Z[a * Q + q] + Z[b * Q + q]) - glob->center[q];
         pair_zz[p * Q + q] = make_double2(zc, zc * zc);
+        pair_zc[p * QP + q] = zc;
     }
+    if (QP > Q) pair_zc[p * QP + Q] = 0.0;
 }
 
 int gp_launch_pair_table(gparml_ctx *c)
 {
     const int64_t total = (int64_t)c->M * c->M;
-    pair_table_kernel<<<(int)((total + 255) / 256), 256, 0, c->stream>>>(c->Z, c->M, c->Q, c->d_glob, c->pair_idx, c->pair_lk, c->pair_zz);
+    pair_table_kernel<<<(int)((total + 255) / 256), 256, 0, c->stream>>>(c->Z, c->M, c->Q, c->d_glob, c->pair_idx, c->pair_lk, c->pair_zz, c->pair_zc);
     GP_LAUNCH_CHECK(c);
     return GPARML_OK;
 }
