@@ -418,12 +418,10 @@ int gp_launch_global_step(gparml_ctx *c, bool kmm_only, cudaStream_t s)
 // phase 1 (head) on `s`; *split = true if the tail still has to be launched (gp_launch_global_step_tail)
 int gp_launch_global_step_head(gparml_ctx *c, cudaStream_t s, bool *split)
 {
-    const size_t MM = (size_t)c->M * c->M;
-    const size_t vec = (size_t)(c->M > 258 ? c->M : 258) + c->M;
-    *split = (2 * MM + vec) * sizeof(double) <= (size_t)216 * 1024;      // single-CTA path only
+    *split = true;                            // both paths (single-CTA and multi-kernel) have a separate tail
     cudaStream_t saved = c->stream;
     c->stream = s;
-    const int r = launch_gs(c, false, *split ? 1 : 0);
+    const int r = launch_gs(c, false, 1);
     c->stream = saved;
     return r;
 }

@@ -1,16 +1,24 @@
 // K4 for large M (two M x M work matrices no longer fit one SM's shared memory, M > 116):
 // the same master step as global_step.cu spread over the whole GPU as a short sequence of
-// kernels on L2-resident matrices (M = 500: 2 MB each).
+// kernels on L2-resident matrices (M = 500: 2 MB each), split like the single-CTA path into
 //
-//   build        Kmm, full Psi2                                   elementwise, multi-CTA
-//   block sweep  A <- -A^-1 in blocks of NB = 32 pivots:           M / NB steps of
-//                  pivot   invert the NB x NB pivot block (1 CTA, register-resident sweep)
-//                  panel   T = A[:, K] Pinv, keep the old panel    (M rows in parallel)
-//                  update  A[i,j] -= T[i,:] . Old[j,:]  (rank-NB)  64 x 64 tiles, all SMs
-//   gemm         U = Psi2 Kinv,  T2 = Kinv U,  C = A^-1 Psi1Y      tiled DGEMM, all SMs
-//   assemble     dF/dKmm, dF/dPsi2, scalar contractions            elementwise + partial sums
-//   tail         bound, hyper-parameter gradients, pair table      one CTA (gs_common.cuh)
+//   kmm_only (side stream at set_globals)   Kmm, block sweep -> Kmm^-1, pivots
+//   head (context stream; what embed_grads waits for)
+//       build / form A   full Psi2, A = Kmm + beta Psi2                  elementwise
+//       block sweep      A <- -A^-1 in blocks of NB = 32 pivots: pivot (1 CTA, register-resident sweep),
+//                        panel T = A[:, K] Pinv (one warp per row), rank-NB update (64 x 64 tiles)
+//       gemm             C = A^-1 Psi1Y
+//       head_finish      dF/dPsi1Y, dF/dPsi2 (no M^3 product needed), C C^T kept for the tail,
+//                        partial sums of the contractions that need A^-1 only
+//       pair tables      (lk, Gs), (lk + log|Gs|, sign) for embed_grads
+//   tail (side stream, concurrent with embed_grads)
+//       gemm x 2         U = Psi2 Kinv,  T2 = Kinv U
+//       assemble_gk      dF/dKmm, <dF/dKmm, Kmm>, tr(Kinv Psi2)
+//       grad_alpha / grad_Z   multi-CTA contractions (one warp per element of grad_Z)
+//       final            fixed-order sums of the partials, bound, gradients of sf2 / alpha / beta
 //
+// Round 1 ran everything on the context's stream with a single-CTA O(M^2 Q) tail: 3.5 ms at M = 500, of
+// which the tail 2 ms and the four-CTA panel kernel 0.26 ms (B200, c4).
 // Same arithmetic as the single-CTA kernel (block sweep == sequential sweep of the same
 // pivots), same error behaviour (non-positive pivot -> GPARML_ERR_NOT_PD).
 // Reference lines replaced: see global_step.cu.
@@ -83,29 +91,29 @@ __global__ void __launch_bounds__(1024) gsl_pivot_kernel(const double *__restric
     if (r < nb && c < nb) pinv_out[r * GSL_NB + c] = -e;
 }
 
-// panel: Old[i][c] = A[i][k0 + c],  T[i][c] = sum_c' Old[i][c'] Pinv[c'][c]
-__global__ void __launch_bounds__(128) gsl_panel_kernel(const double *__restrict__ A, int M, int k0, int nb,
+// panel: Old[i][c] = A[i][k0 + c],  T[i][c] = sum_c' Old[i][c'] Pinv[c'][c].  One warp per row (lane = column c),
+// 8 rows per CTA: ceil(M / 8) CTAs instead of the ceil(M / 128) of the thread-per-row version (4 CTAs at M = 500).
+__global__ void __launch_bounds__(256) gsl_panel_kernel(const double *__restrict__ A, int M, int k0, int nb,
                                                         const double *__restrict__ pinv, double *__restrict__ T,
                                                         double *__restrict__ Old, const int *status)
 {
     __shared__ double ps[GSL_NB * GSL_NB];
+    __shared__ double as[8][GSL_NB];
     if (*status) return;
-    for (int idx = threadIdx.x; idx < GSL_NB * GSL_NB; idx += 128) ps[idx] = pinv[idx];
+    for (int idx = threadIdx.x; idx < GSL_NB * GSL_NB; idx += 256) ps[idx] = pinv[idx];
+    const int r = threadIdx.x >> 5, c = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + r;
+    const double a = (i < M && c < nb) ? A[(size_t)i * M + k0 + c] : 0.0;
+    as[r][c] = a;
     __syncthreads();
-    const int i = blockIdx.x * 128 + threadIdx.x;
     if (i >= M) return;
-    double a[GSL_NB];
+    Old[(size_t)i * GSL_NB + c] = a;
+    double s = 0.0;
+    if (c < nb) {
 #pragma unroll
-    for (int c = 0; c < GSL_NB; ++c) a[c] = (c < nb) ? A[(size_t)i * M + k0 + c] : 0.0;
-#pragma unroll
-    for (int c = 0; c < GSL_NB; ++c) Old[(size_t)i * GSL_NB + c] = a[c];
-    for (int c = 0; c < nb; ++c) {
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < GSL_NB; ++k) s = fma(a[k], ps[k * GSL_NB + c], s);
-        T[(size_t)i * GSL_NB + c] = s;
+        for (int k = 0; k < GSL_NB; ++k) s = fma(as[r][k], ps[k * GSL_NB + c], s);
     }
-    for (int c = nb; c < GSL_NB; ++c) T[(size_t)i * GSL_NB + c] = 0.0;
+    T[(size_t)i * GSL_NB + c] = s;
 }
 
 // rank-NB update of the whole matrix, 64 x 64 tile per CTA, 4 x 4 outputs per thread
@@ -203,66 +211,183 @@ __global__ void __launch_bounds__(256) gsl_gemm_kernel(const double *__restrict_
         }
 }
 
-// dF/dKmm, dF/dPsi2 (partial_terms.py:102-131), G1 = beta^2 C, and per-CTA partial sums of
-// the scalar contractions: part[b] = (tr(A^-1 Psi2), tr(C^T Psi2 C), <GK,Kmm>, <G2,Psi2>, tr(Kinv Psi2), <Psi1Y, C>)
-__global__ void __launch_bounds__(256) gsl_assemble_kernel(GsParams p, const double *__restrict__ Kinv, const double *__restrict__ U,
-                                                           const double *__restrict__ T2, double *__restrict__ part)
+// ---- head --------------------------------------------------------------------------------------
+// dF/dPsi1Y = beta^2 C, dF/dPsi2 = 1/2 beta D (Kinv - A^-1) - 1/2 beta^3 C C^T (partial_terms.py:115-131); E = C C^T is
+// kept (in the dF/dKmm buffer) for the tail.  part[b] = (tr(A^-1 Psi2), tr(C^T Psi2 C), <G2, Psi2>, <Psi1Y, C>)
+__global__ void __launch_bounds__(256) gsl_head_finish_kernel(GsParams p, const double *__restrict__ Kinv, double *__restrict__ part)
 {
     __shared__ double sh[33];
     const int M = p.M, D = p.D;
     const size_t MM = (size_t)M * M;
     const double beta = p.glob->beta, hD = 0.5 * (double)D;
-    double s[6] = {0, 0, 0, 0, 0, 0};
+    double s[4] = {0, 0, 0, 0};
     if (*p.status == 0) {
         for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < MM; idx += (size_t)gridDim.x * blockDim.x) {
-            const int i = (int)(idx / M), j = (int)(idx % M);
+            const int i = (int)(idx / M), j = (int)(idx - (size_t)i * M);
             double e = 0.0;
             for (int d = 0; d < D; ++d) e = fma(p.c_mat[i * D + d], p.c_mat[j * D + d], e);
-            const double ai = p.a_inv[idx], wi = Kinv[idx], ps = p.psi2_full[idx], t = T2[idx];
-            const double gk = hD * wi - hD * ai - hD * beta * t - 0.5 * beta * beta * e;
+            const double ai = p.a_inv[idx], wi = Kinv[idx], ps = p.psi2_full[idx];
             const double g2 = hD * beta * (wi - ai) - 0.5 * beta * beta * beta * e;
-            p.g_k[idx] = gk;
+            p.g_k[idx] = e;                       // C C^T, turned into dF/dKmm by the tail
             p.g_2[idx] = g2;
             s[0] = fma(ai, ps, s[0]);
             s[1] = fma(ps, e, s[1]);
-            s[2] = fma(gk, p.kmm[idx], s[2]);
-            s[3] = fma(g2, ps, s[3]);
-            if (i == j) s[4] += U[idx];
+            s[2] = fma(g2, ps, s[2]);
         }
         const double *P1Y = p.stats + p.off_p1y;
         for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (size_t)M * D; idx += (size_t)gridDim.x * blockDim.x) {
             const double c = p.c_mat[idx];
             p.g_1[idx] = beta * beta * c;
-            s[5] = fma(P1Y[idx], c, s[5]);
+            s[3] = fma(P1Y[idx], c, s[3]);
         }
     }
-    for (int k = 0; k < 6; ++k) {
+    for (int k = 0; k < 4; ++k) {
         const double v = gp_block_sum(s[k], sh);
-        if (threadIdx.x == 0) part[(size_t)blockIdx.x * 6 + k] = v;
+        if (threadIdx.x == 0) part[(size_t)blockIdx.x * 4 + k] = v;
     }
 }
 
-// one CTA: finish the scalars (fixed-order sums) and run the shared tail
-__global__ void __launch_bounds__(GS_THREADS, 1) gsl_tail_kernel(GsParams p, const double *__restrict__ part, int nparts,
-                                                                 const double *__restrict__ pivK, const double *__restrict__ pivA)
+// pair tables for embed_grads from dF/dPsi2 (same entries as gs_pair_tables, any number of CTAs)
+__global__ void __launch_bounds__(256) gsl_pair_tables_kernel(GsParams p)
+{
+    if (*p.status) return;
+    const int M = p.M;
+    const size_t MM = (size_t)M * M;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < MM; idx += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / M), j = (int)(idx - (size_t)i * M);
+        if (j < i) continue;
+        const int64_t pp = gp_pair_index(M, i, j);
+        const double gs = (i == j) ? p.g_2[idx] : (p.g_2[idx] + p.g_2[(size_t)j * M + i]);
+        p.pair_g[pp] = make_double2(p.pair_lk[pp], gs);
+        const double lg = log(fabs(gs));
+        p.pair_h[pp] = make_double2(p.pair_lk[pp] + (lg > -700.0 ? lg : -700.0), gs < 0.0 ? -1.0 : 1.0);
+    }
+}
+
+// ---- tail --------------------------------------------------------------------------------------
+// dF/dKmm = 1/2 D Kinv - 1/2 D A^-1 - 1/2 beta D Kinv Psi2 Kinv - 1/2 beta^2 C C^T (partial_terms.py:102-113);
+// part[b] = (<dF/dKmm, Kmm>, tr(Kinv Psi2))
+__global__ void __launch_bounds__(256) gsl_assemble_gk_kernel(GsParams p, const double *__restrict__ Kinv, const double *__restrict__ U,
+                                                              const double *__restrict__ T2, double *__restrict__ part)
+{
+    __shared__ double sh[33];
+    const int M = p.M;
+    const size_t MM = (size_t)M * M;
+    const double beta = p.glob->beta, hD = 0.5 * (double)p.D;
+    double s[2] = {0, 0};
+    if (*p.status == 0) {
+        for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < MM; idx += (size_t)gridDim.x * blockDim.x) {
+            const int i = (int)(idx / M), j = (int)(idx - (size_t)i * M);
+            const double e = p.g_k[idx];          // C C^T from the head
+            const double gk = hD * Kinv[idx] - hD * p.a_inv[idx] - hD * beta * T2[idx] - 0.5 * beta * beta * e;
+            p.g_k[idx] = gk;
+            s[0] = fma(gk, p.kmm[idx], s[0]);
+            if (i == j) s[1] += U[idx];
+        }
+    }
+    for (int k = 0; k < 2; ++k) {
+        const double v = gp_block_sum(s[k], sh);
+        if (threadIdx.x == 0) part[(size_t)blockIdx.x * 2 + k] = v;
+    }
+}
+
+// grad_alpha (partial_terms.py:247-254, 286-299): per-CTA partial sums part[b][q]
+__global__ void __launch_bounds__(256) gsl_grad_alpha_kernel(GsParams p, double *__restrict__ part)
+{
+    __shared__ double sh[33];
+    const int M = p.M, Q = p.Q, D = p.D;
+    const size_t MM = (size_t)M * M;
+    double sq[GP_MAX_Q], ia2[GP_MAX_Q];
+#pragma unroll
+    for (int q = 0; q < GP_MAX_Q; ++q) {
+        sq[q] = 0.0;
+        const double al = q < Q ? p.glob->alpha[q] : 1.0;
+        ia2[q] = 1.0 / (al * al);
+    }
+    if (*p.status == 0) {
+        for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < MM; idx += (size_t)gridDim.x * blockDim.x) {
+            const int i = (int)(idx / M), j = (int)(idx - (size_t)i * M);
+            const int64_t pp = pidx(M, i, j);
+            const double gk = p.g_k[idx], g2 = p.g_2[idx], km = p.kmm[idx], ps = p.psi2_full[idx];
+#pragma unroll
+            for (int q = 0; q < GP_MAX_Q; ++q) {
+                if (q < Q) {
+                    const double dz = p.Z[i * Q + q] - p.Z[j * Q + q];
+                    const double ta = p.stats[p.off_ta + (int64_t)q * p.P + pp];
+                    sq[q] = fma(gk, -0.5 * km * dz * dz, sq[q]);
+                    sq[q] = fma(g2, -0.25 * dz * dz * ps - ta * ia2[q], sq[q]);
+                }
+            }
+        }
+        for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (size_t)M * D; idx += (size_t)gridDim.x * blockDim.x) {
+            const double g1 = p.g_1[idx];
+#pragma unroll
+            for (int q = 0; q < GP_MAX_Q; ++q)
+                if (q < Q) sq[q] = fma(g1, p.stats[p.off_d1a + (int64_t)q * M * D + idx], sq[q]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < GP_MAX_Q; ++q) {
+        if (q < Q) {
+            const double v = gp_block_sum(sq[q], sh);
+            if (threadIdx.x == 0) part[(size_t)blockIdx.x * GP_MAX_Q + q] = v;
+        }
+    }
+}
+
+// grad_Z (partial_terms.py:146-160, 207-240): one warp per element (j, k), lanes over m', fixed-order shuffle tree
+__global__ void __launch_bounds__(256) gsl_grad_z_kernel(GsParams p)
+{
+    if (*p.status) return;
+    const int M = p.M, Q = p.Q, D = p.D;
+    const int lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (idx >= M * Q) return;
+    const int j = idx / Q, k = idx - j * Q;
+    const double al = p.glob->alpha[k], zjk = p.Z[idx];
+    const double *TZk = p.stats + p.off_tz + (int64_t)k * p.P;
+    double s = 0.0;
+    for (int m = lane; m < M; m += 32) {
+        const double dz = zjk - p.Z[m * Q + k];
+        const size_t jm = (size_t)j * M + m, mj = (size_t)m * M + j;
+        s = fma(p.g_k[jm] + p.g_k[mj], -al * dz * p.kmm[jm], s);
+        s = fma(2.0 * p.g_2[jm], -0.5 * al * dz * p.psi2_full[jm] + TZk[pidx(M, j, m)], s);
+    }
+    const double *D1Z = p.stats + p.off_d1z + (int64_t)idx * D;
+    for (int d = lane; d < D; d += 32) s = fma(p.g_1[j * D + d], D1Z[d], s);
+    s = gp_warp_sum(s);
+    if (lane == 0) p.out[1 + idx] = s;
+}
+
+// one CTA: fixed-order sums of all partials, log-determinants, then the bound and the gradients of sf2 / alpha / beta
+__global__ void __launch_bounds__(256) gsl_final_kernel(GsParams p, const double *__restrict__ part_h, const double *__restrict__ part_t,
+                                                        const double *__restrict__ part_a, int nparts, const double *__restrict__ pivK,
+                                                        const double *__restrict__ pivA)
 {
     __shared__ double red[33];
-    __shared__ double qred[32 * GP_MAX_Q];
-    __shared__ double ia2[GP_MAX_Q];
-    if (*p.status) return;
-    const int tid = threadIdx.x, M = p.M;
-    double s[6];
-    for (int k = 0; k < 6; ++k) {
+    if (*p.status & 3) return;
+    const int tid = threadIdx.x, M = p.M, Q = p.Q;
+    double h[4], t[2];
+    for (int k = 0; k < 4; ++k) {
         double v = 0.0;
-        for (int b = tid; b < nparts; b += GS_THREADS) v += part[(size_t)b * 6 + k];
-        s[k] = gp_block_sum(v, red);
+        for (int b = tid; b < nparts; b += 256) v += part_h[(size_t)b * 4 + k];
+        h[k] = gp_block_sum(v, red);
+    }
+    for (int k = 0; k < 2; ++k) {
+        double v = 0.0;
+        for (int b = tid; b < nparts; b += 256) v += part_t[(size_t)b * 2 + k];
+        t[k] = gp_block_sum(v, red);
     }
     double v = 0.0, w = 0.0;
-    for (int i = tid; i < M; i += GS_THREADS) { v += log(pivK[i]); w += log(pivA[i]); }
+    for (int i = tid; i < M; i += 256) { v += log(pivK[i]); w += log(pivA[i]); }
     const double ldK = gp_block_sum(v, red), ldA = gp_block_sum(w, red);
-    __syncthreads();
-    gs_tail(p, p.g_k, p.g_2, p.psi2_full, ldK, ldA, s[5], s[4], s[0], s[1], s[2], s[3], qred, ia2);
-    gs_pair_tables(p, p.g_2);
+    for (int q = 0; q < Q; ++q) {
+        double a = 0.0;
+        for (int b = tid; b < nparts; b += 256) a += part_a[(size_t)b * GP_MAX_Q + q];
+        a = gp_block_sum(a, red);
+        if (tid == 0) p.out[1 + M * Q + 1 + q] = a;
+    }
+    if (tid == 0) gs_tail_scalars(p, ldK, ldA, h[3], t[1], h[0], h[1], t[0], h[2]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -274,7 +399,7 @@ static int block_sweep(gparml_ctx *c, double *X, double *pinv, double *T, double
         const int nb = (M - k0 < GSL_NB) ? (M - k0) : GSL_NB;
         gsl_pivot_kernel<<<1, 1024, 0, c->stream>>>(X, M, k0, nb, pinv, piv, c->d_status, fail_bit);
         GP_LAUNCH_CHECK(c);
-        gsl_panel_kernel<<<(M + 127) / 128, 128, 0, c->stream>>>(X, M, k0, nb, pinv, T, Old, c->d_status);
+        gsl_panel_kernel<<<(M + 7) / 8, 256, 0, c->stream>>>(X, M, k0, nb, pinv, T, Old, c->d_status);
         GP_LAUNCH_CHECK(c);
         gsl_update_kernel<<<dim3(tiles, tiles), 256, 0, c->stream>>>(X, M, k0, nb, pinv, T, Old, c->d_status);
         GP_LAUNCH_CHECK(c);
@@ -290,6 +415,7 @@ static int gemm(gparml_ctx *c, const double *A, int lda, const double *B, int ld
     return GPARML_OK;
 }
 
+// phase 0: whole master step on the context's stream; 1: head only; 2: tail only (p.phase)
 int gp_launch_global_step_large(gparml_ctx *c, GsParams &p)
 {
     const int M = c->M, D = c->D;
@@ -303,38 +429,51 @@ int gp_launch_global_step_large(gparml_ctx *c, GsParams &p)
     double *Old = T + (size_t)M * GSL_NB;                         // (M, NB)
     double *pivK = Old + (size_t)M * GSL_NB;                      // (M)
     double *pivA = pivK + M;                                      // (M)
-    double *part = pivA + M;                                      // (nparts, 6)
     const int nparts = c->sm_count * 2;
+    double *part_h = pivA + M;                                    // (nparts, 4)
+    double *part_t = part_h + (size_t)nparts * 4;                 // (nparts, 2)
+    double *part_a = part_t + (size_t)nparts * 2;                 // (nparts, GP_MAX_Q)
 
-    // two launches like the single-CTA kernel: kmm_only = 1 (from set_globals, side stream): Kmm,
-    // Kmm^-1 (W and kmm_inv) and its pivots; kmm_only = 0: everything that needs the statistics.
-    // The second launch re-runs the cheap build kernel only to expand Psi2 (it rewrites identical Kmm).
-    gsl_build_kernel<<<eb, 256, 0, c->stream>>>(p, X);
-    GP_LAUNCH_CHECK(c);
     if (p.kmm_only) {
+        // from set_globals on the side stream: Kmm, Kmm^-1 (W and kmm_inv) and its pivots
+        gsl_build_kernel<<<eb, 256, 0, c->stream>>>(p, X);
+        GP_LAUNCH_CHECK(c);
         GP_TRY(block_sweep(c, X, pinv, T, Old, pivK, 1));
         gsl_negate_kernel<<<eb, 256, 0, c->stream>>>(X, MM, W, c->kmm_inv);
         GP_LAUNCH_CHECK(c);
         return GPARML_OK;
     }
-
-    gsl_form_a_kernel<<<eb, 256, 0, c->stream>>>(p, X);
-    GP_LAUNCH_CHECK(c);
-    GP_TRY(block_sweep(c, X, pinv, T, Old, pivA, 2));
-    gsl_negate_kernel<<<eb, 256, 0, c->stream>>>(X, MM, c->a_inv, nullptr);
-    GP_LAUNCH_CHECK(c);
-
-    GP_TRY(gemm(c, c->a_inv, M, c->stats + c->L.off_p1y, D, c->c_mat, D, M, D, M, 1.0));      // C = A^-1 Psi1Y
-    GP_TRY(gemm(c, c->psi2_full, M, W, M, X, M, M, M, M, 1.0));                                 // U = Psi2 Kinv
-    GP_TRY(gemm(c, W, M, X, M, T2, M, M, M, M, 1.0));                                           // T2 = Kinv U
-    gsl_assemble_kernel<<<nparts, 256, 0, c->stream>>>(p, W, X, T2, part);
-    GP_LAUNCH_CHECK(c);
-    gsl_tail_kernel<<<1, GS_THREADS, 0, c->stream>>>(p, part, nparts, pivK, pivA);
-    GP_LAUNCH_CHECK(c);
+    if (p.phase != 2) {
+        // the build kernel is re-run only to expand Psi2 (it rewrites identical Kmm)
+        gsl_build_kernel<<<eb, 256, 0, c->stream>>>(p, X);
+        GP_LAUNCH_CHECK(c);
+        gsl_form_a_kernel<<<eb, 256, 0, c->stream>>>(p, X);
+        GP_LAUNCH_CHECK(c);
+        GP_TRY(block_sweep(c, X, pinv, T, Old, pivA, 2));
+        gsl_negate_kernel<<<eb, 256, 0, c->stream>>>(X, MM, c->a_inv, nullptr);
+        GP_LAUNCH_CHECK(c);
+        GP_TRY(gemm(c, c->a_inv, M, c->stats + c->L.off_p1y, D, c->c_mat, D, M, D, M, 1.0));      // C = A^-1 Psi1Y
+        gsl_head_finish_kernel<<<nparts, 256, 0, c->stream>>>(p, W, part_h);
+        GP_LAUNCH_CHECK(c);
+        gsl_pair_tables_kernel<<<nparts, 256, 0, c->stream>>>(p);
+        GP_LAUNCH_CHECK(c);
+    }
+    if (p.phase != 1) {
+        GP_TRY(gemm(c, c->psi2_full, M, W, M, X, M, M, M, M, 1.0));                                 // U = Psi2 Kinv
+        GP_TRY(gemm(c, W, M, X, M, T2, M, M, M, M, 1.0));                                           // T2 = Kinv U
+        gsl_assemble_gk_kernel<<<nparts, 256, 0, c->stream>>>(p, W, X, T2, part_t);
+        GP_LAUNCH_CHECK(c);
+        gsl_grad_alpha_kernel<<<nparts, 256, 0, c->stream>>>(p, part_a);
+        GP_LAUNCH_CHECK(c);
+        gsl_grad_z_kernel<<<(M * c->Q + 7) / 8, 256, 0, c->stream>>>(p);
+        GP_LAUNCH_CHECK(c);
+        gsl_final_kernel<<<1, 256, 0, c->stream>>>(p, part_h, part_t, part_a, nparts, pivK, pivA);
+        GP_LAUNCH_CHECK(c);
+    }
     return GPARML_OK;
 }
 
 size_t gp_global_step_large_ws_doubles(int M, int sm_count)
 {
-    return (size_t)M * M + GSL_NB * GSL_NB + 2 * (size_t)M * GSL_NB + 2 * (size_t)M + (size_t)sm_count * 2 * 6 + 64;
+    return (size_t)M * M + GSL_NB * GSL_NB + 2 * (size_t)M * GSL_NB + 2 * (size_t)M + (size_t)sm_count * 2 * (6 + GP_MAX_Q) + 64;
 }

@@ -50,6 +50,31 @@ __device__ __forceinline__ void gs_pair_tables(const GsParams &p, const double *
     }
 }
 
+// The bound and the gradients of sf2 / beta (one thread): partial_terms.py:462-472, 322-333, 340-360.
+__device__ __forceinline__ void gs_tail_scalars(const GsParams &p, double ldK, double ldA, double tr1, double trKP, double s_ap,
+                                                double s_cpc, double s_kk, double s_22)
+{
+    const int M = p.M, Q = p.Q, D = p.D;
+    const double sf2 = p.glob->sf2, beta = p.glob->beta;
+    const int nz = M * Q;
+    double *grad = p.out + 1;
+    const double N = p.n_total;
+    const double yyt = p.stats[ST_YYT], psi0 = p.stats[ST_PSI0], kl = p.stats[ST_KL], ncount = p.stats[ST_NLOCAL];
+    // partial_terms.py:462-472
+    const double F = -0.5 * N * D * log(2.0 * 3.14159265358979323846) + 0.5 * D * N * log(beta) + 0.5 * D * ldK
+                     - 0.5 * D * ldA - 0.5 * beta * yyt - 0.5 * beta * D * psi0 + 0.5 * beta * D * trKP
+                     + 0.5 * beta * beta * tr1 - kl;
+    p.out[0] = F;
+    // partial_terms.py:322-333 with dF/dPsi0 = -1/2 beta D (:133-138)
+    grad[nz] = s_kk / sf2 + (-0.5 * beta * D) * ncount + beta * beta * tr1 / sf2 + 2.0 * s_22 / sf2;
+    // partial_terms.py:340-360
+    grad[nz + 1 + Q] = p.fixed_beta ? 0.0
+                                    : (0.5 * N * D / beta - 0.5 * D * s_ap - 0.5 * yyt - 0.5 * D * psi0 + 0.5 * D * trKP
+                                       + beta * tr1 - 0.5 * beta * beta * s_cpc);
+    double *extra = p.out + 1 + nz + Q + 2;
+    extra[0] = ldK; extra[1] = ldA; extra[2] = trKP; extra[3] = tr1;
+}
+
 // Bound + gradients from the finished partial derivatives.  GK = dF/dKmm, G2 = dF/dPsi2 (M x M,
 // shared or global memory), P2 = full Psi2.  Must be called by all GS_THREADS threads of ONE CTA.
 // qred: >= 32 * GP_MAX_Q doubles, ia2: >= GP_MAX_Q doubles of shared memory.
@@ -61,26 +86,9 @@ __device__ __forceinline__ void gs_tail(const GsParams &p, const double *X, cons
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const size_t MM = (size_t)M * M;
     const GlobalsDev g = *p.glob;
-    const double sf2 = g.sf2, beta = g.beta;
     const int nz = M * Q;
     double *grad = p.out + 1;
-    if (tid == 0) {
-        const double N = p.n_total;
-        const double yyt = p.stats[ST_YYT], psi0 = p.stats[ST_PSI0], kl = p.stats[ST_KL], ncount = p.stats[ST_NLOCAL];
-        // partial_terms.py:462-472
-        const double F = -0.5 * N * D * log(2.0 * 3.14159265358979323846) + 0.5 * D * N * log(beta) + 0.5 * D * ldK
-                         - 0.5 * D * ldA - 0.5 * beta * yyt - 0.5 * beta * D * psi0 + 0.5 * beta * D * trKP
-                         + 0.5 * beta * beta * tr1 - kl;
-        p.out[0] = F;
-        // partial_terms.py:322-333 with dF/dPsi0 = -1/2 beta D (:133-138)
-        grad[nz] = s_kk / sf2 + (-0.5 * beta * D) * ncount + beta * beta * tr1 / sf2 + 2.0 * s_22 / sf2;
-        // partial_terms.py:340-360
-        grad[nz + 1 + Q] = p.fixed_beta ? 0.0
-                                        : (0.5 * N * D / beta - 0.5 * D * s_ap - 0.5 * yyt - 0.5 * D * psi0 + 0.5 * D * trKP
-                                           + beta * tr1 - 0.5 * beta * beta * s_cpc);
-        double *extra = p.out + 1 + nz + Q + 2;
-        extra[0] = ldK; extra[1] = ldA; extra[2] = trKP; extra[3] = tr1;
-    }
+    if (tid == 0) gs_tail_scalars(p, ldK, ldA, tr1, trKP, s_ap, s_cpc, s_kk, s_22);
 
     // ---- grad_alpha (partial_terms.py:247-254, 286-299): one pass, Q partial sums per thread ----
     {

@@ -43,9 +43,17 @@ void gp_psi1_reduce(gparml_ctx *c, int splits)
         c->ws, splits, c->M, c->Q, c->D, c->d_glob, c->stats, c->L.off_p1y, c->L.off_d1z, c->L.off_d1a);
 }
 
-int gp_launch_psi1_stats_mma(gparml_ctx *c);
+int gp_launch_psi1_stats_mma(gparml_ctx *c);      // psi1_mma.cu: warp-autonomous tasks, row entries in registers (D <= 16: one column chunk)
+int gp_launch_psi1_stats_wide(gparml_ctx *c);     // psi1_wide.cu: stage 1 shared by the CTA through shared memory, all columns at once
 
-int gp_launch_psi1_stats(gparml_ctx *c) { return gp_launch_psi1_stats_mma(c); }
+#ifndef PSI1_WIDE_MIN_D
+#define PSI1_WIDE_MIN_D 17
+#endif
+
+int gp_launch_psi1_stats(gparml_ctx *c)
+{
+    return c->D >= PSI1_WIDE_MIN_D ? gp_launch_psi1_stats_wide(c) : gp_launch_psi1_stats_mma(c);
+}
 
 // ---------------------------------------------------------------------------
 // Psi1 matrix on demand (partial_terms.exp_K_mi, kernel_exp.py:51-82): (n, M)
