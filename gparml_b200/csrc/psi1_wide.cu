@@ -6,30 +6,34 @@
 // Why a second kernel.  In psi1_mma.cu a warp is an autonomous task that keeps its 1 + 2Q row entries in
 // registers and contracts them with at most 16 + 2 output columns; for wider D the columns are chunked and every
 // chunk re-evaluates Psi1 and the row entries (D = 50: five times, 69 ms at c4 on B200).  Here a CTA of 16 warps owns
-// 8 inducing points and a slice of the points and works bulk-synchronously in steps of TP = 64 points:
+// 8 inducing points and a slice of the points and works in steps of TP = 32 points on double-buffered tiles:
 //
-//   phase A  every warp evaluates Psi1 and the J = 1 + 2Q row entries of 4 points x 8 inducing points ONCE (lane =
-//            (inducing point, point)) and stores them in shared memory in A-fragment order;
-//   phase B  the warps turn into consumers of the whole tile: warp w owns the rows j = w % 7 + 7 r and every second of
-//            the ceil(D / 8) column tiles; per group of 4 points it loads its tiles' B fragments (Y) once, each row's A
+//   stage 1  warps 0..7 evaluate Psi1 and the J = 1 + 2Q row entries of 4 points x 8 inducing points of the NEXT step
+//            ONCE (lane = (inducing point, point)) and store them in shared memory in A-fragment order;
+//   MMAs     all warps consume the CURRENT step's tile: warp w owns every fourth row j and every fourth of the
+//            ceil(D / 8) column tiles (classes chosen so that every SM sub-partition gets the same number of MMAs); per group of 4 points it loads its tiles' B fragments (Y) once, each row's A
 //            fragment once, and issues rows x tiles FP64 tensor-core instructions (mma.sync m8n8k4, SASS DMMA) on
 //            accumulators that stay in registers for the whole slice.
 //
-// The next step's Y rows and point records arrive by cp.async during both phases.  Two designs were measured first
-// (c4, N = 100k, B200): one / two producer warps feeding 7 / 14 consumers through a double-buffered tile -- 10.5 / 8.1 ms,
-// tensor pipe 46 % active, barrier stalls dominant: the producers' dependent DFMA chains queue behind the consumers'
-// 16-cycle DMMAs on the SAME FP64 pipe and become the critical path; four producers: 6.7 ms.  Separating the phases
-// lets stage 1 run at its 8-cycle dependent latency on an otherwise idle pipe.
+// Y rows and point records of later steps arrive by cp.async; one block barrier per step.  Designs measured on the way
+// (c4, N = 100k, B200; tools/micro/dmma_feed.cu shows that 3 x 4 DMMAs per 4 points fed from shared memory run at the
+// full 36.7 TFLOP/s with 8 or 16 warps): dedicated producer warps (1 / 2 / 4) feeding 7 / 14 / 12 consumers: 10.5 / 8.1 /
+// 6.7 ms -- the producers' dependent DFMA chains queue behind the consumers' 16-cycle DMMAs on the SAME FP64 pipe and
+// become the critical path (tensor pipe 46 % active, barrier stalls dominant); separate stage-1 and MMA phases of 64
+// points: 6.9 ms (stage 1 + barrier 5.4k of 19.8k cycles per step with the pipe idle).
 //
 // Bound: FP64 pipe (DMMA shares it with DFMA, tools/micro/dmma_probe.cu).
 #include <math.h>
+#include <stdio.h>
 
 #include "common.cuh"
 #include "gp_exp.cuh"
 
 #define P1W_WARPS 16
-#define P1W_RC 7             // row classes: in phase B warp c < 14 owns the rows j = c % 7 + 7 r ...
-#define P1W_TC 2             // ... and the column tiles t = c / 7 + 2 u
+#define P1W_RC 4             // row classes: warp w = 4 a + b owns the rows j = a + 4 r ...
+#define P1W_TC 4             // ... and the column tiles t = ((b - a) mod 4) + 4 u: the four warps of an SM sub-partition
+                             // (same b) then hold one warp of every row class and of every tile class, which balances the
+                             // DMMA work over the sub-partitions (J = 21, 7 tiles: 37 / 37 / 37 / 36 row-tiles per 4 points)
 #define P1W_MAXNT 8          // column tiles per pass (D <= 64 per pass, more: blockIdx.y chunks)
 
 struct Psi1WParams {
@@ -54,18 +58,21 @@ __device__ __forceinline__ void p1w_dmma(double (&c)[2], double a, double b)
                  : "d"(a), "d"(b));
 }
 
-// NS1: warps that evaluate stage 1 (4 points each) -> TP = 4 NS1 points per step
-template <int Q, int NS1>
+#define P1W_NS1 8            // warps that also evaluate stage 1 (4 points each): TP = 32 points per step
+#define P1W_TP (4 * P1W_NS1)
+
+template <int Q>
 __global__ void __launch_bounds__(P1W_WARPS * 32, 1)
 psi1_wide_kernel(Psi1WParams p)
 {
     constexpr int J = 1 + 2 * Q, R = (3 * Q + 2) & ~1;
-    constexpr int TP = 4 * NS1;
+    constexpr int RS = R + 2;                                 // padded record stride: the 4 records a warp reads hit distinct banks
+    constexpr int TP = P1W_TP;
     constexpr int RPW = (J + P1W_RC - 1) / P1W_RC;            // rows per consumer warp
     constexpr int TPW = P1W_MAXNT / P1W_TC;                   // column tiles per consumer warp
-    constexpr int AT = J * TP * 8;                            // doubles of the A tile: [j][point][inducing point]
+    constexpr int AT = J * TP * 8;                            // doubles of one A tile: [j][point][inducing point]
     constexpr int NTH = P1W_WARPS * 32;
-    extern __shared__ __align__(16) double sm[];              // [AT] A tile, [2][TP][DP] Y tiles, [2][TP][R] record tiles
+    extern __shared__ __align__(16) double sm[];              // [2][AT] A tiles, [2][TP][DP] Y tiles, [2][TP][RS] record tiles
     __shared__ double exp_tab[GP_EXP_TAB];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gi = lane >> 2, kk = lane & 3;
@@ -73,7 +80,7 @@ psi1_wide_kernel(Psi1WParams p)
     const int d0 = blockIdx.y * (8 * P1W_MAXNT);
     const int dcols = (p.D - d0 < 8 * P1W_MAXNT) ? (p.D - d0) : 8 * P1W_MAXNT;     // columns of this pass
     const int nt = (dcols + 7) / 8, DP = 8 * nt;
-    double *As = sm, *Ys = sm + AT, *Rs = Ys + 2 * TP * DP;
+    double *As = sm, *Ys = sm + 2 * AT, *Rs = Ys + 2 * TP * DP;
     const int64_t n_lo = (int64_t)s * p.n_per_split;
     const int64_t n_hi = (n_lo + p.n_per_split < p.n) ? (n_lo + p.n_per_split) : p.n;
     const int nsteps = (int)((n_hi - n_lo + TP - 1) / TP);
@@ -86,27 +93,62 @@ psi1_wide_kernel(Psi1WParams p)
     const bool mvalid = m < p.M;
     double z[Q];
 #pragma unroll
-    for (int q = 0; q < Q; ++q) z[q] = (warp < NS1 && mvalid) ? p.Z[(size_t)m * Q + q] : 0.0;
+    for (int q = 0; q < Q; ++q) z[q] = (warp < P1W_NS1 && mvalid) ? p.Z[(size_t)m * Q + q] : 0.0;
+    const bool y16 = ((p.D | d0 | dcols) & 1) == 0;           // Y row pieces are 16-byte aligned
 
-    // Y rows (columns d0 .. d0 + dcols) and point records of `step` into buffer step & 1, asynchronously, by all threads
-    auto fetch = [&](int step) {
+    // asynchronous tile loads, one row (point) per warp and iteration: no integer division in the loops
+    auto fetch_y = [&](int step) {
+        if (step >= nsteps) return;
         const int64_t base = n_lo + (int64_t)step * TP;
         const int cnt = (int)((n_hi - base < TP) ? (n_hi - base) : TP);
-        double *yb = Ys + (size_t)(step & 1) * TP * DP, *rb = Rs + (size_t)(step & 1) * TP * R;
-        if (((p.D | d0 | dcols) & 1) == 0) {              // row pieces are 16-byte aligned
-            const int c2 = dcols / 2;
-            for (int idx = threadIdx.x; idx < cnt * c2; idx += NTH) {
-                const int pt = idx / c2, w = idx - pt * c2;
-                p1w_cp_async16(yb + pt * DP + 2 * w, p.Y + (base + pt) * p.D + d0 + 2 * w);
-            }
-        } else {
-            for (int idx = threadIdx.x; idx < cnt * dcols; idx += NTH) {
-                const int pt = idx / dcols, w = idx - pt * dcols;
-                p1w_cp_async8(yb + pt * DP + w, p.Y + (base + pt) * p.D + d0 + w);
+        double *yb = Ys + (size_t)(step & 1) * TP * DP;
+        for (int pt = warp; pt < cnt; pt += P1W_WARPS) {
+            const double *src = p.Y + (base + pt) * p.D + d0;
+            if (y16) {
+                for (int w = lane; 2 * w < dcols; w += 32) p1w_cp_async16(yb + pt * DP + 2 * w, src + 2 * w);
+            } else {
+                for (int w = lane; w < dcols; w += 32) p1w_cp_async8(yb + pt * DP + w, src + w);
             }
         }
-        for (int idx = threadIdx.x; idx < cnt * (R / 2); idx += NTH) p1w_cp_async16(rb + 2 * idx, p.rec1 + base * R + 2 * idx);
-        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto fetch_rec = [&](int step) {
+        if (step >= nsteps) return;
+        const int64_t base = n_lo + (int64_t)step * TP;
+        const int cnt = (int)((n_hi - base < TP) ? (n_hi - base) : TP);
+        double *rb = Rs + (size_t)(step & 1) * TP * RS;
+        for (int pt = warp; pt < cnt; pt += P1W_WARPS)
+            if (lane < R / 2) p1w_cp_async16(rb + pt * RS + 2 * lane, p.rec1 + (base + pt) * R + 2 * lane);      // R / 2 <= 25 pairs
+    };
+    // stage 1 of 4 points x 8 inducing points (this warp's share of `step`) -> A tile step & 1
+    auto stage1 = [&](int step) {
+        const int64_t base = n_lo + (int64_t)step * TP;
+        const int cnt = (int)((n_hi - base < TP) ? (n_hi - base) : TP);
+        const double *rt = Rs + (size_t)(step & 1) * TP * RS;
+        const int pl_raw = warp * 4 + kk;
+        const bool valid = mvalid && pl_raw < cnt;
+        const int pl = pl_raw < cnt ? pl_raw : cnt - 1;           // lanes past the end read a real record, weight 0
+        const double2 *rec = reinterpret_cast<const double2 *>(rt + pl * RS);
+        double ad[Q];
+        double es0 = 0.0, es1 = 0.0;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const double2 ma = rec[q];                // (mu_q, a_q)
+            const double d = ma.x - z[q];
+            ad[q] = ma.y * d;
+            if (q & 1) es1 = fma(ad[q], d, es1);
+            else es0 = fma(ad[q], d, es0);
+        }
+        const double e = fma(-0.5, es0 + es1, rt[pl * RS + 3 * Q]);
+        const double psi = valid ? gp_exp(e, exp_tab) : 0.0;
+        double *o = As + (size_t)(step & 1) * AT + pl_raw * 8 + gi;      // A-fragment order: [j][point][inducing point]
+        o[0] = psi;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) o[(size_t)(1 + q) * (TP * 8)] = psi * ad[q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const double2 v2 = rec[Q + (q >> 1)];     // (v1_2k, v1_2k+1)
+            o[(size_t)(1 + Q + q) * (TP * 8)] = psi * fma(ad[q], ad[q], (q & 1) ? v2.y : v2.x);
+        }
     };
 
     double C[RPW][TPW][2];
@@ -114,49 +156,37 @@ psi1_wide_kernel(Psi1WParams p)
     for (int r = 0; r < RPW; ++r)
 #pragma unroll
         for (int t = 0; t < TPW; ++t) { C[r][t][0] = 0.0; C[r][t][1] = 0.0; }
-    const int rc = warp % P1W_RC, tc = warp / P1W_RC;         // consumer's row class and tile class (warps 14, 15: none)
+    const int rc = warp >> 2, tc = ((warp & 3) - rc) & 3;     // consumer's row class and tile class
 
-    if (nsteps > 0) fetch(0);
+    // prologue: records of steps 0 and 1, Y of step 0; stage 1 of step 0
+    fetch_rec(0);
+    fetch_rec(1);
+    fetch_y(0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    if (warp < P1W_NS1 && nsteps > 0) stage1(0);
+    __syncthreads();
+#ifdef P1W_PROFILE
+    long long tF = 0, tA = 0, tB = 0, tW = 0, c0, c1, c2, c3, c4;
+#define P1W_CLK(x) x = clock64()
+#else
+#define P1W_CLK(x)
+#endif
     for (int st = 0; st < nsteps; ++st) {
-        const int64_t base = n_lo + (int64_t)st * TP;
-        const int cnt = (int)((n_hi - base < TP) ? (n_hi - base) : TP);
-        if (st + 1 < nsteps) fetch(st + 1);
-        // ---- phase A: stage 1 of 4 points x 8 inducing points per warp -> A tile ---------------------------------
-        if (warp < NS1) {
-            const double *rt = Rs + (size_t)(st & 1) * TP * R;
-            const int pl_raw = warp * 4 + kk;
-            const bool valid = mvalid && pl_raw < cnt;
-            const int pl = pl_raw < cnt ? pl_raw : cnt - 1;           // lanes past the end read a real record, weight 0
-            const double2 *rec = reinterpret_cast<const double2 *>(rt + pl * R);
-            double ad[Q];
-            double es0 = 0.0, es1 = 0.0;
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                const double2 ma = rec[q];                // (mu_q, a_q)
-                const double d = ma.x - z[q];
-                ad[q] = ma.y * d;
-                if (q & 1) es1 = fma(ad[q], d, es1);
-                else es0 = fma(ad[q], d, es0);
-            }
-            const double e = fma(-0.5, es0 + es1, rt[pl * R + 3 * Q]);
-            const double psi = valid ? gp_exp(e, exp_tab) : 0.0;
-            double *o = As + pl_raw * 8 + gi;             // A-fragment order: [j][point][inducing point]
-            o[0] = psi;
-#pragma unroll
-            for (int q = 0; q < Q; ++q) o[(size_t)(1 + q) * (TP * 8)] = psi * ad[q];
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                const double2 v2 = rec[Q + (q >> 1)];     // (v1_2k, v1_2k+1)
-                o[(size_t)(1 + Q + q) * (TP * 8)] = psi * fma(ad[q], ad[q], (q & 1) ? v2.y : v2.x);
-            }
-        }
-        __syncthreads();
-        // ---- phase B: rows x column tiles on the tensor-core instruction ------------------------------------------
-        if (warp < P1W_RC * P1W_TC) {
-            const double *yb = Ys + (size_t)(st & 1) * TP * DP;
-#pragma unroll 2
+        P1W_CLK(c0);
+        // copies for later steps (their buffers were last read before the barrier that ended step st - 1)
+        fetch_rec(st + 2);
+        fetch_y(st + 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        P1W_CLK(c1);
+        // stage 1 of the NEXT step (8 of the 16 warps) runs while the other warps already issue this step's MMAs: the FP64
+        // pipe always has tensor work queued, and no warp's stage-1 chain is longer than one group of 4 points
+        if (warp < P1W_NS1 && st + 1 < nsteps) stage1(st + 1);
+        P1W_CLK(c2);
+        {
+            const double *ab = As + (size_t)(st & 1) * AT, *yb = Ys + (size_t)(st & 1) * TP * DP;
+#pragma unroll 4
             for (int ks = 0; ks < TP / 4; ++ks) {
                 const int pt = 4 * ks + kk;
                 double b[TPW];
@@ -169,7 +199,7 @@ psi1_wide_kernel(Psi1WParams p)
                 for (int r = 0; r < RPW; ++r) {
                     const int j = rc + P1W_RC * r;
                     if (j < J) {                                                                         // warp-uniform
-                        const double a = As[(size_t)j * (TP * 8) + pt * 8 + gi];                          // A: (inducing point gi, point kk)
+                        const double a = ab[(size_t)j * (TP * 8) + pt * 8 + gi];                          // A: (inducing point gi, point kk)
 #pragma unroll
                         for (int u = 0; u < TPW; ++u)
                             if (tc + P1W_TC * u < nt) p1w_dmma(C[r][u], a, b[u]);
@@ -177,12 +207,22 @@ psi1_wide_kernel(Psi1WParams p)
                 }
             }
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");      // the next step's tiles (issued before phase A)
+        P1W_CLK(c3);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
+#ifdef P1W_PROFILE
+        c4 = clock64();
+        tF += c1 - c0; tA += c2 - c1; tB += c3 - c2; tW += c4 - c3;
+#endif
     }
+#ifdef P1W_PROFILE
+    if (blockIdx.x == 5 && blockIdx.y == 0 && lane == 0)
+        printf("warp %2d steps %d: per step fetch %lld  stage1 %lld  MMAs %lld  wait+barrier %lld\n", warp, nsteps, tF / nsteps, tA / nsteps,
+               tB / nsteps, tW / nsteps);
+#endif
 
     // C fragment: (inducing point gi, columns 2 kk and 2 kk + 1 of tile t)
-    if (warp < P1W_RC * P1W_TC && mvalid) {
+    if (mvalid) {
 #pragma unroll
         for (int r = 0; r < RPW; ++r) {
             const int j = rc + P1W_RC * r;
@@ -204,15 +244,13 @@ void gp_psi1_reduce(gparml_ctx *c, int splits);   // psi1.cu
 template <int Q>
 static int launch_wide_q(gparml_ctx *c, Psi1WParams &p)
 {
-    constexpr int NS1 = (Q <= 12) ? 16 : 8;               // 64-point steps while the A tile fits shared memory
-    constexpr int P1W_TP = 4 * NS1;
     constexpr int J = 1 + 2 * Q, AT = J * P1W_TP * 8;
     const int chunks = (c->D + 8 * P1W_MAXNT - 1) / (8 * P1W_MAXNT);
     const int dmax = c->D < 8 * P1W_MAXNT ? c->D : 8 * P1W_MAXNT;
     const int DP = 8 * ((dmax + 7) / 8);
     constexpr int R = (3 * Q + 2) & ~1;
-    const size_t smem = ((size_t)AT + (size_t)2 * P1W_TP * DP + (size_t)2 * P1W_TP * R) * sizeof(double);
-    GP_CUDA(cudaFuncSetAttribute(psi1_wide_kernel<Q, NS1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = ((size_t)2 * AT + (size_t)2 * P1W_TP * DP + (size_t)2 * P1W_TP * (R + 2)) * sizeof(double);
+    GP_CUDA(cudaFuncSetAttribute(psi1_wide_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // slices: G x S x chunks CTAs (one per SM at a time) in whole waves, >= 8 steps per slice, bounded workspace
     const int64_t slots = c->sm_count;
     const int64_t per_s = (int64_t)p.G * chunks;
@@ -237,7 +275,7 @@ static int launch_wide_q(gparml_ctx *c, Psi1WParams &p)
     GP_TRY(gp_ensure_ws(c, (size_t)p.S * c->M * J * c->D * sizeof(double)));
     p.partial = c->ws;
     dim3 grid((unsigned)(p.G * p.S), chunks);
-    psi1_wide_kernel<Q, NS1><<<grid, P1W_WARPS * 32, smem, c->stream>>>(p);
+    psi1_wide_kernel<Q><<<grid, P1W_WARPS * 32, smem, c->stream>>>(p);
     GP_LAUNCH_CHECK(c);
     gp_psi1_reduce(c, p.S);
     GP_LAUNCH_CHECK(c);

@@ -24,12 +24,7 @@ from gparml_b200.build import SOURCES as ALL  # noqa: E402
 # name -> {source: [defines]}
 VARIANTS = {
     "base": {},
-    "k5_pf2": {"embed_x.cu": ["EMBX_PF=2"]},
-    "k5_pf4": {"embed_x.cu": ["EMBX_PF=4"]},
-    "k5_pf6": {"embed_x.cu": ["EMBX_PF=6"]},
-    "k5_cp32": {"embed_x.cu": ["EMBX_CP=32"]},
-    "k5_cp32s3": {"embed_x.cu": ["EMBX_CP=32", "EMBX_STAGES=3"]},
-    "k5_h0": {"embed_x.cu": ["EMBX_HORNER=0"]},
+    "k1w_profile": {"psi1_wide.cu": ["P1W_PROFILE"]},
     # e.g. "p2_compiler": {"psi2.cu": ["PSI2_COMPILER_ORDER"]},  "emx_cp32": {"embed_x.cu": ["EMBX_CP=32", "EMBX_STAGES=3"]},
     #      "p1m_tp32": {"psi1_mma.cu": ["P1M_TP=32"]},  a leading "-" passes an nvcc flag instead of a -D macro
 }
