@@ -544,7 +544,7 @@ def run_config(env, cfg_name, steps, warmup, args, main_line):
         roofline["scg_local_state_hbm"] = {
             "bound": "hbm", "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src,
             "update_d": {"achieved": 3 * vec_bytes / (ms_axpy / 10 * 1e-3) / 1e9, "frac": 3 * vec_bytes / (ms_axpy / 10 * 1e-3) / 1e9 / hbm_peak,
-                         "algorithmic_bytes_per_launch": 3 * vec_bytes, "launch_ms": ms_axpy / 10, "traffic": dram("scg_update_kernel<2>")[0]},
+                         "algorithmic_bytes_per_launch": 3 * vec_bytes, "launch_ms": ms_axpy / 10, "traffic": dram("scg_update_kernel")[0]},
             "update_grad_old": {"achieved": 2 * vec_bytes / (ms_copy / 10 * 1e-3) / 1e9, "frac": 2 * vec_bytes / (ms_copy / 10 * 1e-3) / 1e9 / hbm_peak,
                                 "algorithmic_bytes_per_launch": 2 * vec_bytes, "launch_ms": ms_copy / 10}}
     out["roofline"] = roofline
@@ -652,7 +652,7 @@ def main():
     res = run_config(env, args.config, args.steps, args.warmup, args, main_line=True)
     others = []
     if args.config == "c3" and not args.fp32:
-        for name in [c for c in args.other_configs.split(",") if c]:
+        for name in [c.strip().strip('"\'') for c in args.other_configs.split(",") if c.strip().strip('"\'')]:
             o = run_config(env, name, args.other_steps, 3, args, main_line=False)
             r = o["roofline"]
             others.append({"config": o["config"], "value": o["value"], "unit": UNIT, "ms_per_step": o["ms_per_step"],
@@ -680,6 +680,7 @@ def main():
             cores = os.cpu_count() or 1
             pts = args.cpu_points or default_cpu_points(args.config, "baseline")
             cb = CpuArm(args.config, cores, pts)
+            cb.step()                      # warm-up: worker imports, first-touch (the reference arm warms up too)
             tm, tg = cb.step()
             cb.close()
             line["cpu_baseline"] = {"value": cb.evals_per_s(tm, tg), "unit": UNIT, "cores": cores, "kind": cb.kind,

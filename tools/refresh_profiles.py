@@ -32,12 +32,15 @@ def summaries(rep, tag, workload):
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     seen, traffic = set(), {}
+    # global_step_kernel is launched twice per evaluation (Kmm-only at set_globals, then the head): keep the longer one
+    gs = [r for r in rows[2:] if short(dict(zip(hdr, r))["Kernel Name"]) == "global_step_kernel"]
+    gs_keep = max(gs, key=lambda r: float(dict(zip(hdr, r))["gpu__time_duration.sum"])) if gs else None
     for r in rows[2:]:
         d = dict(zip(hdr, r))
         k = short(d["Kernel Name"])
-        if k == "global_step_kernel" and k not in seen and float(d.get("gpu__time_duration.sum", 0)) < 0.2:
-            pass                                   # the Kmm-only launch comes first; keep the later (full) one
-        if k in seen and k != "global_step_kernel":
+        if k == "global_step_kernel" and r is not gs_keep:
+            continue
+        if k in seen:
             continue
         seen.add(k)
         lines = ["# ncu --set full --clock-control none summary, %s" % workload, "",
@@ -79,7 +82,7 @@ def launches(csv_path, tag):
         e[1] += ns
     allns = sum(v[1] for v in tot.values())
     lines = ["# per-kernel share of the launch list profiles/launches_%s.csv" % tag,
-             "# (ncu --metrics gpu__time_duration.sum --clock-control none, bench.py --steps 2 --warmup 1: 3 evaluations + set-up;",
+             "# (ncu --metrics gpu__time_duration.sum --clock-control none, bench.py --steps 2 --warmup 3: 5 evaluations + set-up + probes;",
              "#  serialised, cold-cache per-launch times: compare SHARES with the live CUDA-event phases of bench.py)",
              "%-34s %8s %12s %7s" % ("kernel", "launches", "total ms", "share")]
     for k, (n, ns) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
@@ -94,7 +97,8 @@ def sass(tag):
     out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
     want = ["prep_points_kernel", "psi1_mma_kernelILi10ELi1ELi2E", "psi2_stats_kernelILi10E", "embed_psi2x_kernelILi10E",
             "embed_psi1_kernelILi10E", "global_step_kernel", "psi2_stats_f32_kernelILi10E", "embed_psi2_f32_kernelILi10E",
-            "gsl_gemm_kernel", "scg_reduce_kernel", "init_scatter_kernel"]
+            "gsl_gemm_kernel", "scg_reduce_kernel", "scg_update_kernel", "init_scatter_kernel", "psi1_wide_kernelILi10E",
+            "global_step_tail_kernel", "stats_allreduce_kernel", "gsl_panel_kernel", "gsl_grad_z_kernel"]
     mn = ["DFMA", "DADD", "DMUL", "DMMA", "DSETP", "FFMA", "MUFU", "UBLKCP", "SYNCS", "LDGSTS", "LDS", "STS", "LDG", "STG", "BAR", "SHFL", "IMAD"]
     lines = ["# SASS evidence (cuobjdump -sass gparml_b200/libgparml_b200.so, sm_100a), %s" % tag,
              "# per kernel: instruction counts of the mnemonics that matter for this path",
@@ -125,6 +129,8 @@ if __name__ == "__main__":
     rep, lcsv, tag = sys.argv[1], sys.argv[2], sys.argv[3]
     workload = "bench.py c3 N=1M, 1 GPU"
     tr = summaries(rep, tag, workload)
+    for extra in sys.argv[4:]:                       # further reports of the same workload (e.g. the K6 kernels)
+        tr.update(summaries(extra, tag, workload))
     for v in tr.values():
         v["n_local"] = 1000000
     json.dump({"c3": tr}, open(os.path.join(ROOT, "profiles", "ncu_traffic_%s.json" % tag), "w"), indent=1)
