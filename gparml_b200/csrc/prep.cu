@@ -82,9 +82,13 @@ struct PrepParams {
     int *status;
 };
 
+#ifndef PREP_TP
 #define PREP_TP 128        // points per tile
+#endif
 #define PREP_THREADS 256
+#ifndef PREP_MINB
 #define PREP_MINB 5        // resident CTAs per SM the register budget is capped for (48 registers)
+#endif
 
 // Two phases per tile of 128 points:
 //   A  thread per (point, q) element: reads mu / S_raw / direction, evaluates the per-element quantities and stores

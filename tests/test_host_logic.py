@@ -127,3 +127,58 @@ def test_bench_reference_arm_line_on_cpu():
     r1 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--config", "c1", "--gpus", "2"],
                         capture_output=True, text=True, timeout=60, env=env)
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+MR_WORKER = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, %(root)r)
+    import numpy as np
+    from gparml_b200 import b200_MapReduce as mr
+    work = %(work)r
+    opts = dict(input=work + "/input", embeddings=work + "/emb", statistics=work + "/stat", tmp=work, M=3, Q=2, D=2,
+                load=True, fixed_embeddings=False, init="PCA", b200_backend="gloo")
+    opts = mr.init(opts)                       # counts the rows of this rank's files, sums over ranks; no device needed with load
+    rank, world, tdev = mr.dist_info(opts)
+    assert world == 2 and tdev is None
+    assert opts["N"] == 5 + 7 + 4 and opts["b200_file_lengths"] == [5, 7, 4], (opts["N"], opts["b200_file_lengths"])
+    s = mr._Session()
+    mr._my_files(opts, s)                      # input file i belongs to rank i %% world
+    assert s.file_index == list(range(rank, 3, 2)) and s.n_files_total == 3, s.file_index
+    assert [os.path.basename(f) for f in s.files] == [["a.npy", "c.npy"], ["b_csv"]][rank]
+    got = mr._bcast({"draw": np.random.RandomState(rank).rand(), "rank": rank}, opts)      # rank 0's host-side decisions everywhere
+    assert got["rank"] == 0 and got["draw"] == np.random.RandomState(0).rand()
+    import torch.distributed as dist
+    dist.barrier(); dist.destroy_process_group()
+    print("rank %%d ok" %% rank)
+""")
+
+
+def test_map_reduce_backend_shards_files_over_ranks_gloo(tmp_path):
+    """Host logic of the one-process-per-GPU layout of b200_MapReduce on CPU (gloo, world_size 2): row counts summed
+    over ranks, input file i -> rank i % world, CSV and .npy shards, rank 0's random decisions broadcast."""
+    (tmp_path / "input").mkdir(); (tmp_path / "emb").mkdir(); (tmp_path / "stat").mkdir()
+    rng = np.random.default_rng(0)
+    np.save(str(tmp_path / "input" / "a.npy"), rng.standard_normal((5, 2)))
+    np.savetxt(str(tmp_path / "input" / "b_csv"), rng.standard_normal((7, 2)), delimiter=",")
+    np.save(str(tmp_path / "input" / "c.npy"), rng.standard_normal((4, 2)))
+    script = tmp_path / "worker.py"
+    script.write_text(MR_WORKER % {"root": ROOT, "work": str(tmp_path)})
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29534", str(script)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+
+
+def test_vectorised_transforms_match_scalar_ones():
+    """The replayed driver transforms the flat parameter vector in one numpy pass; same values as the reference's
+    per-element transform / transform_grad (supporting_functions.py:131-148)."""
+    from gparml_b200 import parallel_GPLVM as drv
+    bounds = [(None, None)] * 6 + [(0, None)] * 4
+    opts = {"flat_positive": np.array([b == (0, None) for b in bounds])}
+    x = np.random.default_rng(1).standard_normal(10) * 3
+    assert np.array_equal(drv._transform_vec(opts, x), np.array([T.transform(b, v) for b, v in zip(bounds, x)]))
+    assert np.array_equal(drv._transform_grad_vec(opts, x), np.array([T.transform_grad(b, v) for b, v in zip(bounds, x)], dtype=float))
+    x[7] = 40.0
+    with pytest.raises(AssertionError):
+        drv._transform_vec(opts, x)
