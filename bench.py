@@ -489,17 +489,17 @@ def run_config(env, cfg_name, steps, warmup, args, main_line):
                 "peak_nominal": 148 * 64 * 2 * 1.965e9 / 1e12,
                 "algorithmic_ops_per_launch": w_psi2, "launch_ms": med.get("psi2_stats"),
                 "ops_rule": "FP64-pipe lane-ops, FMA=1, exp=18: n_local * P * (6Q+20), TFLOP/s = 2*ops/t (SURVEY.md 8d)",
-                # what the kernel actually issues (table-driven exp = 9): the FP64-pipe busy fraction
-                "executed_ops_per_launch": n_loc * P * (6 * Q + 11),
-                "executed_frac": (n_loc * P * (6 * Q + 11) / t_psi2 / dfma) if t_psi2 > 0 and dfma > 0 else None}
+                # what the kernel actually issues (table-driven exp = 8 instructions): the FP64-pipe busy fraction
+                "executed_ops_per_launch": n_loc * P * (6 * Q + 10),
+                "executed_frac": (n_loc * P * (6 * Q + 10) / t_psi2 / dfma) if t_psi2 > 0 and dfma > 0 else None}
     if not fixed and med.get("embed_grads", 0) > 0:
         t_emb = med["embed_grads"] * 1e-3
-        x_emb = n_loc * (P * (4 * Q + 11) + M * (6 * Q + 12 + 2 * D))
+        x_emb = n_loc * (P * (4 * Q + 10) + M * (6 * Q + 11 + 2 * D))
         roofline["embed_grads"] = {"achieved": 2.0 * w_emb / t_emb / 1e12, "frac": (2.0 * w_emb / t_emb / 1e12) / peak,
                                    "launch_ms": med["embed_grads"], "algorithmic_ops_per_launch": w_emb,
                                    "executed_ops_per_launch": x_emb, "executed_frac": x_emb / t_emb / dfma if dfma > 0 else None,
                                    "note": "algorithmic count of SURVEY.md 8d (6Q+21 per point-pair); the expanded-basis kernel "
-                                           "issues 4Q+11, so frac can exceed the pipe-busy fraction (executed_frac)"}
+                                           "issues 4Q+10, so frac can exceed the pipe-busy fraction (executed_frac)"}
     if args.fp32:
         roofline["note"] = "fp32 map kernels selected: the FP64-pipe roofline above does not describe them"
     total_ops = algorithmic_ops(N, M, Q, D, fixed)
@@ -543,6 +543,8 @@ def run_config(env, cfg_name, steps, warmup, args, main_line):
         ms_copy, _, _ = env.timed(lambda: ctx.scg_update_grad_old(), 10)      # old = new: 1 read + 1 write
         roofline["scg_local_state_hbm"] = {
             "bound": "hbm", "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src,
+            # at several GPUs a rank's vectors fit the 126 MB L2: the pass is then L2- not HBM-bound and frac can exceed 1
+            "l2_resident": bool(3 * vec_bytes < 100e6),
             "update_d": {"achieved": 3 * vec_bytes / (ms_axpy / 10 * 1e-3) / 1e9, "frac": 3 * vec_bytes / (ms_axpy / 10 * 1e-3) / 1e9 / hbm_peak,
                          "algorithmic_bytes_per_launch": 3 * vec_bytes, "launch_ms": ms_axpy / 10, "traffic": dram("scg_update_kernel")[0]},
             "update_grad_old": {"achieved": 2 * vec_bytes / (ms_copy / 10 * 1e-3) / 1e9, "frac": 2 * vec_bytes / (ms_copy / 10 * 1e-3) / 1e9 / hbm_peak,

@@ -50,7 +50,7 @@ struct ExpState {
     double x, t, r, p, tab;
     int k;
 };
-#define GPX_SHIFT 6755399441055744.0
+#define GPX_SHIFT GP_EXP_SHIFT
 
 #ifndef EMBX_HORNER
 #define EMBX_HORNER 1          // exponent form: 0 = (zc, zc^2) dot product, 1 = Horner on zc, 2 = Horner + register prefetch
@@ -155,7 +155,7 @@ __device__ __forceinline__ void embx_step(const double2 *__restrict__ zn, const 
     }
     if (DO_E) {
 #pragma unroll
-        for (int v = 0; v < NP; ++v) es[v].t = fma(es[v].x, 46.16624130844683, GPX_SHIFT);
+        for (int v = 0; v < NP; ++v) es[v].t = fma(es[v].x, GP_EXP_SCALE, GPX_SHIFT);
     }
     EMBX_GROUP(0)
     if (DO_E) {
@@ -169,20 +169,16 @@ __device__ __forceinline__ void embx_step(const double2 *__restrict__ zn, const 
     if (DO_E) {
 #pragma unroll
         for (int v = 0; v < NP; ++v) {
-            es[v].r = fma(es[v].t, -0.02166084939249829, es[v].x);
+            es[v].r = fma(es[v].t, GP_EXP_NEG_STEP, es[v].x);
             es[v].tab = exp_tab[es[v].k & (GP_EXP_TAB - 1)];
         }
     }
     EMBX_GROUP(2)
     if (DO_E) {
 #pragma unroll
-        for (int v = 0; v < NP; ++v) es[v].p = fma(es[v].r, 1.0 / 120.0, 1.0 / 24.0);
+        for (int v = 0; v < NP; ++v) es[v].p = fma(es[v].r, 1.0 / 24.0, 1.0 / 6.0);
     }
     EMBX_GROUP(3)
-    if (DO_E) {
-#pragma unroll
-        for (int v = 0; v < NP; ++v) es[v].p = fma(es[v].p, es[v].r, 1.0 / 6.0);
-    }
     EMBX_GROUP(4)
     if (DO_E) {
 #pragma unroll
@@ -216,7 +212,7 @@ __device__ __forceinline__ void embx_step(const double2 *__restrict__ zn, const 
     if (DO_E) {
 #pragma unroll
         for (int v = 0; v < NP; ++v) {
-            int m = es[v].k >> 5;
+            int m = es[v].k >> GP_EXP_LOG2_TAB;
             m = m < -1021 ? -1021 : m;
             hn[v] = __hiloint2double((__double2hiint(es[v].p) + (m << 20)) ^ sg, __double2loint(es[v].p));
         }

@@ -1,13 +1,13 @@
 // Table-driven double-precision exp for the Psi kernels.
 //
-//   exp(x) = 2^m * 2^(j/32) * exp(r),   k = round(x * 32/ln2) = 32 m + j,   r = x - k ln2/32,
-//   |r| <= ln2/64 = 0.0108  ->  degree-5 Taylor polynomial (truncation 2.2e-15 relative).
+//   exp(x) = 2^m * 2^(j/64) * exp(r),   k = round(x * 64/ln2) = 64 m + j,   r = x - k ln2/64,
+//   |r| <= ln2/128 = 0.0054  ->  degree-4 Taylor polynomial (truncation r^5/120 <= 3.9e-14 relative).
 //
-// 9 FP64-pipe instructions (3 DFMA/DADD for the reduction, 5 DFMA polynomial, 1 DMUL by the
-// table entry) instead of the 18 of libdevice's exp(); the 2^m scaling and the table index are
-// integer-pipe work and the table read is one 8-byte shared-memory load.  Relative error
-// <= ~1e-14 for |x| < 100 (argument reduction with a single rounded ln2/32: |k| * 2e-18
-// absolute error in r), far inside the 1e-9 parity budget on the summed statistics.
+// 8 FP64-pipe instructions (3 DFMA/DADD for the reduction, 4 DFMA polynomial, 1 DMUL by the
+// table entry) instead of the 18 of libdevice's exp() (round 1: 32 entries, degree 5, 9 instructions); the 2^m
+// scaling and the table index are integer-pipe work and the table read is one 8-byte shared-memory load.
+// Relative error <= ~5e-14 for |x| < 100 (truncation, plus the argument reduction with a single rounded ln2/64:
+// |x| * 1.1e-16), far inside the 1e-9 parity budget on the summed statistics.
 //
 // Domain: any x <= 700 including -inf (Psi values are bounded by sf^2 resp. sf^4).  The argument is first
 // clamped to >= -745.25 by gp_exp_clamp -- an unsigned integer min on the high word (negative doubles order
@@ -18,16 +18,27 @@
 // to any sum.
 #pragma once
 
-#define GP_EXP_TAB 32
+#define GP_EXP_TAB 64
+#define GP_EXP_LOG2_TAB 6
+#define GP_EXP_SCALE 92.33248261689366            // 64 / ln2
+#define GP_EXP_NEG_STEP -0.010830424696249145     // -ln2 / 64
+#define GP_EXP_SHIFT 6755399441055744.0           // 1.5 * 2^52: the low word of fma(x, SCALE, SHIFT) is round(x SCALE)
 
-#define GP_EXP_TABLE_VALUES                                                                                                   \
-    1.0, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237, 1.0905077326652577, 1.1143867425958924,                  \
-        1.1387886347566916, 1.1637248587775775, 1.189207115002721, 1.215247359980469, 1.241857812073484,                     \
-        1.2690509571917332, 1.2968395546510096, 1.3252366431597413, 1.3542555469368927, 1.383909881963832,                   \
-        1.4142135623730951, 1.4451808069770467, 1.4768261459394993, 1.5091644275934228, 1.5422108254079407,                  \
-        1.5759808451078865, 1.6104903319492543, 1.6457554781539649, 1.681792830507429, 1.7186192981224779,                   \
-        1.7562521603732995, 1.7947090750031072, 1.8340080864093424, 1.8741676341103, 1.9152065613971474,                     \
-        1.9571441241754002
+// 2^(j/64), j = 0 .. 63, correctly rounded
+#define GP_EXP_TABLE_VALUES                                                                                          \
+    1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284, 1.0442737824274138,                          \
+    1.0556451783605572, 1.0671404006768237, 1.0787607977571199, 1.0905077326652577, 1.102382583307841,            \
+    1.1143867425958924, 1.1265216186082418, 1.1387886347566916, 1.1511892299529827, 1.1637248587775775,           \
+    1.1763969916502812, 1.189207115002721, 1.202156731452703, 1.215247359980469, 1.22848053610687,                \
+    1.241857812073484, 1.255380757024691, 1.2690509571917332, 1.2828700160787783, 1.2968395546510096,             \
+    1.3109612115247644, 1.3252366431597413, 1.339667524053303, 1.3542555469368927, 1.3690024229745905,            \
+    1.383909881963832, 1.3989796725383112, 1.4142135623730951, 1.42961333839197, 1.4451808069770467,              \
+    1.460917794180647, 1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384,            \
+    1.5422108254079407, 1.559004400237837, 1.5759808451078865, 1.593142151342267, 1.6104903319492543,             \
+    1.6280274218573478, 1.645755478153965, 1.6636765803267364, 1.681792830507429, 1.7001063537185235,             \
+    1.718619298122478, 1.7373338352737062, 1.7562521603732995, 1.7753764925265212, 1.7947090750031072,            \
+    1.8142521755003989, 1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,              \
+    1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951                                 
 
 static __constant__ double gp_exp_table_const[GP_EXP_TAB] = {GP_EXP_TABLE_VALUES};
 
@@ -53,23 +64,15 @@ __device__ __forceinline__ double gp_exp(double x, const double *tab_smem) { ret
 __device__ __forceinline__ double gp_exp_signed(double x, const double *tab_smem, int sign_word)
 {
     x = gp_exp_clamp(x);
-    const double SHIFT = 6755399441055744.0;                  // 1.5 * 2^52: the low word of t is round(v)
-    const double t = fma(x, 46.16624130844683, SHIFT);        // 32 / ln2
+    const double t = fma(x, GP_EXP_SCALE, GP_EXP_SHIFT);
     const int k = __double2loint(t);
-    const double kd = t - SHIFT;
-    const double r = fma(kd, -0.02166084939249829, x);        // ln2 / 32
-#ifdef GP_EXP_ESTRIN      // 6 instructions, dependency depth 3 (instead of 5 / 5)
-    const double r2 = r * r;
-    const double pa = fma(r, 1.0 / 6.0, 0.5), pb = fma(r, 1.0 / 120.0, 1.0 / 24.0), pd = 1.0 + r;
-    const double p = fma(r2, fma(r2, pb, pa), pd);
-#else
-    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-    p = fma(p, r, 1.0 / 6.0);
+    const double kd = t - GP_EXP_SHIFT;
+    const double r = fma(kd, GP_EXP_NEG_STEP, x);
+    double p = fma(r, 1.0 / 24.0, 1.0 / 6.0);
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-#endif
-    int m = k >> 5;
+    int m = k >> GP_EXP_LOG2_TAB;
     m = m < -1021 ? -1021 : m;
     const double s = tab_smem[k & (GP_EXP_TAB - 1)] * p;      // in [1, 2.03)
     return __hiloint2double((__double2hiint(s) + (m << 20)) ^ sign_word, __double2loint(s));

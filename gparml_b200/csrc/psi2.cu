@@ -27,7 +27,7 @@
 // launchers work on point ranges so that gparml_statistics can follow a row-range upload (capi.cu).
 //
 // Bound: FP64 pipe.  Algorithmic count 6Q + 20 per (point, pair) with exp = 18;
-// executed: 6Q + 11 with the table-driven exp of gp_exp.cuh (9 FP64 instructions).
+// executed: 6Q + 10 with the table-driven exp of gp_exp.cuh (8 FP64 instructions).
 #include <math.h>
 
 #include "common.cuh"
@@ -122,23 +122,22 @@ __device__ __forceinline__ void psi2_step(const double *__restrict__ rn, const d
     if (DO_E) {                                                 \
         _Pragma("unroll") for (int u = 0; u < 2; ++u) { stmt; } \
     }
-    PSI2_EXP(es[u].t = fma(es[u].x, 46.16624130844683, 6755399441055744.0))
+    PSI2_EXP(es[u].t = fma(es[u].x, GP_EXP_SCALE, GP_EXP_SHIFT))
     PSI2_CHUNK(0, 0)
-    PSI2_EXP(es[u].k = __double2loint(es[u].t); es[u].t = es[u].t - 6755399441055744.0)
+    PSI2_EXP(es[u].k = __double2loint(es[u].t); es[u].t = es[u].t - GP_EXP_SHIFT)
     PSI2_CHUNK(0, 1)
-    PSI2_EXP(es[u].r = fma(es[u].t, -0.02166084939249829, es[u].x); es[u].tab = exp_tab[es[u].k & (GP_EXP_TAB - 1)])
+    PSI2_EXP(es[u].r = fma(es[u].t, GP_EXP_NEG_STEP, es[u].x); es[u].tab = exp_tab[es[u].k & (GP_EXP_TAB - 1)])
     PSI2_CHUNK(1, 0)
-    PSI2_EXP(es[u].p = fma(es[u].r, 1.0 / 120.0, 1.0 / 24.0))
+    PSI2_EXP(es[u].p = fma(es[u].r, 1.0 / 24.0, 1.0 / 6.0))
     PSI2_CHUNK(1, 1)
-    PSI2_EXP(es[u].p = fma(es[u].p, es[u].r, 1.0 / 6.0))
-    PSI2_CHUNK(2, 0)
     PSI2_EXP(es[u].p = fma(es[u].p, es[u].r, 0.5))
+    PSI2_CHUNK(2, 0)
+    PSI2_EXP(es[u].p = fma(es[u].p, es[u].r, 1.0))
     PSI2_CHUNK(2, 1)
     PSI2_EXP(es[u].p = fma(es[u].p, es[u].r, 1.0))
     PSI2_CHUNK(3, 0)
-    PSI2_EXP(es[u].p = fma(es[u].p, es[u].r, 1.0))
-    PSI2_CHUNK(3, 1)
     PSI2_EXP(es[u].p = es[u].tab * es[u].p)
+    PSI2_CHUNK(3, 1)
     PSI2_CHUNK(4, 0)
     PSI2_CHUNK(4, 1)
     PSI2_CHUNK(5, 0)
@@ -152,7 +151,7 @@ __device__ __forceinline__ void psi2_step(const double *__restrict__ rn, const d
     if (DO_E) {
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            int m = es[u].k >> 5;
+            int m = es[u].k >> GP_EXP_LOG2_TAB;
             m = m < -1021 ? -1021 : m;
             psin[u] = __hiloint2double(__double2hiint(es[u].p) + (m << 20), __double2loint(es[u].p));
         }

@@ -268,6 +268,142 @@ __global__ void __launch_bounds__(GS_THREADS, 1) probe_la_kernel(const double *s
     if (threadIdx.x == 0) *cycles = t / reps;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Blocked version: pivots in blocks of 8.  Per block: (1) the owners publish the block's 8 columns, (2) ONE warp
+// inverts the 8 x 8 pivot block with shuffles (the only sequential part: 8 dependent reciprocals), (3) all threads
+// form T = A[:, K] P (one element each), (4) every thread applies the rank-8 update to its NS x NS elements and
+// repairs the block's rows / columns.  Three barriers per 8 pivots instead of eight.
+// smem: Cs[8][128] columns, Ts[8][128], Ps[8][8], flag.
+// ---------------------------------------------------------------------------------------------------------
+template <int NS>
+__device__ __forceinline__ bool sweep_blk(double *A, int M, double *Cs, double *Ts, double *Ps, int *flag, double *piv)
+{
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    double e[NS][NS];
+#pragma unroll
+    for (int a = 0; a < NS; ++a)
+#pragma unroll
+        for (int b = 0; b < NS; ++b) {
+            const int i = ty + 32 * a, j = tx + 32 * b;
+            e[a][b] = (i < M && j < M) ? A[(size_t)i * M + j] : 0.0;
+        }
+    if (tid == 0) *flag = 0;
+    for (int k0 = 0; k0 < M; k0 += 8) {
+        const int nb = (M - k0 < 8) ? (M - k0) : 8;
+        const int x0 = k0 & 31, kb = k0 >> 5;            // the block's columns: lanes x0 .. x0 + 7 of slot kb; rows: warps x0 .. x0 + 7, slot kb
+        const int cx = tx - x0, ry = ty - x0;            // this lane's column / this warp's row inside the block (valid if 0 <= . < nb)
+        const bool colK = cx >= 0 && cx < nb, rowK = ry >= 0 && ry < nb;
+        // (1) publish the columns (zero for the columns a partial last block does not have)
+        if (cx >= 0 && cx < 8) {
+#pragma unroll
+            for (int b = 0; b < NS; ++b)
+                if (b == kb) {
+#pragma unroll
+                    for (int a = 0; a < NS; ++a) Cs[cx * 128 + ty + 32 * a] = colK ? e[a][b] : 0.0;
+                }
+        }
+        __syncthreads();
+        // (2) warp 0: P = A_KK^-1 by an 8 x 8 sweep in registers; lane (r = lane / 8, c = lane % 8) holds rows r and r + 4 of column c
+        if (ty == 0) {
+            const int r = tx >> 3, c = tx & 7;
+            double v0 = (r < nb && c < nb) ? Cs[c * 128 + k0 + r] : ((r == c) ? 1.0 : 0.0);
+            double v1 = (r + 4 < nb && c < nb) ? Cs[c * 128 + k0 + r + 4] : ((r + 4 == c) ? 1.0 : 0.0);
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const double dk = __shfl_sync(0xffffffffu, (k < 4) ? v0 : v1, (k & 3) * 8 + k);
+                if (k < nb && (!(dk > 0.0) || !isfinite(dk))) ok = false;
+                if (k < nb && tx == 0) piv[k0 + k] = dk;
+                const double pinv = 1.0 / dk;
+                const double rowk = __shfl_sync(0xffffffffu, (k < 4) ? v0 : v1, (k & 3) * 8 + c);     // A[k][c]
+                const double c0 = __shfl_sync(0xffffffffu, v0, r * 8 + k);                           // A[r][k]
+                const double c1 = __shfl_sync(0xffffffffu, v1, r * 8 + k);                           // A[r + 4][k]
+                const double t0 = c0 * pinv, t1 = c1 * pinv;
+                double n0 = fma(-t0, rowk, v0), n1 = fma(-t1, rowk, v1);
+                if (c == k) { n0 = t0; n1 = t1; }
+                if (r == k) n0 = (c == k) ? -pinv : rowk * pinv;
+                if (r + 4 == k) n1 = (c == k) ? -pinv : rowk * pinv;
+                v0 = n0; v1 = n1;
+            }
+            Ps[r * 8 + c] = -v0;
+            Ps[(r + 4) * 8 + c] = -v1;
+            if (!ok && tx == 0) *flag = 1;
+        }
+        __syncthreads();
+        if (*flag) return false;                         // uniform
+        // (3) T[i][c] = sum_c' Cs[c'][i] P[c'][c]: thread t -> (c = t / 128, i = t % 128)
+        {
+            const int c = tid >> 7, i = tid & 127;
+            double s = 0.0;
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) s = fma(Cs[cc * 128 + i], Ps[cc * 8 + c], s);
+            Ts[c * 128 + i] = s;
+        }
+        __syncthreads();
+        // (4) rank-8 update, then the block's rows and columns
+#pragma unroll 2
+        for (int c = 0; c < 8; ++c) {
+            double ti[NS], tj[NS];
+#pragma unroll
+            for (int a = 0; a < NS; ++a) ti[a] = Ts[c * 128 + ty + 32 * a];
+#pragma unroll
+            for (int b = 0; b < NS; ++b) tj[b] = Cs[c * 128 + tx + 32 * b];
+#pragma unroll
+            for (int a = 0; a < NS; ++a)
+#pragma unroll
+                for (int b = 0; b < NS; ++b) e[a][b] = fma(-ti[a], tj[b], e[a][b]);
+        }
+        if (rowK) {                                       // rows of the block: A'[k0 + ry][j] = T[j][ry]
+#pragma unroll
+            for (int a = 0; a < NS; ++a)
+                if (a == kb) {
+#pragma unroll
+                    for (int b = 0; b < NS; ++b) e[a][b] = Ts[ry * 128 + tx + 32 * b];
+                }
+        }
+        if (colK) {                                       // columns of the block: A'[i][k0 + cx] = T[i][cx]; inside the block -P
+#pragma unroll
+            for (int b = 0; b < NS; ++b)
+                if (b == kb) {
+#pragma unroll
+                    for (int a = 0; a < NS; ++a) e[a][b] = (rowK && a == kb) ? -Ps[ry * 8 + cx] : Ts[cx * 128 + ty + 32 * a];
+                }
+        }
+        __syncthreads();                                 // Cs / Ts / Ps are rewritten by the next block
+    }
+#pragma unroll
+    for (int a = 0; a < NS; ++a)
+#pragma unroll
+        for (int b = 0; b < NS; ++b) {
+            const int i = ty + 32 * a, j = tx + 32 * b;
+            if (i < M && j < M) A[(size_t)i * M + j] = e[a][b];
+        }
+    __syncthreads();
+    return true;
+}
+
+template <int NS>
+__global__ void __launch_bounds__(GS_THREADS, 1) probe_blk_kernel(const double *src, double *dst, int M, int reps, long long *cycles, int *status)
+{
+    extern __shared__ __align__(16) double sm[];
+    __shared__ double Cs[8 * 128], Ts[8 * 128], Ps[64], piv[128];
+    __shared__ int flag;
+    double *A = sm;
+    long long t = 0;
+    for (int r = 0; r < reps; ++r) {
+        for (int idx = threadIdx.x; idx < M * M; idx += GS_THREADS) A[idx] = src[idx];
+        __syncthreads();
+        const long long t0 = clock64();
+        const bool ok = sweep_blk<NS>(A, M, Cs, Ts, Ps, &flag, piv);
+        t += clock64() - t0;
+        if (!ok && threadIdx.x == 0) *status = 1;
+        if (!ok) return;
+    }
+    for (int idx = threadIdx.x; idx < M * M; idx += GS_THREADS) dst[idx] = -A[idx];
+    if (threadIdx.x == 0) *cycles = t / reps;
+}
+
 template <int TY, int NA, int NB>
 __global__ void __launch_bounds__(GS_THREADS, 1) probe_kernel(const double *src, double *dst, int M, int reps, long long *cycles, int *status)
 {
@@ -309,6 +445,31 @@ static void run_la(int M, const std::vector<double> &A, const std::vector<double
     double err = 0.0, nrm = 0.0;
     for (size_t i = 0; i < out.size(); ++i) { err = fmax(err, fabs(out[i] - I[i])); nrm = fmax(nrm, fabs(I[i])); }
     printf("M=%3d LOOK-AHEAD slots %dx%d: %s status %d  %7lld cycles (%.0f per pivot, %.1f us)  max rel err %.2e\n", M, NB, NB,
+           cudaGetErrorString(e), st, cyc, (double)cyc / M, cyc / 1965.0, err / nrm);
+    cudaFree(dA); cudaFree(dO); cudaFree(dC); cudaFree(dS);
+}
+
+template <int NS>
+static void run_blk(int M, const std::vector<double> &A, const std::vector<double> &I)
+{
+    if (M > 32 * NS || M <= 32 * (NS - 1)) return;
+    std::vector<double> out((size_t)M * M);
+    double *dA, *dO;
+    long long *dC;
+    int *dS;
+    cudaMalloc(&dA, A.size() * 8); cudaMalloc(&dO, A.size() * 8); cudaMalloc(&dC, 8); cudaMalloc(&dS, 4);
+    cudaMemcpy(dA, A.data(), A.size() * 8, cudaMemcpyHostToDevice);
+    cudaMemset(dS, 0, 4);
+    const size_t smem = (size_t)M * M * 8;
+    cudaFuncSetAttribute(probe_blk_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    probe_blk_kernel<NS><<<1, GS_THREADS, smem>>>(dA, dO, M, 20, dC, dS);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long cyc = 0; int st = 0;
+    cudaMemcpy(&cyc, dC, 8, cudaMemcpyDeviceToHost); cudaMemcpy(&st, dS, 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(out.data(), dO, A.size() * 8, cudaMemcpyDeviceToHost);
+    double err = 0.0, nrm = 0.0;
+    for (size_t i = 0; i < out.size(); ++i) { err = fmax(err, fabs(out[i] - I[i])); nrm = fmax(nrm, fabs(I[i])); }
+    printf("M=%3d BLOCKED (8 pivots) slots %dx%d: %s status %d  %7lld cycles (%.0f per pivot, %.1f us)  max rel err %.2e\n", M, NS, NS,
            cudaGetErrorString(e), st, cyc, (double)cyc / M, cyc / 1965.0, err / nrm);
     cudaFree(dA); cudaFree(dO); cudaFree(dC); cudaFree(dS);
 }
@@ -367,6 +528,10 @@ int main(int argc, char **argv)
         run<32, 4, 4>(M, A, I);
         run<32, 2, 2>(M, A, I);
         run<32, 1, 1>(M, A, I);
+        run_blk<1>(M, A, I);
+        run_blk<2>(M, A, I);
+        run_blk<3>(M, A, I);
+        run_blk<4>(M, A, I);
         run_la<1>(M, A, I);
         run_la<2>(M, A, I);
         run_la<3>(M, A, I);
