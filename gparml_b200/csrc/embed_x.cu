@@ -52,6 +52,9 @@ struct ExpState {
 };
 #define GPX_SHIFT GP_EXP_SHIFT
 
+#ifndef EMBX_HORNER_DEPTH
+#define EMBX_HORNER_DEPTH 1    // software-pipeline depth of the Horner exponent (t leads e by this many latent dimensions)
+#endif
 #ifndef EMBX_HORNER
 #define EMBX_HORNER 1          // exponent form: 0 = (zc, zc^2) dot product, 1 = Horner on zc, 2 = Horner + register prefetch
 #endif
@@ -108,7 +111,30 @@ __device__ __forceinline__ void embx_step(const double2 *__restrict__ zn, const 
 #pragma unroll
         for (int k = 0; k < QP2; ++k) zr[k] = cn[k];
 #endif
-        double e[NP][2], t[NP], tn[NP];
+        double e[NP][2];
+#if EMBX_HORNER_DEPTH == 2
+        // t two latent dimensions ahead of e: 8 instructions between a t and the e that consumes it
+        double tq[3][NP];
+#pragma unroll
+        for (int v = 0; v < NP; ++v) {
+            e[v][0] = gn.x;
+            e[v][1] = kn[v];
+            tq[0][v] = fma(nW[v][0], zr[0].x, A[v][0]);
+            if (Q > 1) tq[1][v] = fma(nW[v][Q > 1 ? 1 : 0], zr[0].y, A[v][Q > 1 ? 1 : 0]);
+        }
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const double zq = (q & 1) ? zr[q >> 1].y : zr[q >> 1].x;
+            if (q + 2 < Q) {
+                const double zq2 = ((q + 2) & 1) ? zr[(q + 2) >> 1].y : zr[(q + 2) >> 1].x;
+#pragma unroll
+                for (int v = 0; v < NP; ++v) tq[(q + 2) % 3][v] = fma(nW[v][(q + 2) < Q ? (q + 2) : 0], zq2, A[v][(q + 2) < Q ? (q + 2) : 0]);
+            }
+#pragma unroll
+            for (int v = NP - 1; v >= 0; --v) e[v][q & 1] = fma(tq[q % 3][v], zq, e[v][q & 1]);
+        }
+#else
+        double t[NP], tn[NP];
 #pragma unroll
         for (int v = 0; v < NP; ++v) {
             e[v][0] = gn.x;
@@ -128,6 +154,7 @@ __device__ __forceinline__ void embx_step(const double2 *__restrict__ zn, const 
 #pragma unroll
             for (int v = 0; v < NP; ++v) t[v] = tn[v];
         }
+#endif
 #pragma unroll
         for (int v = 0; v < NP; ++v) es[v].x = gp_exp_clamp(e[v][0] + e[v][1]);
     }

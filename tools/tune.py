@@ -24,10 +24,8 @@ from gparml_b200.build import SOURCES as ALL  # noqa: E402
 # name -> {source: [defines]}
 VARIANTS = {
     "base": {},
-    "k0_tp64_b6": {"prep.cu": ["PREP_TP=64", "PREP_MINB=6"]},
-    "k0_tp64_b8": {"prep.cu": ["PREP_TP=64", "PREP_MINB=8"]},
-    "k0_tp64_b5": {"prep.cu": ["PREP_TP=64", "PREP_MINB=5"]},
-    "k0_tp128_b4": {"prep.cu": ["PREP_MINB=4"]},
+    "k5_depth2": {"embed_x.cu": ["EMBX_HORNER_DEPTH=2"]},
+    "k5_depth2_e4": {"embed_x.cu": ["EMBX_HORNER_DEPTH=2", "EMBX_E4"]},
     # e.g. "p2_compiler": {"psi2.cu": ["PSI2_COMPILER_ORDER"]},  "emx_cp32": {"embed_x.cu": ["EMBX_CP=32", "EMBX_STAGES=3"]},
     #      "p1m_tp32": {"psi1_mma.cu": ["P1M_TP=32"]},  a leading "-" passes an nvcc flag instead of a -D macro
 }
