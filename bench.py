@@ -596,13 +596,21 @@ def through_driver(env, cfg_name, g, rows, steps, warmup, step_size, F_raw):
         if world > 1:
             env.dist.barrier()
         name = "shard_%03d.npy" % rank
-        np.save(os.path.join(dirs["input"], name), rows["Y"])
-        np.save(os.path.join(dirs["embeddings"], name + ".embedding.npy"), rows["X_mu"])
-        np.save(os.path.join(dirs["embeddings"], name + ".variance.npy"), rows["X_S"])
-        if "d" in rows:
-            np.save(os.path.join(dirs["embeddings"], name + ".grad_d.npy"), rows["d"])
-        if world > 1:
-            env.dist.barrier()
+        ok, why = 1, ""
+        try:
+            np.save(os.path.join(dirs["input"], name), rows["Y"])
+            np.save(os.path.join(dirs["embeddings"], name + ".embedding.npy"), rows["X_mu"])
+            np.save(os.path.join(dirs["embeddings"], name + ".variance.npy"), rows["X_S"])
+            if "d" in rows:
+                np.save(os.path.join(dirs["embeddings"], name + ".grad_d.npy"), rows["d"])
+        except Exception as e:
+            ok, why = 0, repr(e)
+        if world > 1:           # all ranks go on, or none (a rank that failed alone would leave the others in a collective)
+            flag = env.torch.tensor([ok], dtype=env.torch.int32, device=env.dev)
+            env.dist.all_reduce(flag, op=env.dist.ReduceOp.MIN)
+            ok = int(flag.item())
+        if not ok:
+            raise RuntimeError("could not stage the shard files in %s: %s" % (work, why or "another rank failed"))
         # b200_stream='torch': the shard contexts work on torch's current stream, the one the CUDA events of
         # Env.timed are recorded on (on their own streams the last step's embeddings map would fall outside e0..e1)
         opts = drv.default_options(M=g["M"], Q=g["Q"], D=g["D"], load=True, fixed_embeddings=g["fixed_embeddings"],
