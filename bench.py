@@ -654,7 +654,7 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--other-configs", default="c5,c4,c2", help="comma-separated BASELINE configs measured after the main one "
-                                                                "('' = none); only with the default main config c3")
+                                                                "('' or 'none' = none); only with the default main config c3")
     ap.add_argument("--other-steps", type=int, default=3)
     ap.add_argument("--cpu-points", type=int, default=0, help="points per CPU worker in the baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -675,7 +675,8 @@ def main():
     res = run_config(env, args.config, args.steps, args.warmup, args, main_line=True)
     others = []
     if args.config == "c3" and not args.fp32:
-        for name in [c.strip().strip('"\'') for c in args.other_configs.split(",") if c.strip().strip('"\'')]:
+        names = [c.strip().strip('"\'') for c in args.other_configs.split(",")]
+        for name in [c for c in names if c and c.lower() != "none"]:
             o = run_config(env, name, args.other_steps, 3, args, main_line=False)
             r = o["roofline"]
             others.append({"config": o["config"], "value": o["value"], "unit": UNIT, "ms_per_step": o["ms_per_step"],
