@@ -135,14 +135,14 @@ extern "C" int gparml_create(gparml_ctx **out, int device, int M, int Q, int D, 
     A_(c->stats, (size_t)c->L.count);
     A_(c->red_ws, 4096);
     A_(c->d_yyt, 1100);
-    A_(c->d_status, 1);
+    A_(c->d_status, 2);
     A_(c->kmm, MM); A_(c->kmm_inv, MM); A_(c->a_inv, MM);
     A_(c->g_k, MM); A_(c->g_2, MM); A_(c->g_1, (size_t)M * D); A_(c->c_mat, (size_t)M * D);
     A_(c->scratch_x, MM); A_(c->scratch_w, MM); A_(c->psi2_full, MM);
     A_(c->glob_out, (size_t)M * Q + Q + 16);
 #undef A_
     if (cudaMemsetAsync(c->stats, 0, c->L.count * sizeof(double), c->stream) != cudaSuccess ||
-        cudaMemsetAsync(c->d_status, 0, sizeof(int), c->stream) != cudaSuccess) { gp_set_error("memset failed"); return fail(GPARML_ERR_CUDA); }
+        cudaMemsetAsync(c->d_status, 0, 2 * sizeof(int), c->stream) != cudaSuccess) { gp_set_error("memset failed"); return fail(GPARML_ERR_CUDA); }
     for (int i = 0; i < 8; ++i)
         if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { gp_set_error("event create failed"); return fail(GPARML_ERR_CUDA); }
     *out = c;
@@ -157,7 +157,7 @@ extern "C" int gparml_destroy(gparml_ctx *c)
     void *ptrs[] = {c->Y, c->x_mu, c->x_s, c->grad_d, c->grad_latest, c->grad_new, c->grad_old, c->rec1, c->rec2, c->s_pos, c->s_sig,
                     c->gx_mu, c->gx_s, c->psi1, c->Z, c->d_glob, c->pair_idx, c->pair_lk, c->pair_g, c->pair_zz, c->pair_zc, c->pair_h, c->stats, c->ws, c->red_ws,
                     c->d_status, c->kmm, c->kmm_inv, c->a_inv, c->g_k, c->g_1, c->g_2, c->scratch_x, c->scratch_w, c->c_mat,
-                    c->glob_out, c->named_tmp, c->psi2_full, c->gsl_ws, c->rec2f, c->d_yyt};
+                    c->glob_out, c->named_tmp, c->psi2_full, c->gsl_ws, c->rec2f, c->d_yyt, c->rec2x};
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->gs_stream) cudaStreamSynchronize(c->gs_stream);
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -227,6 +227,7 @@ static int ensure_shard_capacity(gparml_ctx *c, int64_t n)
     GP_TRY(dev_alloc(&c->rec1, (size_t)n * R));
     GP_TRY(dev_alloc(&c->rec2, (size_t)n * R));
     if (c->flags & GPARML_FLAG_FP32_MAP) GP_TRY(dev_alloc(&c->rec2f, (size_t)n * gp_rec_len_f32(c->Q)));
+    else if (c->Q <= GP_PSI2X_MAX_Q) GP_TRY(dev_alloc(&c->rec2x, (size_t)n * gp_recx_len(c->Q)));
     GP_TRY(dev_alloc(&c->s_pos, nq));
     GP_TRY(dev_alloc(&c->s_sig, nq));
     GP_TRY(dev_alloc(&c->gx_mu, nq));

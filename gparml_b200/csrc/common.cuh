@@ -47,6 +47,14 @@ void gp_set_error(const char *fmt, ...);
 __host__ __device__ inline int gp_rec_len(int Q) { return (3 * Q + 2) & ~1; }
 // fp32 record: same fields as floats, padded to a multiple of 4 (16-byte records)
 __host__ __device__ inline int gp_rec_len_f32(int Q) { return (3 * Q + 4) & ~3; }
+// Psi2 records of psi2x_stats (Q <= GP_PSI2X_MAX_Q), centred on the column means of Z (mc = mu - center):
+//   recx[0 .. 2Q)    : (-w_q, w_q mc_q) interleaved
+//   recx[2Q .. 4Q)   : (v_q, -1 / w_q) interleaved,  v = alpha S w
+//   recx[4Q], [4Q+1] : lc2 + sum_q alpha_q S_q  (the exponent is accumulated as sum_q (t^2 + v)(-1/w), which
+//                      carries -sum_q alpha_q S_q),  lc2
+#define GP_PSI2X_MAX_Q 10
+#define GP_PSI2X_ROBUST_AS 1024.0   // alpha S above this: the cancellation-free variant of psi2x_stats runs instead
+__host__ __device__ inline int gp_recx_len(int Q) { return 4 * Q + 2; }
 
 // packed partial-sum buffer (see DESIGN.md "packed statistics")
 struct StatLayout {
@@ -117,6 +125,7 @@ struct gparml_ctx {
     double *x_s = nullptr;      // (n, Q) uploaded domain
     double *grad_d = nullptr, *grad_latest = nullptr, *grad_new = nullptr, *grad_old = nullptr;  // (2, n, Q)
     double *rec1 = nullptr, *rec2 = nullptr;   // (n, R)
+    double *rec2x = nullptr;    // (n, 4Q + 2) records of psi2x_stats (Q <= GP_PSI2X_MAX_Q, fp64 map)
     float *rec2f = nullptr;     // (n, RF) fp32 copy of the Psi2 records (GPARML_FLAG_FP32_MAP only)
     double *s_pos = nullptr;    // (n, Q) positive variance of this evaluation
     double *s_sig = nullptr;    // (n, Q) d softplus / d raw (sigmoid) of this evaluation, 1 if positive domain
@@ -156,7 +165,8 @@ struct gparml_ctx {
     double *ws = nullptr;       // workspace for split partial sums
     size_t ws_bytes = 0;
     double *red_ws = nullptr;   // small reduction workspace (4096 doubles)
-    int *d_status = nullptr;    // device status word (range / not-PD flags)
+    int *d_status = nullptr;    // [0] device status word (range / not-PD flags); [1] != 0: some alpha S of this evaluation
+                                // exceeds GP_PSI2X_ROBUST_AS (set by prep_points, selects the psi2x_stats variant)
 
     // global step outputs (device)
     double *kmm = nullptr, *kmm_inv = nullptr, *a_inv = nullptr;

@@ -78,6 +78,7 @@ struct PrepParams {
     double *rec1, *rec2, *s_pos, *s_sig;
     float *rec2f;           // optional fp32 copy of the Psi2 records (centred means), RF floats per point
     int RF;
+    double *rec2x;          // optional records of psi2x_stats (common.cuh), 4Q + 2 doubles per point
     double *kl_partials;    // [gridDim.x][2]: (kl sum, number of exactly-zero variances)
     int *status;
 };
@@ -104,12 +105,15 @@ __global__ void __launch_bounds__(PREP_THREADS, PREP_MINB) prep_points_kernel(Pr
     extern __shared__ __align__(16) double dens[];      // [tile parity][den1 | den2][PREP_TP * Q]
     __shared__ double sh[33];
     __shared__ GlobalsDev g;
+    __shared__ double ninv_al[GP_MAX_Q];                // -1 / alpha_q
     const int Q = p.Q, R = p.R, tid = threadIdx.x;
     const int RF = p.RF;
     if (tid == 0) g = *p.glob;
+    if (tid < Q) ninv_al[tid] = -1.0 / p.glob->alpha[tid];
     __syncthreads();
     double kl = 0.0, zeros = 0.0;
-    bool bad = false;
+    bool bad = false, big = false;
+    const int RX = gp_recx_len(Q);
     const bool stepping = p.mode == 0 && p.grad_d != nullptr && p.step != 0.0;
     int parity = 0;
     for (int64_t base = p.i0 + (int64_t)blockIdx.x * PREP_TP; base < p.i1; base += (int64_t)gridDim.x * PREP_TP, parity ^= 1) {
@@ -145,6 +149,12 @@ __global__ void __launch_bounds__(PREP_THREADS, PREP_MINB) prep_points_kernel(Pr
                 *reinterpret_cast<float2 *>(rf + 2 * q) = make_float2((float)(mu - g.center[q]), (float)w);
                 rf[2 * Q + q] = (float)(al * S * w);
             }
+            if (p.rec2x) {
+                double *rx = p.rec2x + (base + pt) * RX;
+                *reinterpret_cast<double2 *>(rx + 2 * q) = make_double2(-w, w * (mu - g.center[q]));
+                *reinterpret_cast<double2 *>(rx + 2 * Q + 2 * q) = make_double2(al * S * w, den2 * ninv_al[q]);
+                if (al * S > GP_PSI2X_ROBUST_AS) big = true;
+            }
             d1s[e] = den1;
             d2s[e] = den2;
             p.s_pos[gi] = S;
@@ -172,10 +182,16 @@ __global__ void __launch_bounds__(PREP_THREADS, PREP_MINB) prep_points_kernel(Pr
                 rf[3 * Q] = (float)l2;
                 for (int k = 3 * Q + 1; k < RF; ++k) rf[k] = 0.f;
             }
+            if (p.rec2x) {
+                double as = 0.0;                                  // sum_q alpha_q S_q = sum_q (den1 - 1)
+                for (int q = 0; q < Q; ++q) as += d1s[pt * Q + q] - 1.0;
+                *reinterpret_cast<double2 *>(p.rec2x + (base + pt) * RX + 4 * Q) = make_double2(l2 + as, l2);
+            }
         }
         // no second barrier: the next tile writes the other half of the denominator buffer
     }
     if (bad) atomicOr(p.status, 4);
+    if (big) atomicOr(p.status + 1, 1);
     kl = gp_block_sum(bad ? NAN : 0.5 * kl, sh);      // NaN marks the failed input check for prep_finish (ST_FLAGS)
     zeros = gp_block_sum(zeros, sh);
     if (tid == 0) {
@@ -230,6 +246,8 @@ int gp_launch_prep_range(gparml_ctx *c, int64_t i0, int64_t i1, double *kl_parti
     p.status = c->d_status;
     p.rec2f = (c->flags & GPARML_FLAG_FP32_MAP) ? c->rec2f : nullptr;
     p.RF = gp_rec_len_f32(c->Q);
+    p.rec2x = (c->flags & GPARML_FLAG_FP32_MAP) ? nullptr : c->rec2x;
+    if (i0 == 0) GP_CUDA(cudaMemsetAsync(c->d_status + 1, 0, sizeof(int), c->stream));     // ranges arrive in order
     int blocks = (int)((i1 - i0 + PREP_TP - 1) / PREP_TP);
     if (blocks > max_blocks) blocks = max_blocks;
     if (blocks < 1) blocks = 1;

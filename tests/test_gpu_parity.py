@@ -415,6 +415,37 @@ def test_huge_negative_exponents_gplvm_path():
     assert not bad, bad
 
 
+@pytest.mark.parametrize("alpha_scale,expect_robust", [(1.0, False), (40.0, False), (2.0e3, True), (3.0e5, True)])
+def test_variance_large_against_length_scale(alpha_scale, expect_robust):
+    """psi2x_stats builds the Psi2 exponent from the u = t^2 + v it accumulates anyway (sum_q u_q (-1/w_q) started
+    at lc2 + sum_q alpha_q S_q), which cancels sum_q alpha_q S_q in rounding.  Posterior variances far above the
+    squared length-scale (alpha S up to 1e3 on this path) must stay inside the tolerance; beyond alpha S = 1024
+    prep_points switches the evaluation to the cancellation-free instantiation (one more FMA per q), which has to
+    agree with the reference formulas (kernel_exp.py:126-148, partial_terms.py:190-205,273-284) for any alpha S."""
+    from gparml_b200.synthetic import softplus_inv
+    from oracle import c_oracle
+    rng = np.random.default_rng(20141208 + 240)
+    n, M, Q, D = 1500, 30, 10, 3
+    X = rng.standard_normal((n, Q))
+    Z = X[rng.choice(n, M, replace=False)] + 0.05 * rng.standard_normal((M, Q))
+    Y = rng.standard_normal((n, D))
+    S = np.clip(0.5 + 0.2 * rng.standard_normal((n, Q)), 0.05, 1.5)
+    S[rng.random((n, Q)) < 0.02] = 14.0                                  # a few very uncertain coordinates
+    alpha = rng.uniform(0.5, 1.5, Q)
+    alpha[[1, 6]] *= alpha_scale                                          # two short length-scales next to ordinary ones (all ten
+    Z[:, [1, 6]] = X[:M, [1, 6]] + 0.02 / np.sqrt(alpha_scale) * rng.standard_normal((M, 2))   # would make every Psi vanish)
+    assert (np.max(alpha[None, :] * S) > 1024.0) == expect_robust
+    shards = [dict(Y=Y[:700], X_mu=X[:700], X_S=softplus_inv(S[:700])), dict(Y=Y[700:], X_mu=X[700:], X_S=softplus_inv(S[700:]))]
+    ref = c_oracle.evaluate(shards, Z, 1.3, alpha, 2.0)
+    res = _gpu_evaluate(shards, Z, 1.3, alpha, 2.0)
+    # not a vacuous comparison
+    assert np.max(np.abs(ref["stats"]["sum_exp_K_mi_K_im"])) > 1e-6
+    errs = _compare_all(res, ref)
+    print("max alpha S %.3g: max rel err %.2e at %s" % (np.max(alpha[None, :] * S), max(errs.values()), max(errs, key=errs.get)))
+    bad = {k2: v for k2, v in errs.items() if not v <= TOL}
+    assert not bad, bad
+
+
 @pytest.mark.parametrize("zero_dims", [(1,), (0, 3)])
 def test_alpha_zero_switches_dimension_off_with_finite_gradient(zero_dims):
     """alpha_q = 0 (infinite length-scale) is legal in the reference (kernel_exp.py:30,130 assert >= 0;

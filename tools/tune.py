@@ -24,8 +24,11 @@ from gparml_b200.build import SOURCES as ALL  # noqa: E402
 # name -> {source: [defines]}
 VARIANTS = {
     "base": {},
-    "k5_depth2": {"embed_x.cu": ["EMBX_HORNER_DEPTH=2"]},
-    "k5_depth2_e4": {"embed_x.cu": ["EMBX_HORNER_DEPTH=2", "EMBX_E4"]},
+    "x_tn128": {"psi2.cu": ["PSI2_TN=128"]},
+    "x_nob": {"psi2.cu": ["PSI2X_PROBE_NOB"]},
+    "x_notab": {"psi2.cu": ["PSI2X_PROBE_NOTAB"]},
+    "x_nob_notab": {"psi2.cu": ["PSI2X_PROBE_NOB", "PSI2X_PROBE_NOTAB"]},
+    "x_t128": {"psi2.cu": ["PSI2_THREADS=128", "PSI2X_MINB=2"]},
     # e.g. "p2_compiler": {"psi2.cu": ["PSI2_COMPILER_ORDER"]},  "emx_cp32": {"embed_x.cu": ["EMBX_CP=32", "EMBX_STAGES=3"]},
     #      "p1m_tp32": {"psi1_mma.cu": ["P1M_TP=32"]},  a leading "-" passes an nvcc flag instead of a -D macro
 }
