@@ -482,16 +482,22 @@ def run_config(env, cfg_name, steps, warmup, args, main_line):
     peak = 2.0 * dfma / 1e12
     # "bound": the contract's vocabulary is hbm | tensor; this kernel is compute-bound on the FP64 pipe, which on
     # B200 is also where the FP64 tensor-core instruction executes (same 37.2 TFLOP/s peak, tools/micro/dmma_probe.cu)
-    roofline = {"kernel": "psi2_stats_kernel<Q=%d>" % Q, "bound": "tensor", "bound_detail": "fp64_pipe (DFMA; DMMA shares it)",
+    k2x = Q <= 10 and not args.fp32                      # psi2x_stats: exponent from the accumulated u, 5Q + 10 executed
+    x_psi2 = n_loc * P * ((5 if k2x else 6) * Q + 10)
+    k2_name = "psi2x_stats_kernel" if k2x else "psi2_stats_kernel"
+    roofline = {"kernel": "%s<Q=%d>" % (k2_name, Q), "bound": "tensor", "bound_detail": "fp64_pipe (DFMA; DMMA shares it)",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak if peak > 0 else None, "traffic": None,
                 "peak_source": "pure-DFMA probe kernel measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                 "peak_nominal": 148 * 64 * 2 * 1.965e9 / 1e12,
                 "algorithmic_ops_per_launch": w_psi2, "launch_ms": med.get("psi2_stats"),
                 "ops_rule": "FP64-pipe lane-ops, FMA=1, exp=18: n_local * P * (6Q+20), TFLOP/s = 2*ops/t (SURVEY.md 8d)",
-                # what the kernel actually issues (table-driven exp = 8 instructions): the FP64-pipe busy fraction
-                "executed_ops_per_launch": n_loc * P * (6 * Q + 10),
-                "executed_frac": (n_loc * P * (6 * Q + 10) / t_psi2 / dfma) if t_psi2 > 0 and dfma > 0 else None}
+                # what the kernel actually issues (table-driven exp = 8 instructions; psi2x_stats 5 instead of 6 per
+                # latent dimension): the FP64-pipe busy fraction.  frac counts the survey's 6Q+20 and can exceed it
+                "executed_ops_per_launch": x_psi2,
+                "executed_frac": (x_psi2 / t_psi2 / dfma) if t_psi2 > 0 and dfma > 0 else None,
+                "note": "frac uses the algorithmic count of SURVEY.md 8d; the kernel issues %dQ+10 FP64 instructions per "
+                        "point-pair, so executed_frac is the pipe-busy fraction" % (5 if k2x else 6)}
     if not fixed and med.get("embed_grads", 0) > 0:
         t_emb = med["embed_grads"] * 1e-3
         x_emb = n_loc * (P * (4 * Q + 10) + M * (6 * Q + 11 + 2 * D))
@@ -516,7 +522,7 @@ def run_config(env, cfg_name, steps, warmup, args, main_line):
         if ent and int(ent["n_local"]) == n_loc:
             return ent["dram_bytes"], ent.get("source")
         return None, None
-    roofline["traffic"], src = dram("psi2_stats_kernel")
+    roofline["traffic"], src = dram(k2_name)
     if src:
         roofline["traffic_source"] = src
     # the HBM-bound streaming kernels: algorithmic bytes against the measured copy bandwidth
@@ -527,7 +533,7 @@ def run_config(env, cfg_name, steps, warmup, args, main_line):
     except Exception:
         pass
     R = (3 * Q + 2) & ~1
-    prep_bytes = n_loc * 8 * ((2 * Q if fixed else 4 * Q) + 2 * R + 2 * Q)
+    prep_bytes = n_loc * 8 * ((2 * Q if fixed else 4 * Q) + 2 * R + 2 * Q + ((4 * Q + 2) if k2x else 0))
     if med.get("prep_points", 0) > 0:
         gbs = prep_bytes / (med["prep_points"] * 1e-3) / 1e9
         roofline["prep_points_hbm"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,

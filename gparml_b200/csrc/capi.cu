@@ -135,14 +135,14 @@ extern "C" int gparml_create(gparml_ctx **out, int device, int M, int Q, int D, 
     A_(c->stats, (size_t)c->L.count);
     A_(c->red_ws, 4096);
     A_(c->d_yyt, 1100);
-    A_(c->d_status, 2);
+    A_(c->d_status, 4);
     A_(c->kmm, MM); A_(c->kmm_inv, MM); A_(c->a_inv, MM);
     A_(c->g_k, MM); A_(c->g_2, MM); A_(c->g_1, (size_t)M * D); A_(c->c_mat, (size_t)M * D);
     A_(c->scratch_x, MM); A_(c->scratch_w, MM); A_(c->psi2_full, MM);
     A_(c->glob_out, (size_t)M * Q + Q + 16);
 #undef A_
     if (cudaMemsetAsync(c->stats, 0, c->L.count * sizeof(double), c->stream) != cudaSuccess ||
-        cudaMemsetAsync(c->d_status, 0, 2 * sizeof(int), c->stream) != cudaSuccess) { gp_set_error("memset failed"); return fail(GPARML_ERR_CUDA); }
+        cudaMemsetAsync(c->d_status, 0, 4 * sizeof(int), c->stream) != cudaSuccess) { gp_set_error("memset failed"); return fail(GPARML_ERR_CUDA); }
     for (int i = 0; i < 8; ++i)
         if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { gp_set_error("event create failed"); return fail(GPARML_ERR_CUDA); }
     *out = c;

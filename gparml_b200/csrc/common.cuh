@@ -166,7 +166,8 @@ struct gparml_ctx {
     size_t ws_bytes = 0;
     double *red_ws = nullptr;   // small reduction workspace (4096 doubles)
     int *d_status = nullptr;    // [0] device status word (range / not-PD flags); [1] != 0: some alpha S of this evaluation
-                                // exceeds GP_PSI2X_ROBUST_AS (set by prep_points, selects the psi2x_stats variant)
+                                // exceeds GP_PSI2X_ROBUST_AS (set by prep_points, selects the psi2x_stats variant);
+                                // [2] retry pass of the large-M block sweep is live (global_step_large.cu)
 
     // global step outputs (device)
     double *kmm = nullptr, *kmm_inv = nullptr, *a_inv = nullptr;

@@ -20,12 +20,47 @@
 // Round 1 ran everything on the context's stream with a single-CTA O(M^2 Q) tail: 3.5 ms at M = 500, of
 // which the tail 2 ms and the four-CTA panel kernel 0.26 ms (B200, c4).
 // Same arithmetic as the single-CTA kernel (block sweep == sequential sweep of the same
-// pivots), same error behaviour (non-positive pivot -> GPARML_ERR_NOT_PD).
+// pivots), same error behaviour (non-positive pivot -> one retry with 1e-7 on the diagonal like the reference,
+// partial_terms.py:453-457, then GPARML_ERR_NOT_PD).
 // Reference lines replaced: see global_step.cu.
 #include "gs_common.cuh"
 
 #define GSL_NB 32
 #define GSL_TILE 64
+#define GSL_JITTER 1e-7   // partial_terms.py:454,456
+
+// Every kernel of a block sweep starts here.  status[0]: error bits 1 (Kmm not positive definite), 2 (Kmm + beta Psi2),
+// 4 (input check) stop the evaluation -- it raises anyway; bits 8 / 16 only record that a factorisation needed the
+// reference's jitter.  status[2] != 0: the retry pass (pass 1) of the current sweep is live; without it the kernels
+// of pass 1 return at once (they are launched unconditionally: the host never waits for the first pass).
+__device__ __forceinline__ bool gsl_skip(const int *status, int pass)
+{
+    if (status[0] & 7) return true;
+    return pass == 1 && status[2] == 0;
+}
+
+// After the first pass of a sweep: a non-positive pivot (fail_bit) becomes one retry with 1e-7 on the diagonal, like
+// the reference (partial_terms.py:453-457: slogdet sign < 0 -> + 1e-7 I); event_bit records it.
+__global__ void gsl_retry_decide_kernel(int *status, int fail_bit, int event_bit)
+{
+    const int st = status[0];
+    if ((st & fail_bit) && !(st & 4)) {
+        status[0] = (st & ~fail_bit) | event_bit;
+        status[2] = 1;
+    } else {
+        status[2] = 0;
+    }
+}
+
+// X = Kmm (+ beta Psi2) + 1e-7 I for the retry pass
+__global__ void __launch_bounds__(256) gsl_retry_build_kernel(GsParams p, double *__restrict__ X, int with_psi2, const int *status)
+{
+    if (gsl_skip(status, 1)) return;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)p.M * p.M) return;
+    const double a = with_psi2 ? fma(p.glob->beta, p.psi2_full[idx], p.kmm[idx]) : p.kmm[idx];
+    X[idx] = a + ((idx / p.M == idx % p.M) ? GSL_JITTER : 0.0);
+}
 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gsl_build_kernel(GsParams p, double *__restrict__ X)
@@ -68,9 +103,10 @@ __global__ void __launch_bounds__(256) gsl_negate_kernel(const double *__restric
 // pivot block: Pinv = (A[k0:k0+nb, k0:k0+nb])^-1 by a register-resident sweep; pivots -> piv[]
 __global__ void __launch_bounds__(1024) gsl_pivot_kernel(const double *__restrict__ A, int M, int k0, int nb,
                                                          double *__restrict__ pinv_out, double *__restrict__ piv, int *status,
-                                                         int fail_bit)
+                                                         int fail_bit, int pass)
 {
     __shared__ double col[2][GSL_NB];
+    if (gsl_skip(status, pass)) return;
     const int r = threadIdx.x >> 5, c = threadIdx.x & 31;
     double e = (r < nb && c < nb) ? A[(size_t)(k0 + r) * M + k0 + c] : 0.0;
     for (int k = 0; k < nb; ++k) {
@@ -95,11 +131,11 @@ __global__ void __launch_bounds__(1024) gsl_pivot_kernel(const double *__restric
 // 8 rows per CTA: ceil(M / 8) CTAs instead of the ceil(M / 128) of the thread-per-row version (4 CTAs at M = 500).
 __global__ void __launch_bounds__(256) gsl_panel_kernel(const double *__restrict__ A, int M, int k0, int nb,
                                                         const double *__restrict__ pinv, double *__restrict__ T,
-                                                        double *__restrict__ Old, const int *status)
+                                                        double *__restrict__ Old, const int *status, int pass)
 {
     __shared__ double ps[GSL_NB * GSL_NB];
     __shared__ double as[8][GSL_NB];
-    if (*status) return;
+    if (gsl_skip(status, pass)) return;
     for (int idx = threadIdx.x; idx < GSL_NB * GSL_NB; idx += 256) ps[idx] = pinv[idx];
     const int r = threadIdx.x >> 5, c = threadIdx.x & 31;
     const int i = blockIdx.x * 8 + r;
@@ -119,11 +155,11 @@ __global__ void __launch_bounds__(256) gsl_panel_kernel(const double *__restrict
 // rank-NB update of the whole matrix, 64 x 64 tile per CTA, 4 x 4 outputs per thread
 __global__ void __launch_bounds__(256) gsl_update_kernel(double *__restrict__ A, int M, int k0, int nb,
                                                          const double *__restrict__ pinv, const double *__restrict__ T,
-                                                         const double *__restrict__ Old, const int *status)
+                                                         const double *__restrict__ Old, const int *status, int pass)
 {
     __shared__ __align__(16) double Ts[GSL_NB][GSL_TILE];      // [c][i]
     __shared__ __align__(16) double Os[GSL_NB][GSL_TILE];      // [c][j]
-    if (*status) return;
+    if (gsl_skip(status, pass)) return;
     const int i0 = blockIdx.y * GSL_TILE, j0 = blockIdx.x * GSL_TILE;
     for (int idx = threadIdx.x; idx < GSL_TILE * GSL_NB; idx += 256) {
         const int r = idx / GSL_NB, c = idx % GSL_NB;
@@ -174,7 +210,7 @@ __global__ void __launch_bounds__(256) gsl_gemm_kernel(const double *__restrict_
 {
     __shared__ __align__(16) double As[16][GSL_TILE];          // [k][i]
     __shared__ __align__(16) double Bs[16][GSL_TILE];          // [k][j]
-    if (*status) return;
+    if (*status & 7) return;
     const int i0 = blockIdx.y * GSL_TILE, j0 = blockIdx.x * GSL_TILE;
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
     double acc[4][4];
@@ -221,7 +257,7 @@ __global__ void __launch_bounds__(256) gsl_head_finish_kernel(GsParams p, const 
     const size_t MM = (size_t)M * M;
     const double beta = p.glob->beta, hD = 0.5 * (double)D;
     double s[4] = {0, 0, 0, 0};
-    if (*p.status == 0) {
+    if ((*p.status & 7) == 0) {
         for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < MM; idx += (size_t)gridDim.x * blockDim.x) {
             const int i = (int)(idx / M), j = (int)(idx - (size_t)i * M);
             double e = 0.0;
@@ -250,7 +286,7 @@ __global__ void __launch_bounds__(256) gsl_head_finish_kernel(GsParams p, const 
 // pair tables for embed_grads from dF/dPsi2 (same entries as gs_pair_tables, any number of CTAs)
 __global__ void __launch_bounds__(256) gsl_pair_tables_kernel(GsParams p)
 {
-    if (*p.status) return;
+    if (*p.status & 7) return;
     const int M = p.M;
     const size_t MM = (size_t)M * M;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < MM; idx += (size_t)gridDim.x * blockDim.x) {
@@ -275,7 +311,7 @@ __global__ void __launch_bounds__(256) gsl_assemble_gk_kernel(GsParams p, const 
     const size_t MM = (size_t)M * M;
     const double beta = p.glob->beta, hD = 0.5 * (double)p.D;
     double s[2] = {0, 0};
-    if (*p.status == 0) {
+    if ((*p.status & 7) == 0) {
         for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < MM; idx += (size_t)gridDim.x * blockDim.x) {
             const int i = (int)(idx / M), j = (int)(idx - (size_t)i * M);
             const double e = p.g_k[idx];          // C C^T from the head
@@ -304,7 +340,7 @@ __global__ void __launch_bounds__(256) gsl_grad_alpha_kernel(GsParams p, double 
         const double al = q < Q ? p.glob->alpha[q] : 1.0;
         ia2[q] = 1.0 / (al * al);
     }
-    if (*p.status == 0) {
+    if ((*p.status & 7) == 0) {
         for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < MM; idx += (size_t)gridDim.x * blockDim.x) {
             const int i = (int)(idx / M), j = (int)(idx - (size_t)i * M);
             const int64_t pp = pidx(M, i, j);
@@ -338,7 +374,7 @@ __global__ void __launch_bounds__(256) gsl_grad_alpha_kernel(GsParams p, double 
 // grad_Z (partial_terms.py:146-160, 207-240): one warp per element (j, k), lanes over m', fixed-order shuffle tree
 __global__ void __launch_bounds__(256) gsl_grad_z_kernel(GsParams p)
 {
-    if (*p.status) return;
+    if (*p.status & 7) return;
     const int M = p.M, Q = p.Q, D = p.D;
     const int lane = threadIdx.x & 31;
     const int idx = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -391,20 +427,32 @@ __global__ void __launch_bounds__(256) gsl_final_kernel(GsParams p, const double
 }
 
 // ---------------------------------------------------------------------------------------------
-static int block_sweep(gparml_ctx *c, double *X, double *pinv, double *T, double *Old, double *piv, int fail_bit)
+static int block_sweep_pass(gparml_ctx *c, double *X, double *pinv, double *T, double *Old, double *piv, int fail_bit, int pass)
 {
     const int M = c->M;
     const int tiles = (M + GSL_TILE - 1) / GSL_TILE;
     for (int k0 = 0; k0 < M; k0 += GSL_NB) {
         const int nb = (M - k0 < GSL_NB) ? (M - k0) : GSL_NB;
-        gsl_pivot_kernel<<<1, 1024, 0, c->stream>>>(X, M, k0, nb, pinv, piv, c->d_status, fail_bit);
+        gsl_pivot_kernel<<<1, 1024, 0, c->stream>>>(X, M, k0, nb, pinv, piv, c->d_status, fail_bit, pass);
         GP_LAUNCH_CHECK(c);
-        gsl_panel_kernel<<<(M + 7) / 8, 256, 0, c->stream>>>(X, M, k0, nb, pinv, T, Old, c->d_status);
+        gsl_panel_kernel<<<(M + 7) / 8, 256, 0, c->stream>>>(X, M, k0, nb, pinv, T, Old, c->d_status, pass);
         GP_LAUNCH_CHECK(c);
-        gsl_update_kernel<<<dim3(tiles, tiles), 256, 0, c->stream>>>(X, M, k0, nb, pinv, T, Old, c->d_status);
+        gsl_update_kernel<<<dim3(tiles, tiles), 256, 0, c->stream>>>(X, M, k0, nb, pinv, T, Old, c->d_status, pass);
         GP_LAUNCH_CHECK(c);
     }
     return GPARML_OK;
+}
+
+// X <- -X^-1 (pivots -> piv); if a pivot is not positive, once more from X + 1e-7 I (decided on the device: the
+// kernels of the second pass are always launched and return at once when the first pass went through)
+static int block_sweep(gparml_ctx *c, const GsParams &p, double *X, double *pinv, double *T, double *Old, double *piv, int fail_bit)
+{
+    GP_TRY(block_sweep_pass(c, X, pinv, T, Old, piv, fail_bit, 0));
+    gsl_retry_decide_kernel<<<1, 1, 0, c->stream>>>(c->d_status, fail_bit, fail_bit == 1 ? 8 : 16);
+    GP_LAUNCH_CHECK(c);
+    gsl_retry_build_kernel<<<(int)(((size_t)c->M * c->M + 255) / 256), 256, 0, c->stream>>>(p, X, fail_bit == 2, c->d_status);
+    GP_LAUNCH_CHECK(c);
+    return block_sweep_pass(c, X, pinv, T, Old, piv, fail_bit, 1);
 }
 
 static int gemm(gparml_ctx *c, const double *A, int lda, const double *B, int ldb, double *C, int ldc, int M, int N, int K, double alpha)
@@ -438,7 +486,7 @@ int gp_launch_global_step_large(gparml_ctx *c, GsParams &p)
         // from set_globals on the side stream: Kmm, Kmm^-1 (W and kmm_inv) and its pivots
         gsl_build_kernel<<<eb, 256, 0, c->stream>>>(p, X);
         GP_LAUNCH_CHECK(c);
-        GP_TRY(block_sweep(c, X, pinv, T, Old, pivK, 1));
+        GP_TRY(block_sweep(c, p, X, pinv, T, Old, pivK, 1));
         gsl_negate_kernel<<<eb, 256, 0, c->stream>>>(X, MM, W, c->kmm_inv);
         GP_LAUNCH_CHECK(c);
         return GPARML_OK;
@@ -449,7 +497,7 @@ int gp_launch_global_step_large(gparml_ctx *c, GsParams &p)
         GP_LAUNCH_CHECK(c);
         gsl_form_a_kernel<<<eb, 256, 0, c->stream>>>(p, X);
         GP_LAUNCH_CHECK(c);
-        GP_TRY(block_sweep(c, X, pinv, T, Old, pivA, 2));
+        GP_TRY(block_sweep(c, p, X, pinv, T, Old, pivA, 2));
         gsl_negate_kernel<<<eb, 256, 0, c->stream>>>(X, MM, c->a_inv, nullptr);
         GP_LAUNCH_CHECK(c);
         GP_TRY(gemm(c, c->a_inv, M, c->stats + c->L.off_p1y, D, c->c_mat, D, M, D, M, 1.0));      // C = A^-1 Psi1Y

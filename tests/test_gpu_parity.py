@@ -162,13 +162,14 @@ def test_finite_differences_through_cuda_path():
     assert abs(fd + base["grad_latest"][0][1, 3, 0]) <= 2e-6 * max(1.0, abs(fd))
 
 
-def test_error_mapping_not_pd_and_range():
+@pytest.mark.parametrize("M", [6, 130])
+def test_error_mapping_not_pd_and_range(M):
     """Device-side numerical failure surfaces as the exception types the reference's
-    optimiser wrapper survives (scg_adapted.py:55)."""
+    optimiser wrapper survives (scg_adapted.py:55); M = 130 takes the multi-kernel master step."""
     from gparml_b200.engine import ShardContext
     rng = np.random.default_rng(0)
-    M, Q, D, n = 6, 2, 2, 40
-    Z = rng.standard_normal((M, Q))
+    Q, D, n = 2, 2, 40
+    Z = rng.standard_normal((M, Q)) * (1.0 if M < 50 else 8.0)     # 130 points in the unit square would make Kmm singular to 1e-15
     with ShardContext(M, Q, D, n) as c:
         c.upload_shard(rng.standard_normal((n, D)), rng.standard_normal((n, Q)), rng.standard_normal((n, Q)) - 1.0)
         c.set_globals(Z, 1.0, np.ones(Q), 1.0)
@@ -181,21 +182,22 @@ def test_error_mapping_not_pd_and_range():
             c.global_step()
         bad = rng.standard_normal((n, Q)); bad[5, 1] = 40.0   # supporting_functions.py:154 assert
         c.upload_shard(rng.standard_normal((n, D)), rng.standard_normal((n, Q)), bad)
-        c.set_globals(rng.standard_normal((M, Q)), 1.0, np.ones(Q), 1.0)
+        c.set_globals(Z + 0.1, 1.0, np.ones(Q), 1.0)
         with pytest.raises(AssertionError):
             c.statistics()
 
 
-def test_jitter_retry_follows_reference_branch():
+@pytest.mark.parametrize("M", [12, 130])
+def test_jitter_retry_follows_reference_branch(M):
     """partial_terms.py:453-457: when a factorisation says "not positive definite" the reference retries with 1e-7
-    on the diagonal and only gives up (assert) if that fails too.  The device does the same (single-CTA master
-    step): a Kmm + beta Psi2 with one eigenvalue of -1e-9 evaluates to the bound of the reference's jitter branch
+    on the diagonal and only gives up (assert) if that fails too.  The device does the same (M = 12: single-CTA
+    master step; M = 130: the multi-kernel block sweep, whose retry pass is decided on the device): a Kmm + beta Psi2 with one eigenvalue of -1e-9 evaluates to the bound of the reference's jitter branch
     (the oracle restates it: oracle/gparml_oracle.py global_step), the event is counted, and a matrix that is
     indefinite beyond the jitter still raises LinAlgError (test_error_mapping_not_pd_and_range)."""
     from gparml_b200.engine import ShardContext
     from gparml_b200.synthetic import make_problem
     from oracle import gparml_oracle as O
-    M, Q, D, n = 12, 3, 2, 300
+    Q, D, n = 3, 2, 300
     p = make_problem(n, M, Q, D, seed=91, generic_hypers=True)
     rng = np.random.default_rng(91)
     V, _ = np.linalg.qr(rng.standard_normal((M, M)))
