@@ -201,6 +201,7 @@ __device__ __forceinline__ void embx_step(const double2 *__restrict__ zn, const 
         }
     }
     EMBX_GROUP(2)
+#if GP_EXP_POLY_STEPS == 4
     if (DO_E) {
 #pragma unroll
         for (int v = 0; v < NP; ++v) es[v].p = fma(es[v].r, 1.0 / 24.0, 1.0 / 6.0);
@@ -211,15 +212,23 @@ __device__ __forceinline__ void embx_step(const double2 *__restrict__ zn, const 
 #pragma unroll
         for (int v = 0; v < NP; ++v) es[v].p = fma(es[v].p, es[v].r, 0.5);
     }
+#else
+    EMBX_GROUP(3)
+    if (DO_E) {
+#pragma unroll
+        for (int v = 0; v < NP; ++v) es[v].p = fma(es[v].r, GP_EXP_C3, GP_EXP_C2);
+    }
+    EMBX_GROUP(4)
+#endif
     EMBX_GROUP(5)
     if (DO_E) {
 #pragma unroll
-        for (int v = 0; v < NP; ++v) es[v].p = fma(es[v].p, es[v].r, 1.0);
+        for (int v = 0; v < NP; ++v) es[v].p = fma(es[v].p, es[v].r, GP_EXP_C1);
     }
     EMBX_GROUP(6)
     if (DO_E) {
 #pragma unroll
-        for (int v = 0; v < NP; ++v) es[v].p = fma(es[v].p, es[v].r, 1.0);
+        for (int v = 0; v < NP; ++v) es[v].p = fma(es[v].p, es[v].r, GP_EXP_C0);
     }
     EMBX_GROUP(7)
     if (DO_E) {

@@ -1,29 +1,54 @@
 // Table-driven double-precision exp for the Psi kernels.
 //
-//   exp(x) = 2^m * 2^(j/64) * exp(r),   k = round(x * 64/ln2) = 64 m + j,   r = x - k ln2/64,
-//   |r| <= ln2/128 = 0.0054  ->  degree-4 Taylor polynomial (truncation r^5/120 <= 3.9e-14 relative).
-//
-// 8 FP64-pipe instructions (3 DFMA/DADD for the reduction, 4 DFMA polynomial, 1 DMUL by the
-// table entry) instead of the 18 of libdevice's exp() (round 1: 32 entries, degree 5, 9 instructions); the 2^m
-// scaling and the table index are integer-pipe work and the table read is one 8-byte shared-memory load.
-// Relative error <= ~5e-14 for |x| < 100 (truncation, plus the argument reduction with a single rounded ln2/64:
-// |x| * 1.1e-16), far inside the 1e-9 parity budget on the summed statistics.
+//   exp(x) = 2^m * 2^(j/N) * exp(r),   k = round(x * N/ln2) = N m + j,   r = x - k ln2/N
+//   N = 256 (default): |r| <= ln2/512 = 1.35e-3, degree-3 near-minimax polynomial, max relative error 1.8e-14
+//                      -> 7 FP64-pipe instructions (3 DFMA/DADD reduction, 3 DFMA polynomial, 1 DMUL by the table entry)
+//   N = 64  (GP_EXP_LOG2_TAB 6, psi2.cu): |r| <= ln2/128 = 5.4e-3, degree-4 Taylor polynomial (truncation 3.9e-14) -> 8
+// instead of the 18 of libdevice's exp() (round 1: 32 entries, degree 5, 9 instructions).  The 2^m scaling and the
+// table index are integer-pipe work and the table read is one 8-byte shared-memory load (tools/gen_exp_table.py wrote
+// gp_exp_table8.inc, correctly rounded entries).  Measured on B200 at c3 (tools/tune.py): embed_psi2x 18.98 ms with
+// 64 entries / 8 instructions, 18.67 with 256 / 7, 18.73 with 1024 entries and the degree-3 Taylor polynomial;
+// psi2x_stats 21.24 / 22.27 / 22.90 -- there the shorter polynomial no longer hides the table read and the larger
+// tables add bank conflicts, so psi2.cu keeps the 64-entry form.
+// Relative error <= ~4e-14 + |x| * 1.1e-16 (argument reduction with a single rounded ln2/N), far inside the 1e-9
+// parity budget on the summed statistics.
 //
 // Domain: any x <= 700 including -inf (Psi values are bounded by sf^2 resp. sf^4).  The argument is first
 // clamped to >= -745.25 by gp_exp_clamp -- an unsigned integer min on the high word (negative doubles order
-// like their bit patterns), one integer-pipe instruction, no FP64 slot -- because k = round(x 32/ln2) is read
-// from the low word of t and would wrap for x < -4.65e7 (an exponent that size is what un-normalised
+// like their bit patterns), one integer-pipe instruction, no FP64 slot -- because k = round(x N/ln2) is read
+// from the low word of t and would wrap for very negative x (an exponent of -1e8 is what un-normalised
 // regression inputs give: alpha = 1, inputs spanning 1e4, kernel_exp.py:143-146 then calls np.exp(-1e8) = 0).
 // x < -709 returns ~4e-308..9e-308 instead of a denormal / zero (m is clamped), which contributes nothing
 // to any sum.
 #pragma once
 
-#define GP_EXP_TAB 64
-#define GP_EXP_LOG2_TAB 6
-#define GP_EXP_SCALE 92.33248261689366            // 64 / ln2
-#define GP_EXP_NEG_STEP -0.010830424696249145     // -ln2 / 64
+#ifndef GP_EXP_LOG2_TAB
+#define GP_EXP_LOG2_TAB 8
+#endif
+#define GP_EXP_TAB (1 << GP_EXP_LOG2_TAB)
 #define GP_EXP_SHIFT 6755399441055744.0           // 1.5 * 2^52: the low word of fma(x, SCALE, SHIFT) is round(x SCALE)
 
+#if GP_EXP_LOG2_TAB == 8
+// 256 entries, |r| <= ln2/512 = 1.35e-3: degree-3 near-minimax polynomial (Chebyshev interpolation refined on the max
+// relative error: 1.8e-14; the Taylor coefficients would give 1.4e-13)
+#define GP_EXP_SCALE 369.3299304675746           // 256 / ln2
+#define GP_EXP_NEG_STEP -0.0027076061740622863    // -ln2 / 256
+#define GP_EXP_C3 0.16666670155072924
+#define GP_EXP_C2 0.5000000762607874
+#define GP_EXP_C1 0.9999999999999927
+#define GP_EXP_C0 0.9999999999999827
+#define GP_EXP_POLY_HEAD(r) fma(fma((r), GP_EXP_C3, GP_EXP_C2), (r), GP_EXP_C1)
+#define GP_EXP_POLY_STEPS 3
+static __device__ const double gp_exp_table_const[GP_EXP_TAB] = {
+#include "gp_exp_table8.inc"
+};
+#elif GP_EXP_LOG2_TAB == 6
+#define GP_EXP_SCALE 92.33248261689366            // 64 / ln2
+#define GP_EXP_NEG_STEP -0.010830424696249145     // -ln2 / 64
+#define GP_EXP_POLY_HEAD(r) fma(fma(fma((r), 1.0 / 24.0, 1.0 / 6.0), (r), 0.5), (r), 1.0)
+#define GP_EXP_POLY_STEPS 4
+#define GP_EXP_C1 1.0
+#define GP_EXP_C0 1.0
 // 2^(j/64), j = 0 .. 63, correctly rounded
 #define GP_EXP_TABLE_VALUES                                                                                          \
     1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284, 1.0442737824274138,                          \
@@ -38,9 +63,12 @@
     1.6280274218573478, 1.645755478153965, 1.6636765803267364, 1.681792830507429, 1.7001063537185235,             \
     1.718619298122478, 1.7373338352737062, 1.7562521603732995, 1.7753764925265212, 1.7947090750031072,            \
     1.8142521755003989, 1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,              \
-    1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951                                 
+    1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951
 
-static __constant__ double gp_exp_table_const[GP_EXP_TAB] = {GP_EXP_TABLE_VALUES};
+static __device__ const double gp_exp_table_const[GP_EXP_TAB] = {GP_EXP_TABLE_VALUES};
+#else
+#error "GP_EXP_LOG2_TAB must be 6 or 8"
+#endif
 
 // copy the table into shared memory (call from all threads, then __syncthreads())
 __device__ __forceinline__ void gp_exp_load_table(double *tab_smem)
@@ -68,10 +96,7 @@ __device__ __forceinline__ double gp_exp_signed(double x, const double *tab_smem
     const int k = __double2loint(t);
     const double kd = t - GP_EXP_SHIFT;
     const double r = fma(kd, GP_EXP_NEG_STEP, x);
-    double p = fma(r, 1.0 / 24.0, 1.0 / 6.0);
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
+    const double p = fma(GP_EXP_POLY_HEAD(r), r, GP_EXP_C0);
     int m = k >> GP_EXP_LOG2_TAB;
     m = m < -1021 ? -1021 : m;
     const double s = tab_smem[k & (GP_EXP_TAB - 1)] * p;      // in [1, 2.03)

@@ -30,6 +30,7 @@
 
 #include "common.cuh"
 
+#define GP_EXP_LOG2_TAB 6      // 64-entry table, degree-4 polynomial: faster here than the 256-entry / degree-3 default (gp_exp.cuh)
 #include "gp_exp.cuh"
 
 #ifndef PSI2_THREADS
@@ -258,14 +259,19 @@ __device__ __forceinline__ void psi2x_point(const double *__restrict__ rp, const
     for (int v = 0; v < 2; ++v) { k[v] = __double2loint(tt[v]); tt[v] = tt[v] - GP_EXP_SHIFT; }
 #pragma unroll
     for (int v = 0; v < 2; ++v) { r[v] = fma(tt[v], GP_EXP_NEG_STEP, x[v]); tab[v] = exp_tab[k[v] & (GP_EXP_TAB - 1)]; }
+#if GP_EXP_POLY_STEPS == 4
 #pragma unroll
     for (int v = 0; v < 2; ++v) pl[v] = fma(r[v], 1.0 / 24.0, 1.0 / 6.0);
 #pragma unroll
     for (int v = 0; v < 2; ++v) pl[v] = fma(pl[v], r[v], 0.5);
+#else
 #pragma unroll
-    for (int v = 0; v < 2; ++v) pl[v] = fma(pl[v], r[v], 1.0);
+    for (int v = 0; v < 2; ++v) pl[v] = fma(r[v], GP_EXP_C3, GP_EXP_C2);
+#endif
 #pragma unroll
-    for (int v = 0; v < 2; ++v) pl[v] = fma(pl[v], r[v], 1.0);
+    for (int v = 0; v < 2; ++v) pl[v] = fma(pl[v], r[v], GP_EXP_C1);
+#pragma unroll
+    for (int v = 0; v < 2; ++v) pl[v] = fma(pl[v], r[v], GP_EXP_C0);
 #pragma unroll
     for (int v = 0; v < 2; ++v) pl[v] = tab[v] * pl[v];
 #pragma unroll

@@ -24,11 +24,10 @@ from gparml_b200.build import SOURCES as ALL  # noqa: E402
 # name -> {source: [defines]}
 VARIANTS = {
     "base": {},
-    "x_tn128": {"psi2.cu": ["PSI2_TN=128"]},
-    "x_nob": {"psi2.cu": ["PSI2X_PROBE_NOB"]},
-    "x_notab": {"psi2.cu": ["PSI2X_PROBE_NOTAB"]},
-    "x_nob_notab": {"psi2.cu": ["PSI2X_PROBE_NOB", "PSI2X_PROBE_NOTAB"]},
-    "x_t128": {"psi2.cu": ["PSI2_THREADS=128", "PSI2X_MINB=2"]},
+    "exp64": {f: ["GP_EXP_LOG2_TAB=6"] for f in ("psi2.cu", "embed_x.cu", "embed.cu", "psi1_mma.cu", "psi1_wide.cu", "psi1.cu")},
+    "exp8": {f: ["GP_EXP_LOG2_TAB=8"] for f in ("psi2.cu", "embed_x.cu", "embed.cu", "psi1_mma.cu", "psi1_wide.cu", "psi1.cu")},
+    "k2_exp64": {"psi2.cu": ["GP_EXP_LOG2_TAB=6"]},
+    "k2_exp8": {"psi2.cu": ["GP_EXP_LOG2_TAB=8"]},
     # e.g. "p2_compiler": {"psi2.cu": ["PSI2_COMPILER_ORDER"]},  "emx_cp32": {"embed_x.cu": ["EMBX_CP=32", "EMBX_STAGES=3"]},
     #      "p1m_tp32": {"psi1_mma.cu": ["P1M_TP=32"]},  a leading "-" passes an nvcc flag instead of a -D macro
 }
