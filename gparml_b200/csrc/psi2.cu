@@ -373,7 +373,8 @@ __global__ void __launch_bounds__(256) psi2_reduce_kernel(const double *__restri
     dst[i] = a;
 }
 
-// number of n-splits for `cnt` points: whole waves of resident CTAs, >= 4 point tiles per split, bounded workspace
+#define PSI2_CTA_SETUP_POINTS 24.0
+// number of n-splits for `cnt` points: whole waves of resident CTAs, bounded workspace
 template <int Q>
 static int plan_q(gparml_ctx *c, int64_t cnt, int *splits_out)
 {
@@ -397,7 +398,7 @@ static int plan_q(gparml_ctx *c, int64_t cnt, int *splits_out)
     const int tiles = (int)((P + PSI2_THREADS * pp - 1) / (PSI2_THREADS * pp));
     const int64_t slots = (int64_t)c->sm_count * occ;
     const int64_t rows_x_P = (int64_t)(1 + 2 * Q) * P;
-    int64_t max_splits = (cnt + 4 * tn - 1) / (4 * tn);
+    int64_t max_splits = (cnt + tn - 1) / tn;             // at least one point tile per split
     const int64_t ws_cap = ((int64_t)512 << 20) / (rows_x_P * (int64_t)sizeof(double)) / GP_MAX_RANGES;   // all ranges of an evaluation share the workspace
     if (max_splits > ws_cap) max_splits = ws_cap;
     if (max_splits > 65535) max_splits = 65535;
@@ -408,7 +409,10 @@ static int plan_q(gparml_ctx *c, int64_t cnt, int *splits_out)
         const int64_t total = (int64_t)tiles * s;
         const int64_t waves = (total + slots - 1) / slots;
         if (waves > 8) break;
-        const double eff = (double)total / (double)(waves * slots);
+        // wave fill x the share of a CTA's life spent on points (its set-up -- pair registers, exp table, first
+        // tile in flight -- costs about as much as PSI2_CTA_SETUP_POINTS points)
+        const double per = (double)cnt / (double)s;
+        const double eff = (double)total / (double)(waves * slots) * per / (per + PSI2_CTA_SETUP_POINTS);
         if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
     }
     *splits_out = (int)best;

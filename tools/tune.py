@@ -24,10 +24,6 @@ from gparml_b200.build import SOURCES as ALL  # noqa: E402
 # name -> {source: [defines]}
 VARIANTS = {
     "base": {},
-    "exp64": {f: ["GP_EXP_LOG2_TAB=6"] for f in ("psi2.cu", "embed_x.cu", "embed.cu", "psi1_mma.cu", "psi1_wide.cu", "psi1.cu")},
-    "exp8": {f: ["GP_EXP_LOG2_TAB=8"] for f in ("psi2.cu", "embed_x.cu", "embed.cu", "psi1_mma.cu", "psi1_wide.cu", "psi1.cu")},
-    "k2_exp64": {"psi2.cu": ["GP_EXP_LOG2_TAB=6"]},
-    "k2_exp8": {"psi2.cu": ["GP_EXP_LOG2_TAB=8"]},
     # e.g. "p2_compiler": {"psi2.cu": ["PSI2_COMPILER_ORDER"]},  "emx_cp32": {"embed_x.cu": ["EMBX_CP=32", "EMBX_STAGES=3"]},
     #      "p1m_tp32": {"psi1_mma.cu": ["P1M_TP=32"]},  a leading "-" passes an nvcc flag instead of a -D macro
 }
@@ -73,9 +69,10 @@ def one(lib, n):
     from gparml_b200 import _lib
     from gparml_b200.engine import ShardContext
     from gparml_b200.synthetic import CONFIGS, make_problem
-    k = CONFIGS["c3"]
-    p = make_problem(n, k["M"], k["Q"], k["D"], seed=3, with_direction=True)
-    c = ShardContext(k["M"], k["Q"], k["D"], n, fp32_map=os.environ.get("GPARML_TUNE_FP32") == "1")
+    k = CONFIGS[os.environ.get("GPARML_TUNE_CFG", "c3")]
+    fixed = bool(k.get("fixed_embeddings"))
+    p = make_problem(n, k["M"], k["Q"], k["D"], seed=3, with_direction=not fixed, fixed_embeddings=fixed)
+    c = ShardContext(k["M"], k["Q"], k["D"], n, fp32_map=os.environ.get("GPARML_TUNE_FP32") == "1", fixed_embeddings=fixed)
     c.upload_shard(p["Y"], p["X_mu"], p["X_S"])
     c.enable_timing(True)
     acc = {}
@@ -83,15 +80,15 @@ def one(lib, n):
         c.set_globals(p["Z"], p["sf2"], p["alpha"], p["beta"])
         c.statistics()
         F, g = c.global_step()
-        c.embedding_grads()
+        if not fixed:
+            c.embedding_grads()
         t = c.phase_times_ms()
         if it >= 2:
             for kk, v in t.items():
                 acc.setdefault(kk, []).append(v)
-    gl = c.grad_latest()
     out = {kk: float(np.median(v)) for kk, v in acc.items()}
     out["F"] = F
-    out["chk"] = float(np.abs(gl).sum())
+    out["chk"] = 0.0 if fixed else float(np.abs(c.grad_latest()).sum())
     print(json.dumps(out))
 
 
