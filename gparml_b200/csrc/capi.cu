@@ -120,6 +120,8 @@ extern "C" int gparml_create(gparml_ctx **out, int device, int M, int Q, int D, 
         cudaMallocHost((void **)&c->glob_host, ((size_t)M * Q + Q + 16) * sizeof(double)) != cudaSuccess) { gp_set_error("copy stream create failed"); return fail(GPARML_ERR_CUDA); }
     for (int i = 0; i < 8; ++i)
         if (cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming) != cudaSuccess) { gp_set_error("event create failed"); return fail(GPARML_ERR_CUDA); }
+    for (int i = 0; i < 4; ++i)
+        if (cudaEventCreate(&c->ev_dl[i]) != cudaSuccess) { gp_set_error("event create failed"); return fail(GPARML_ERR_CUDA); }
     for (int i = 0; i < GP_MAX_RANGES; ++i)
         if (cudaEventCreateWithFlags(&c->ev_x[i], cudaEventDisableTiming) != cudaSuccess) { gp_set_error("event create failed"); return fail(GPARML_ERR_CUDA); }
     const size_t MM = (size_t)M * M;
@@ -167,6 +169,7 @@ extern "C" int gparml_destroy(gparml_ctx *c)
     if (c->gs_stream) cudaStreamDestroy(c->gs_stream);
     for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 8; ++i) if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
+    for (int i = 0; i < 4; ++i) if (c->ev_dl[i]) cudaEventDestroy(c->ev_dl[i]);
     for (int i = 0; i < GP_MAX_RANGES; ++i) if (c->ev_x[i]) cudaEventDestroy(c->ev_x[i]);
     if (c->ev_main) cudaEventDestroy(c->ev_main);
     if (c->ev_y) cudaEventDestroy(c->ev_y);
@@ -250,10 +253,19 @@ extern "C" int gparml_upload_shard(gparml_ctx *c, const double *Y, const double 
     // then Y, which only psi1_stats / the Psi1 part of embed_grads need.
     GP_CUDA(cudaEventRecord(c->ev_main, c->stream));
     GP_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
-    int ranges = (int)(n / GP_RANGE_ROWS);
-    if (ranges > GP_MAX_RANGES) ranges = GP_MAX_RANGES;
-    if (ranges < 1 || (c->flags & GPARML_FLAG_FP32_MAP)) ranges = 1;
-    for (int k = 0; k <= ranges; ++k) c->x_bounds[k] = n * k / ranges;
+    // Row ranges that double in size: only the first (small) range's transfer is exposed, and the kernels of range k
+    // (twice the work of range k - 1) cover the transfer of range k + 1 as long as the link moves a point faster than
+    // half the time prep_points + psi2_stats need for it; few, large ranges keep the per-launch wave quantisation of
+    // psi2_stats small (8 equal ranges cost it 4 % at c3).
+    int ranges = 1;
+    while (ranges < GP_MAX_RANGES && (n / GP_RANGE_ROWS + 1) >> ranges) ++ranges;      // floor(log2(n / 16384 + 1)), >= 1
+    if (n / GP_RANGE_ROWS < 1 || (c->flags & GPARML_FLAG_FP32_MAP)) ranges = 1;
+    c->x_bounds[0] = 0;
+    for (int k = 1; k <= ranges; ++k) {
+        int64_t b = (int64_t)((double)n * (double)((1 << k) - 1) / (double)((1 << ranges) - 1));
+        b = (b + 127) / 128 * 128;
+        c->x_bounds[k] = (k == ranges || b > n) ? n : b;
+    }
     if (n > 0) {
         for (int k = 0; k < ranges; ++k) {
             const size_t off = (size_t)c->x_bounds[k] * c->Q, cnt = (size_t)(c->x_bounds[k + 1] - c->x_bounds[k]) * c->Q;
@@ -464,18 +476,26 @@ extern "C" int gparml_statistics_launch(gparml_ctx *c)
         // pipelined with the upload: range k is prepared and reduced while range k + 1 is still arriving
         const int ranges = c->x_pending;
         c->x_pending = 0;
-        int splits = 1, slice = 0, blocks = 0;
-        GP_TRY(gp_psi2_plan_range(c, c->x_bounds[1] - c->x_bounds[0], &splits));
-        GP_TRY(gp_ensure_ws(c, (size_t)ranges * splits * (1 + 2 * c->Q) * c->L.P * sizeof(double)));
-        const int kl_blocks = 4096 / 2 / ranges;                       // KL block partials of all ranges share red_ws
+        int splits[GP_MAX_RANGES], slice = 0, blocks = 0, total = 0;
+        for (int k = 0; k < ranges; ++k) {
+            splits[k] = 1;
+            if (c->x_bounds[k + 1] > c->x_bounds[k]) GP_TRY(gp_psi2_plan_range(c, c->x_bounds[k + 1] - c->x_bounds[k], &splits[k]));
+            total += splits[k];
+        }
+        GP_TRY(gp_ensure_ws(c, (size_t)total * (1 + 2 * c->Q) * c->L.P * sizeof(double)));
         for (int k = 0; k < ranges; ++k) {
             GP_CUDA(cudaStreamWaitEvent(c->stream, c->ev_x[k], 0));
             int b = 0;
+            // KL block partials of all ranges share red_ws (2 x 2048 doubles): each range gets its share of the slots
+            int kl_blocks = (int)(2000.0 * (double)(c->x_bounds[k + 1] - c->x_bounds[k]) / (double)c->n);
+            if (kl_blocks < 4) kl_blocks = 4;
             GP_TRY(gp_launch_prep_range(c, c->x_bounds[k], c->x_bounds[k + 1], c->red_ws + 2 * blocks, kl_blocks, &b));
             blocks += b;
             if (k == 0) GP_TRY(record(c, 1));
-            GP_TRY(gp_launch_psi2_stats_range(c, c->x_bounds[k], c->x_bounds[k + 1], slice, splits));
-            slice += splits;
+            if (c->x_bounds[k + 1] > c->x_bounds[k]) {
+                GP_TRY(gp_launch_psi2_stats_range(c, c->x_bounds[k], c->x_bounds[k + 1], slice, splits[k]));
+                slice += splits[k];
+            }
         }
         GP_TRY(gp_launch_prep_finish(c, c->red_ws, blocks));
         GP_TRY(gp_launch_psi2_reduce(c, slice));
@@ -637,13 +657,16 @@ extern "C" int gparml_embedding_grads_download(gparml_ctx *c, double *host_grad_
     GP_TRY(wait_y(c));
     GP_TRY(record(c, 6));
     const int64_t n = c->n, Q = c->Q;
-    // Geometric ranges (each 0.7 x the one before): the copy of range k hides behind the kernels of range k + 1 as
-    // long as the link moves a point's gradient faster than 0.7 x the time the kernels need for it, and only the
-    // LAST range's copy is exposed -- 13 % of the points with 4 ranges instead of 25 % with equal ones.
+    // Geometric ranges (each r x the one before): the copy of range k hides behind the kernels of range k + 1 as long
+    // as the link moves a point's gradient faster than r x the time the kernels need for it, and only the LAST range's
+    // copy is exposed.  r is measured: the previous call timed its kernels and the (unobstructed) copy of its last
+    // range; the first call assumes 0.7 (the value 8 ranks sharing one host link see at c3).  One rank alone on the
+    // link gets r = 0.17: ranges of 83 / 14 / 2.4 % of the points instead of 46 / 32 / 22 %.
     int64_t bounds[9];
     {
+        const double r = c->dl_ratio;
         double w[8], tot = 0.0, acc = 0.0;
-        for (int k = 0; k < chunks; ++k) { w[k] = pow(0.7, k); tot += w[k]; }
+        for (int k = 0; k < chunks; ++k) { w[k] = pow(r, k); tot += w[k]; }
         bounds[0] = 0;
         for (int k = 0; k < chunks; ++k) {
             acc += w[k];
@@ -654,19 +677,35 @@ extern "C" int gparml_embedding_grads_download(gparml_ctx *c, double *host_grad_
             bounds[k + 1] = b;
         }
     }
+    int last = -1;
+    for (int k = 0; k < chunks; ++k) if (bounds[k + 1] > bounds[k]) last = k;
+    GP_CUDA(cudaEventRecord(c->ev_dl[0], c->stream));
     for (int k = 0; k < chunks; ++k) {
         const int64_t lo = bounds[k], hi = bounds[k + 1];
         if (hi <= lo) continue;
         GP_TRY(gp_launch_embed_grads_range(c, lo, hi));
         GP_CUDA(cudaEventRecord(c->ev_chunk[k], c->stream));
+        if (k == last) GP_CUDA(cudaEventRecord(c->ev_dl[1], c->stream));
         GP_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_chunk[k], 0));
         const size_t bytes = (size_t)(hi - lo) * Q * sizeof(double);
+        if (k == last) GP_CUDA(cudaEventRecord(c->ev_dl[2], c->copy_stream));
         GP_CUDA(cudaMemcpyAsync(host_grad_latest + lo * Q, c->grad_latest + lo * Q, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
         GP_CUDA(cudaMemcpyAsync(host_grad_latest + (n + lo) * Q, c->grad_latest + (n + lo) * Q, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+        if (k == last) GP_CUDA(cudaEventRecord(c->ev_dl[3], c->copy_stream));
     }
     GP_TRY(record(c, 7));
     GP_CUDA(cudaStreamSynchronize(c->copy_stream));
     GP_CUDA(cudaStreamSynchronize(c->stream));
+    if (last >= 0 && chunks > 1 && n >= 4096) {
+        float t_kern = 0.f, t_copy = 0.f;
+        if (cudaEventElapsedTime(&t_kern, c->ev_dl[0], c->ev_dl[1]) == cudaSuccess &&
+            cudaEventElapsedTime(&t_copy, c->ev_dl[2], c->ev_dl[3]) == cudaSuccess && t_kern > 0.f && t_copy > 0.f) {
+            const double n_last = (double)(bounds[last + 1] - bounds[last]);
+            double r = 1.15 * ((double)t_copy / n_last) / ((double)t_kern / (double)n);      // 15 % margin
+            r = r < 0.1 ? 0.1 : (r > 0.9 ? 0.9 : r);
+            c->dl_ratio = r;
+        }
+    }
     return GPARML_OK;
 }
 

@@ -145,6 +145,10 @@ struct gparml_ctx {
     cudaEvent_t ev_x[GP_MAX_RANGES] = {};
     int x_pending = 0;                 // ranges of the last upload the main stream has not been ordered behind yet
     int64_t x_bounds[GP_MAX_RANGES + 1] = {};
+    // gparml_embedding_grads_download: timing events (kernels of all ranges; copy of the last range) and the ratio
+    // (copy time per point) / (kernel time per point) they gave last time -- the next call sizes its ranges with it
+    cudaEvent_t ev_dl[4] = {nullptr, nullptr, nullptr, nullptr};
+    double dl_ratio = 0.7;
     cudaEvent_t ev_main = nullptr, ev_y = nullptr, ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     // globals
