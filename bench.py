@@ -668,7 +668,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-through-driver", action="store_true")
-    ap.add_argument("--e2e-chunks", type=int, default=4, help="point ranges of the overlapped gradient download (1..8)")
+    ap.add_argument("--e2e-chunks", type=int, default=3, help="point ranges of the overlapped gradient download (1..8)")
     ap.add_argument("--traffic-file", default="ncu_traffic_r02.json")
     ap.add_argument("--fp32", action="store_true", help="opt-in fp32 map path (psi2_stats / embed_grads in fp32, fp64 sums); "
                                                         "not the headline configuration")

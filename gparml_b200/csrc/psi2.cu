@@ -309,7 +309,7 @@ psi2x_stats_kernel(const double *__restrict__ recx, int64_t n, int64_t P, const 
     double lk[2], zc[2][Q], acc[2][1 + 2 * Q];
 #pragma unroll
     for (int v = 0; v < 2; ++v) {
-        p[v] = ((int64_t)blockIdx.x * 2 + v) * PSI2_THREADS + tid;
+        p[v] = ((int64_t)blockIdx.x * 2 + v) * blockDim.x + tid;       // 256 or 128 threads (gp_psi2x_threads)
         const int64_t pc = p[v] < P ? p[v] : P - 1;       // out-of-range threads work on a real pair and never store
         lk[v] = pair_lk[pc];
 #pragma unroll
@@ -373,17 +373,26 @@ __global__ void __launch_bounds__(256) psi2_reduce_kernel(const double *__restri
     dst[i] = a;
 }
 
+// CTA size of psi2x_stats: 128 threads where that wastes fewer pair slots in the last pair tile (c2: P = 1275 pairs fill
+// 5 tiles of 256 pairs to 99.6 %, 3 tiles of 512 to 83 %)
+static int gp_psi2x_threads(int64_t P)
+{
+    const int64_t w256 = (P + 511) / 512 * 512, w128 = (P + 255) / 256 * 256;
+    return (w128 < w256) ? 128 : 256;
+}
+
 #define PSI2_CTA_SETUP_POINTS 24.0
 // number of n-splits for `cnt` points: whole waves of resident CTAs, bounded workspace
 template <int Q>
 static int plan_q(gparml_ctx *c, int64_t cnt, int *splits_out)
 {
-    int occ = 1, pp, tn;
+    int occ = 1, pp, tn, threads = PSI2_THREADS;
     if constexpr (Q <= GP_PSI2X_MAX_Q) {
         const size_t smem = (size_t)PSI2_STAGES * PSI2X_TN * gp_recx_len(Q) * sizeof(double);
         GP_CUDA(cudaFuncSetAttribute(psi2x_stats_kernel<Q, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GP_CUDA(cudaFuncSetAttribute(psi2x_stats_kernel<Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, psi2x_stats_kernel<Q, false>, PSI2_THREADS, smem));
+        threads = gp_psi2x_threads(c->L.P);
+        GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, psi2x_stats_kernel<Q, false>, threads, smem));
         pp = 2;
         tn = PSI2X_TN;
     } else {
@@ -395,7 +404,7 @@ static int plan_q(gparml_ctx *c, int64_t cnt, int *splits_out)
     }
     if (occ < 1) occ = 1;
     const int64_t P = c->L.P;
-    const int tiles = (int)((P + PSI2_THREADS * pp - 1) / (PSI2_THREADS * pp));
+    const int tiles = (int)((P + threads * pp - 1) / (threads * pp));
     const int64_t slots = (int64_t)c->sm_count * occ;
     const int64_t rows_x_P = (int64_t)(1 + 2 * Q) * P;
     int64_t max_splits = (cnt + tn - 1) / tn;             // at least one point tile per split
@@ -430,12 +439,13 @@ static int launch_range_q(gparml_ctx *c, int64_t i0, int64_t i1, int slice0, int
     if constexpr (Q <= GP_PSI2X_MAX_Q) {
         constexpr int RX = 4 * Q + 2;
         const size_t smem = (size_t)PSI2_STAGES * PSI2X_TN * RX * sizeof(double);
-        dim3 grid((unsigned)((P + PSI2_THREADS * 2 - 1) / (PSI2_THREADS * 2)), splits);
+        const int threads = gp_psi2x_threads(P);
+        dim3 grid((unsigned)((P + threads * 2 - 1) / (threads * 2)), splits);
         // both instantiations are launched; the flag prep_points left in d_status[1] lets exactly one of them run
-        psi2x_stats_kernel<Q, false><<<grid, PSI2_THREADS, smem, c->stream>>>(c->rec2x + i0 * RX, cnt, P, c->pair_zc, c->pair_lk,
+        psi2x_stats_kernel<Q, false><<<grid, threads, smem, c->stream>>>(c->rec2x + i0 * RX, cnt, P, c->pair_zc, c->pair_lk,
                                                                              n_per_split, part, c->d_status + 1);
         GP_LAUNCH_CHECK(c);
-        psi2x_stats_kernel<Q, true><<<grid, PSI2_THREADS, smem, c->stream>>>(c->rec2x + i0 * RX, cnt, P, c->pair_zc, c->pair_lk,
+        psi2x_stats_kernel<Q, true><<<grid, threads, smem, c->stream>>>(c->rec2x + i0 * RX, cnt, P, c->pair_zc, c->pair_lk,
                                                                             n_per_split, part, c->d_status + 1);
         GP_LAUNCH_CHECK(c);
     } else {
