@@ -88,7 +88,8 @@ struct PrepParams {
 #endif
 #define PREP_THREADS 256
 #ifndef PREP_MINB
-#define PREP_MINB 5        // resident CTAs per SM the register budget is capped for (48 registers)
+#define PREP_MINB 3        // resident CTAs per SM the register budget is capped for (B200, c3 with the psi2x records: 6 CTAs 0.505 ms,
+                           // 5 (48 registers, spills) 0.429, 4 0.390, 3 0.385)
 #endif
 
 // Two phases per tile of 128 points:

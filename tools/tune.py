@@ -24,6 +24,10 @@ from gparml_b200.build import SOURCES as ALL  # noqa: E402
 # name -> {source: [defines]}
 VARIANTS = {
     "base": {},
+    "prep_minb4": {"prep.cu": ["PREP_MINB=4"]},
+    "prep_minb3": {"prep.cu": ["PREP_MINB=3"]},
+    "prep_minb6": {"prep.cu": ["PREP_MINB=6"]},
+    "prep_tp64": {"prep.cu": ["PREP_TP=64"]},
     # e.g. "p2_compiler": {"psi2.cu": ["PSI2_COMPILER_ORDER"]},  "emx_cp32": {"embed_x.cu": ["EMBX_CP=32", "EMBX_STAGES=3"]},
     #      "p1m_tp32": {"psi1_mma.cu": ["P1M_TP=32"]},  a leading "-" passes an nvcc flag instead of a -D macro
 }
