@@ -148,7 +148,7 @@ static int launch_psi1_part(gparml_ctx *c, const EmbedParams &p, int64_t cnt)
 // Combine the split partials and the Psi1 part, add the KL terms (partial_terms.py:385,418),
 // apply the softplus chain and the sign flip (local_MapReduce.py:357-360).  Runs when the pair range was split over
 // several CTAs (or on the fp32 path); with one split the epilogue of embed_psi2x does this itself.
-__global__ void __launch_bounds__(256) embed_finish_kernel(const double *__restrict__ partial, int splits,
+__global__ void __launch_bounds__(256) embed_finish_kernel(const double *__restrict__ partial, int splits, int64_t pstride, int64_t pbase,
                                                            const double *__restrict__ psi1_part, int64_t n, int64_t i0, int64_t cnt, int Q, int R,
                                                            const double *__restrict__ rec2,
                                                            const double *__restrict__ s_pos, const double *__restrict__ s_sig,
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256) embed_finish_kernel(const double *__restr
     const int W = 2 * Q + 1;
     double am = 0.0, as = 0.0, ah = 0.0;
     for (int s = 0; s < splits; ++s) {
-        const double *pr = partial + ((size_t)s * n + i) * W;
+        const double *pr = partial + ((size_t)s * pstride + (i - pbase)) * W;
         am += pr[q];
         as += pr[Q + q];
         ah += pr[2 * Q];
@@ -218,7 +218,21 @@ static int launch_q(gparml_ctx *c, int64_t i0, int64_t i1)
     const int64_t Pn = c->L.P;
     int max_splits = c->M < EMB_MAX_SPLITS ? c->M : EMB_MAX_SPLITS;
     if (!fp32 && Pn / 64 < max_splits) max_splits = (int)(Pn / 64 > 0 ? Pn / 64 : 1);   // >= 64 pairs per split
-    const int splits = pick_splits(ntiles, slots, max_splits);
+    // Two launches (fp64 path): the point tiles that make whole rounds -- every SM gets the same number -- run with the
+    // whole pair range and finish the gradients in their epilogue; the remaining tiles (fewer than one per SM) are split
+    // over the pair range so that they, too, fill the machine, and go through embed_finish.  One launch with a partial
+    // last round costs up to one round of an SM's time (2 GPUs at c3: 13.2 tiles per SM took the time of 14).
+    // (an odd number of tiles per SM leaves every SM with one CTA running alone at the end, which costs more the fewer
+    // rounds there are: below 8 tiles per SM the whole part is cut to an even number)
+    int64_t per_sm = fp32 ? 0 : ntiles / c->sm_count;
+    if ((per_sm & 1) && per_sm < 8 && occ >= 2) --per_sm;
+    int64_t full_tiles = per_sm * c->sm_count;
+#ifdef EMB_NO_FUSE
+    full_tiles = 0;
+#endif
+    const int64_t t0 = i0 + full_tiles * per_cta < i1 ? i0 + full_tiles * per_cta : i1;      // first point of the split part
+    const int64_t tail_cnt = i1 - t0, tail_tiles = (tail_cnt + per_cta - 1) / per_cta;
+    const int splits = tail_tiles > 0 ? pick_splits(tail_tiles, slots, max_splits) : 1;
     EmbedParams p;
     p.rec1 = c->rec1; p.rec2 = c->rec2; p.Y = c->Y; p.Z = c->Z; p.G1 = c->g_1; p.pair_g = c->pair_g;
     p.pair_zz = c->pair_zz; p.pair_zc = c->pair_zc; p.pair_h = c->pair_h; p.glob = c->d_glob;
@@ -235,17 +249,15 @@ static int launch_q(gparml_ctx *c, int64_t i0, int64_t i1)
         p.m_bounds[s] = m;
     }
     p.m_bounds[splits] = c->M;
-    for (int s = 0; s <= splits; ++s) p.p_bounds[s] = (int)(Pn * s / splits);   // pair splits (fp64 kernel)
     const size_t W = 2 * Q + 1;
-    GP_TRY(gp_ensure_ws(c, (size_t)(splits + 1) * c->n * W * sizeof(double)));
-    p.partial = c->ws;
-    p.psi1_part = c->ws + (size_t)splits * c->n * W;
-#ifdef EMB_NO_FUSE
-    p.fuse_finish = 0;
-#else
-    p.fuse_finish = (!fp32 && splits == 1) ? 1 : 0;
-#endif
+    // workspace: [n][W] Psi1 part, then [splits][pstride][W] partials of the split part (fp32 path: stride n, absolute rows)
+    const int64_t pstride = fp32 ? c->n : (tail_cnt > 0 ? tail_cnt : 1), pbase = fp32 ? 0 : t0;
+    GP_TRY(gp_ensure_ws(c, ((size_t)c->n + (size_t)splits * pstride) * W * sizeof(double)));
+    p.psi1_part = c->ws;
+    p.partial = c->ws + (size_t)c->n * W;
+    p.pstride = pstride; p.pbase = pbase;
     p.s_pos = c->s_pos; p.s_sig = c->s_sig; p.gx_mu = c->gx_mu; p.gx_s = c->gx_s; p.grad_latest = c->grad_latest;
+    p.fuse_finish = 0;
     {   // Psi1 side: Y row in registers / G1 in shared memory when they fit
         const bool fits = (size_t)c->M * (Q + 16) * sizeof(double) <= (size_t)96 * 1024;
         if (fits && c->D <= 4) GP_TRY((launch_psi1_part<Q, 4>(c, p, cnt)));
@@ -253,13 +265,32 @@ static int launch_q(gparml_ctx *c, int64_t i0, int64_t i1)
         else if (fits && c->D <= 16) GP_TRY((launch_psi1_part<Q, 16>(c, p, cnt)));
         else GP_TRY((launch_psi1_part<Q, 0>(c, p, cnt)));
     }
-    if (fp32) GP_TRY(gp_launch_embed_psi2_f32(c, p.m_bounds, splits, p.partial, i0, i1));   // opt-in fp32 evaluation of the Psi2 part
-    else GP_TRY(gp_launch_embed_psi2x(c, p, (int)ntiles, splits));
-    const int64_t total = cnt * Q;
-    if (p.fuse_finish) return GPARML_OK;          // the epilogue of embed_psi2x wrote the gradients
-    embed_finish_kernel<<<(int)((total + 255) / 256), 256, 0, c->stream>>>(c->ws, splits, p.psi1_part, c->n, i0, cnt, Q, gp_rec_len(Q),
-                                                                           c->rec2, c->s_pos, c->s_sig, c->gx_mu, c->gx_s,
-                                                                           c->grad_latest, fp32 ? 0 : 1, c->d_glob);
+    if (fp32) {
+        GP_TRY(gp_launch_embed_psi2_f32(c, p.m_bounds, splits, p.partial, i0, i1));   // opt-in fp32 evaluation of the Psi2 part
+    } else {
+        if (full_tiles > 0) {                              // whole rounds, one pair range, fused finish
+            EmbedParams pf = p;
+            pf.i1 = t0;
+            pf.p_bounds[0] = 0; pf.p_bounds[1] = (int)Pn;
+            pf.fuse_finish = 1;
+            GP_TRY(gp_launch_embed_psi2x(c, pf, (int)full_tiles, 1));
+        }
+        if (tail_cnt > 0) {
+            EmbedParams pt = p;
+            pt.i0 = t0;
+            for (int s = 0; s <= splits; ++s) pt.p_bounds[s] = (int)(Pn * s / splits);   // pair splits
+#ifndef EMB_NO_FUSE
+            pt.fuse_finish = splits == 1 ? 1 : 0;
+#endif
+            GP_TRY(gp_launch_embed_psi2x(c, pt, (int)tail_tiles, splits));
+            if (pt.fuse_finish) return GPARML_OK;
+        }
+    }
+    if (tail_cnt <= 0) return GPARML_OK;
+    const int64_t f0 = fp32 ? i0 : t0, fcnt = fp32 ? cnt : tail_cnt;
+    embed_finish_kernel<<<(int)((fcnt * Q + 255) / 256), 256, 0, c->stream>>>(p.partial, splits, pstride, pbase, p.psi1_part, c->n, f0, fcnt, Q,
+                                                                          gp_rec_len(Q), c->rec2, c->s_pos, c->s_sig, c->gx_mu, c->gx_s,
+                                                                          c->grad_latest, fp32 ? 0 : 1, c->d_glob);
     GP_LAUNCH_CHECK(c);
     return GPARML_OK;
 }

@@ -19,7 +19,8 @@ struct EmbedParams {
     int M, D;
     int m_bounds[EMB_MAX_SPLITS + 1];   // row splits (sqrt(w)-basis kernels)
     int p_bounds[EMB_MAX_SPLITS + 1];   // pair splits (expanded-basis kernel)
-    double *partial;     // [splits][n][2Q + 1]  (AM, AS, AH) resp. (BZ, BZZ, AH)
+    double *partial;     // [splits][pstride][2Q + 1]  (AM, AS, AH) resp. (BZ, BZZ, AH); row of point i: i - pbase
+    int64_t pstride, pbase;
     double *psi1_part;   // [n][2Q + 1]          (sum_m h1 ad_q, sum_m h1 (ad_q^2 - a_q), -),  h1 = B Psi1
     // fused finish (expanded-basis kernel with ONE pair split): the epilogue of embed_psi2x writes the gradients itself
     int fuse_finish;

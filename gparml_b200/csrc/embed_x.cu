@@ -378,7 +378,7 @@ embed_psi2x_kernel(EmbedParams p)
 #pragma unroll
     for (int v = 0; v < NP; ++v) {
         if (valid[v]) {
-            double *out = p.partial + ((size_t)blockIdx.y * p.n + i[v]) * (2 * Q + 1);
+            double *out = p.partial + ((size_t)blockIdx.y * p.pstride + (i[v] - p.pbase)) * (2 * Q + 1);
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
                 out[q] = bz[v][q];
