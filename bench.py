@@ -502,12 +502,19 @@ def run_config(env, cfg_name, steps, warmup, args, main_line):
                         "point-pair, so executed_frac is the pipe-busy fraction" % (5 if k2x else 6)}
     if not fixed and med.get("embed_grads", 0) > 0:
         t_emb = med["embed_grads"] * 1e-3
-        x_emb = n_loc * (P * (4 * Q + 9) + M * (6 * Q + 10 + 2 * D))     # exp = 7 instructions (256-entry table)
+        k5m = 5 <= Q <= 10 and not args.fp32                  # embed_psi2m: both products on the FP64 tensor-core instruction
+        if k5m:      # per (point, pair): (ceil(2Q/4) + 2 ceil((2Q+1)/8)) MMAs of 256 FMAs per 64 items + 7 (exp) + 1 (add)
+            per_pair = ((2 * Q + 3) // 4 + 2 * ((2 * Q + 8) // 8)) * 4 + 8
+        else:
+            per_pair = 4 * Q + 9                                # embed_psi2x; exp = 7 instructions (256-entry table)
+        x_emb = n_loc * (P * per_pair + M * (6 * Q + 10 + 2 * D))
         roofline["embed_grads"] = {"achieved": 2.0 * w_emb / t_emb / 1e12, "frac": (2.0 * w_emb / t_emb / 1e12) / peak,
                                    "launch_ms": med["embed_grads"], "algorithmic_ops_per_launch": w_emb,
                                    "executed_ops_per_launch": x_emb, "executed_frac": x_emb / t_emb / dfma if dfma > 0 else None,
-                                   "note": "algorithmic count of SURVEY.md 8d (6Q+21 per point-pair); the expanded-basis kernel "
-                                           "issues 4Q+9, so frac can exceed the pipe-busy fraction (executed_frac)"}
+                                   "kernel": "embed_psi2m_kernel (FP64 MMA)" if k5m else "embed_psi2x_kernel",
+                                   "note": "algorithmic count of SURVEY.md 8d (6Q+21 per point-pair); the expanded-basis kernels "
+                                           "execute %d FP64-pipe lane-ops per point-pair (MMA lanes included), so frac can exceed "
+                                           "the pipe-busy fraction (executed_frac)" % per_pair}
     if args.fp32:
         roofline["note"] = "fp32 map kernels selected: the FP64-pipe roofline above does not describe them"
     total_ops = algorithmic_ops(N, M, Q, D, fixed)

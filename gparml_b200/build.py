@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libgparml_b200.so")
-SOURCES = ["capi.cu", "prep.cu", "psi1.cu", "psi1_mma.cu", "psi1_wide.cu", "psi2.cu", "psi2_f32.cu", "embed.cu", "embed_x.cu", "global_step.cu", "global_step_large.cu", "misc.cu", "init.cu"]
+SOURCES = ["capi.cu", "prep.cu", "psi1.cu", "psi1_mma.cu", "psi1_wide.cu", "psi2.cu", "psi2_f32.cu", "embed.cu", "embed_x.cu", "embed_m.cu", "global_step.cu", "global_step_large.cu", "misc.cu", "init.cu"]
 HEADERS = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".inc"))] + [
     os.path.join(os.path.dirname(HERE), "include", "gparml_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

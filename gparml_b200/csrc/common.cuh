@@ -52,6 +52,12 @@ __host__ __device__ inline int gp_rec_len_f32(int Q) { return (3 * Q + 4) & ~3; 
 //   recx[2Q .. 4Q)   : (v_q, -1 / w_q) interleaved,  v = alpha S w
 //   recx[4Q], [4Q+1] : lc2 + sum_q alpha_q S_q  (the exponent is accumulated as sum_q (t^2 + v)(-1/w), which
 //                      carries -sum_q alpha_q S_q),  lc2
+// pair feature table of embed_psi2m (embed_m.cu): 64-pair chunks, per chunk [feature / 4][pair][4] doubles with
+// features (zc_1..zc_Q, zc_1^2..zc_Q^2, 1, 0...) padded to GP_PAIR_R_TILES(Q) tiles of 8
+#define GP_PAIR_CHUNK 64
+#define GP_PAIR_R_TILES(Q) ((2 * (Q) + 1 + 7) / 8)
+#define GP_PSI2M_MIN_Q 5
+#define GP_PSI2M_MAX_Q 10
 #define GP_PSI2X_MAX_Q 10
 #define GP_PSI2X_ROBUST_AS 1024.0   // alpha S above this: the cancellation-free variant of psi2x_stats runs instead
 __host__ __device__ inline int gp_recx_len(int Q) { return 4 * Q + 2; }
@@ -162,6 +168,7 @@ struct gparml_ctx {
     double2 *pair_h = nullptr;  // (P) (lk + log|Gs|, sign(Gs)) for the expanded-basis embed_grads kernel
     double2 *pair_zz = nullptr; // (P, Q) (zbar_q - center_q, (zbar_q - center_q)^2) for embed_grads
     double *pair_zc = nullptr;  // (P, Q rounded up to even) zbar_q - center_q alone: the exponent of embed_psi2x reads only this
+    double *pair_r = nullptr;   // blocked pair feature table of embed_psi2m (GP_PSI2M_MIN_Q <= Q <= GP_PSI2M_MAX_Q), zero padded
 
     // statistics
     StatLayout L;

@@ -207,25 +207,35 @@ static int launch_q(gparml_ctx *c, int64_t i0, int64_t i1)
     const int64_t cnt = i1 - i0;
     const bool fp32 = (c->flags & GPARML_FLAG_FP32_MAP) != 0;
     int occ = 4, np = 1;                                  // fp32 kernel: one point per thread, 4 CTAs per SM
-    if (!fp32) {
+#ifdef EMB_NO_MMA
+    const bool use_m = false;
+#else
+    // the tensor-core formulation (embed_m.cu) where its padding is small: 2Q + 1 features in tiles of 8
+    const bool use_m = !fp32 && c->pair_r != nullptr && Q >= GP_PSI2M_MIN_Q && Q <= GP_PSI2M_MAX_Q;
+#endif
+    if (use_m) {
+        GP_TRY(gp_embed_psi2m_occupancy(Q, &occ));
+    } else if (!fp32) {
         np = gp_embed_psi2x_points_per_cta(Q) / EMB_THREADS;
         GP_TRY(gp_embed_psi2x_occupancy(Q, &occ));
     }
     if (occ < 1) occ = 1;
-    const int64_t per_cta = (int64_t)EMB_THREADS * np;
+    const int64_t per_cta = use_m ? gp_embed_psi2m_points_per_cta() : (int64_t)EMB_THREADS * np;
+    const int64_t pchunks = (c->L.P + GP_PAIR_CHUNK - 1) / GP_PAIR_CHUNK;      // pair range of embed_psi2m in chunks
     const int64_t ntiles = (cnt + per_cta - 1) / per_cta;
     const int64_t slots = (int64_t)c->sm_count * occ;
     const int64_t Pn = c->L.P;
     int max_splits = c->M < EMB_MAX_SPLITS ? c->M : EMB_MAX_SPLITS;
     if (!fp32 && Pn / 64 < max_splits) max_splits = (int)(Pn / 64 > 0 ? Pn / 64 : 1);   // >= 64 pairs per split
+    if (use_m && max_splits > pchunks / 2) max_splits = (int)(pchunks / 2 > 0 ? pchunks / 2 : 1);   // >= 2 chunks per split
     // Two launches (fp64 path): the point tiles that make whole rounds -- every SM gets the same number -- run with the
     // whole pair range and finish the gradients in their epilogue; the remaining tiles (fewer than one per SM) are split
     // over the pair range so that they, too, fill the machine, and go through embed_finish.  One launch with a partial
     // last round costs up to one round of an SM's time (2 GPUs at c3: 13.2 tiles per SM took the time of 14).
-    // (an odd number of tiles per SM leaves every SM with one CTA running alone at the end, which costs more the fewer
-    // rounds there are: below 8 tiles per SM the whole part is cut to an even number)
+    // (a number of tiles per SM that is no multiple of the resident CTAs leaves every SM with a partly filled last
+    // round, which costs more the fewer rounds there are: below 4 rounds the whole part is cut to whole rounds)
     int64_t per_sm = fp32 ? 0 : ntiles / c->sm_count;
-    if ((per_sm & 1) && per_sm < 8 && occ >= 2) --per_sm;
+    if (per_sm < 4 * occ) per_sm -= per_sm % occ;
     int64_t full_tiles = per_sm * c->sm_count;
 #ifdef EMB_NO_FUSE
     full_tiles = 0;
@@ -235,7 +245,7 @@ static int launch_q(gparml_ctx *c, int64_t i0, int64_t i1)
     const int splits = tail_tiles > 0 ? pick_splits(tail_tiles, slots, max_splits) : 1;
     EmbedParams p;
     p.rec1 = c->rec1; p.rec2 = c->rec2; p.Y = c->Y; p.Z = c->Z; p.G1 = c->g_1; p.pair_g = c->pair_g;
-    p.pair_zz = c->pair_zz; p.pair_zc = c->pair_zc; p.pair_h = c->pair_h; p.glob = c->d_glob;
+    p.pair_zz = c->pair_zz; p.pair_zc = c->pair_zc; p.pair_h = c->pair_h; p.pair_r = c->pair_r; p.glob = c->d_glob;
     p.n = c->n; p.i0 = i0; p.i1 = i1; p.M = c->M; p.D = c->D;
     // row splits (fp32 kernel): every split owns about P / splits pairs (row m has M - m pairs)
     const double P = (double)c->L.P;
@@ -271,18 +281,20 @@ static int launch_q(gparml_ctx *c, int64_t i0, int64_t i1)
         if (full_tiles > 0) {                              // whole rounds, one pair range, fused finish
             EmbedParams pf = p;
             pf.i1 = t0;
-            pf.p_bounds[0] = 0; pf.p_bounds[1] = (int)Pn;
+            pf.p_bounds[0] = 0; pf.p_bounds[1] = use_m ? (int)pchunks : (int)Pn;
             pf.fuse_finish = 1;
-            GP_TRY(gp_launch_embed_psi2x(c, pf, (int)full_tiles, 1));
+            if (use_m) GP_TRY(gp_launch_embed_psi2m(c, pf, (int)full_tiles, 1));
+            else GP_TRY(gp_launch_embed_psi2x(c, pf, (int)full_tiles, 1));
         }
         if (tail_cnt > 0) {
             EmbedParams pt = p;
             pt.i0 = t0;
-            for (int s = 0; s <= splits; ++s) pt.p_bounds[s] = (int)(Pn * s / splits);   // pair splits
+            for (int s = 0; s <= splits; ++s) pt.p_bounds[s] = (int)((use_m ? pchunks : Pn) * s / splits);   // pair (chunk) splits
 #ifndef EMB_NO_FUSE
             pt.fuse_finish = splits == 1 ? 1 : 0;
 #endif
-            GP_TRY(gp_launch_embed_psi2x(c, pt, (int)tail_tiles, splits));
+            if (use_m) GP_TRY(gp_launch_embed_psi2m(c, pt, (int)tail_tiles, splits));
+            else GP_TRY(gp_launch_embed_psi2x(c, pt, (int)tail_tiles, splits));
             if (pt.fuse_finish) return GPARML_OK;
         }
     }

@@ -13,6 +13,7 @@ struct EmbedParams {
     const double2 *pair_h;     // (P) (lk + log|Gs|, sign Gs)
     const double2 *pair_zz;    // (P, Q) (zc, zc^2), zc = zbar - center
     const double *pair_zc;     // (P, Q rounded up to even) zc alone
+    const double *pair_r;      // blocked feature table of embed_psi2m (common.cuh)
     const GlobalsDev *glob;
     int64_t n;           // points in the shard (stride of the partial buffers)
     int64_t i0, i1;      // this launch covers points [i0, i1)
@@ -50,3 +51,7 @@ __device__ __forceinline__ void gp_embed_finish_one(double mu, double w, double 
 int gp_embed_psi2x_points_per_cta(int Q);
 int gp_embed_psi2x_occupancy(int Q, int *occ);
 int gp_launch_embed_psi2x(gparml_ctx *c, const EmbedParams &p, int ntiles, int splits);
+// embed_m.cu: the same sums on the FP64 tensor-core instruction; p_bounds are in chunks of GP_PAIR_CHUNK pairs
+int gp_embed_psi2m_points_per_cta();
+int gp_embed_psi2m_occupancy(int Q, int *occ);
+int gp_launch_embed_psi2m(gparml_ctx *c, const EmbedParams &p, int ntiles, int splits);

@@ -1,0 +1,282 @@
+// K5 (Psi2 part) on the FP64 tensor-core instruction: embed_psi2m_kernel.
+//
+// Replaces partial_terms.py:367-431 (the Psi2 terms of grad_X_mu / grad_X_S), like embed_psi2x (embed_x.cu), whose
+// arithmetic it shares: in the expanded basis centred on c = column means of Z (mc = mu - c, zc = zbar - c)
+//   exponent[n, p] = kn_n + lkg_p + sum_q (2 w mc)_nq zc_pq + sum_q (-w)_nq zc_pq^2      h[n, p] = sign_p exp(exponent)
+//   sums[n, :]     = sum_p h[n, p] (zc_p1 .. zc_pQ, zc_p1^2 .. zc_pQ^2, 1)
+// Both lines are matrix products between a per-point feature matrix X (n x 2Q) and a per-pair feature matrix
+// R (P x (2Q + 1)), with an exp between them:
+//   E = X R^T        (8 points x 8 pairs per warp step, K = 2Q:  ceil(2Q / 4) mma.sync m8n8k4 f64)
+//   S += h R         (8 points x 8 NT features, K = 8 pairs:     2 NT MMAs, NT = ceil((2Q + 1) / 8))
+// On B200 the FP64 MMA runs at the DFMA rate (same pipe) but reads 4 register operands per 256 FMAs, so it does
+// not hit the register-file limit that holds the DFMA formulation at ~75 % of the pipe.  Per
+// 64 (point, pair) items at Q = 10: 5 + 6 MMAs (176 pipe cycles) + 2 x 7 DFMA-pipe instructions per lane for the
+// two exps + 2 adds (32 cycles) = 208 cycles; embed_psi2x issues 49 DFMAs per item = 196 cycles at 100 % and needs 264.
+// Measured (B200, c3, tools/tune.py): 255 cycles per 64 items -- 17.7 ms against 18.4 for embed_psi2x.  Without the
+// exps the MMA stream runs at 96 % (184 cycles); the 16 DFMA-pipe instructions of the exps cost 71 cycles instead of
+// 32 because each queues behind the other warps' 16-cycle MMAs (ncu: tensor pipe 69 % + FP64 pipe 12.7 % busy,
+// stall reason math_pipe_throttle).  Tried without gain: all warps of an SM in the same phase (block barriers around
+// the exps), the exps of 2 / 4 steps evaluated together (more independent chains), one row group per warp with 3 CTAs.
+//
+// Fragments (lane = 4 g + k):  A[row g][col k], B[row k][col g], C[row g][cols 2k, 2k + 1].
+//   E step s:   A = X[point g][feature 4s + k] (registers, constant over the pair loop),
+//               B = R[pair pi(g)][feature 4s + k], pi(c) = c / 2 + 4 (c % 2)
+//   -> lane (g, k) holds the exponents of point g for pairs k and 4 + k of the step's 8 pairs: exactly the A
+//      fragments of the two accumulation MMAs (K = pairs 0..3, then 4..7) -- h never leaves its lane.
+//   S tile t:   B = R[pair k (resp. 4 + k)][feature 8t + g]
+// R lives in shared memory as [feature / 4][pair][4]: both access patterns are conflict-free (32 lanes = 32
+// consecutive doubles resp. two runs of 16).  The table is point-independent and static per set_globals
+// (pair_table_kernel writes it in 64-pair chunks, one 1-D bulk copy per stage); only (lk + log|Gs|, sign Gs) per pair
+// comes from the master step.
+#include <math.h>
+
+#include "embed.cuh"
+#include "gp_exp.cuh"
+
+#ifndef EMBM_WARPS
+#define EMBM_WARPS 8
+#endif
+#ifndef EMBM_MINB
+#define EMBM_MINB 2
+#endif
+#ifndef EMBM_NG
+#define EMBM_NG 2              // row groups of 8 points per warp: every B fragment read from shared memory feeds EMBM_NG MMAs
+#endif
+#ifndef EMBM_US
+#define EMBM_US 1               // steps of 8 pairs whose exps are evaluated together
+#endif
+#define EMBM_STAGES 2
+#define EMBM_TAB_REP 16        // copies of the exp table, one per 8-byte bank slot: lane l reads copy l % 16, no bank conflicts
+
+__device__ __forceinline__ void embm_dmma(double (&c)[2], double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c[0]), "+d"(c[1])
+                 : "d"(a), "d"(b));
+}
+
+template <int Q>
+__global__ void __launch_bounds__(EMBM_WARPS * 32, EMBM_MINB)
+embed_psi2m_kernel(EmbedParams p)
+{
+    constexpr int R2 = (3 * Q + 2) & ~1;                 // Psi2 record length (prep_points)
+    constexpr int KS = (2 * Q + 3) / 4;                  // K steps of the exponent product
+    constexpr int NT = GP_PAIR_R_TILES(Q), NB = 2 * NT;  // feature tiles of 8 / blocks of 4
+    constexpr int CP = GP_PAIR_CHUNK, NG = EMBM_NG, US = EMBM_US;
+    constexpr int RD = NB * CP * 4;                      // doubles of R per stage
+    constexpr int OUTW = 8 * NT + 1;                     // padded row of the epilogue staging
+    constexpr int RING_D = EMBM_STAGES * (RD + 2 * CP);
+    constexpr int OUT_D = EMBM_WARPS * NG * 8 * OUTW;
+    extern __shared__ __align__(16) double smem[];       // ring: [stage][R | (lkg, sign) x CP]; reused by the epilogue; then the exp table copies
+    __shared__ __align__(8) uint64_t bar[EMBM_STAGES];
+    double *exp_tab = smem + (RING_D > OUT_D ? RING_D : OUT_D);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, k = lane & 3;
+    const int c_lo = p.p_bounds[blockIdx.y], c_hi = p.p_bounds[blockIdx.y + 1];      // chunks of CP pairs
+    const int nchunks = c_hi - c_lo;
+
+    for (int idx = tid; idx < GP_EXP_TAB * EMBM_TAB_REP; idx += EMBM_WARPS * 32) exp_tab[idx] = gp_exp_table_const[idx / EMBM_TAB_REP];
+    if (tid == 0) {
+        for (int s = 0; s < EMBM_STAGES; ++s) gp_mbar_init(&bar[s], 1);
+        gp_fence_mbar_init();
+    }
+    __syncthreads();
+    auto issue = [&](int t) {
+        const int s = t % EMBM_STAGES;
+        const size_t chunk = (size_t)(c_lo + t);
+        double *dst = smem + (size_t)s * (RD + 2 * CP);
+        gp_mbar_expect_tx(&bar[s], (uint32_t)(RD * sizeof(double) + CP * sizeof(double2)));
+        gp_bulk_g2s(dst, p.pair_r + chunk * RD, (uint32_t)(RD * sizeof(double)), &bar[s]);
+        gp_bulk_g2s(dst + RD, p.pair_h + chunk * CP, (uint32_t)(CP * sizeof(double2)), &bar[s]);
+    };
+    if (tid == 0)
+        for (int t = 0; t < EMBM_STAGES && t < nchunks; ++t) issue(t);
+
+    // ---- per-point features: X[f] = 2 w mc (f < Q), -w (Q <= f < 2Q), 0 beyond; kn = lc2 - sum_q w mc^2 ----------
+    const int64_t i_base = p.i0 + ((int64_t)blockIdx.x * EMBM_WARPS + warp) * (8 * NG);
+    double kn[NG], xa[NG][KS], acc[NG][NT][2];
+#pragma unroll
+    for (int u = 0; u < NG; ++u) {
+        int64_t i = i_base + 8 * u + g;
+        if (i >= p.i1) i = p.i1 - 1;                     // compute on a real record, never store
+        const double2 *r2 = reinterpret_cast<const double2 *>(p.rec2 + i * R2);
+        kn[u] = p.rec2[i * R2 + 3 * Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const double2 mw = r2[q];
+            const double mc = mw.x - p.glob->center[q];
+            kn[u] = fma(-(mw.y * mc), mc, kn[u]);
+        }
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+            const int f = 4 * s + k;
+            double v = 0.0;
+            if (f < 2 * Q) {
+                const int q = f < Q ? f : f - Q;
+                const double2 mw = r2[q];
+                v = f < Q ? 2.0 * (mw.y * (mw.x - p.glob->center[q])) : -mw.y;
+            }
+            xa[u][s] = v;
+        }
+#pragma unroll
+        for (int t = 0; t < NT; ++t) acc[u][t][0] = acc[u][t][1] = 0.0;
+    }
+
+    // per-lane offsets into a stage (doubles)
+    const int off_e = ((g >> 1) + 4 * (g & 1)) * 4 + k;                  // E product: pair pi(g), feature k of block s
+    const int off_s = (g >> 2) * (CP * 4) + k * 4 + (g & 3);             // S product: pair k, feature g of tile t
+    const double *tab = exp_tab + (lane & (EMBM_TAB_REP - 1));
+
+    for (int t = 0; t < nchunks; ++t) {
+        const int s = t % EMBM_STAGES;
+        gp_mbar_wait(&bar[s], (uint32_t)((t / EMBM_STAGES) & 1));
+        const double *R = smem + (size_t)s * (RD + 2 * CP);
+        const double *H = R + RD;                        // (lk + log|Gs|, sign Gs) per pair
+        // EMBM_US steps of 8 pairs at a time: all their exponent MMAs, then all their exps interleaved step by step (a
+        // dependent DFMA queues behind the other warps' MMAs -- ~36 cycles per step of the chain -- so the pipe stays
+        // fed only with enough independent chains in flight: 2 NG EMBM_US per warp), then all their accumulation MMAs
+#pragma unroll 1
+        for (int j0 = 0; j0 < CP; j0 += 8 * US) {
+            constexpr int NE = US * NG * 2;
+            double e[NE], lg[US][2];
+            int sg[US][2];
+#pragma unroll
+            for (int v = 0; v < US; ++v) {
+                const double *re = R + (j0 + 8 * v) * 4 + off_e;
+#pragma unroll
+                for (int u = 0; u < NG; ++u) e[(v * NG + u) * 2] = e[(v * NG + u) * 2 + 1] = kn[u];
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    const double b = re[ks * (CP * 4)];
+#pragma unroll
+                    for (int u = 0; u < NG; ++u) {
+                        double (&c2)[2] = *reinterpret_cast<double (*)[2]>(&e[(v * NG + u) * 2]);
+                        embm_dmma(c2, xa[u][ks], b);
+                    }
+                }
+                lg[v][0] = H[2 * (j0 + 8 * v + k)];
+                lg[v][1] = H[2 * (j0 + 8 * v + 4 + k)];
+                sg[v][0] = reinterpret_cast<const int *>(H)[4 * (j0 + 8 * v + k) + 3] & 0x80000000;
+                sg[v][1] = reinterpret_cast<const int *>(H)[4 * (j0 + 8 * v + 4 + k) + 3] & 0x80000000;
+            }
+            // exp of the NE exponents in lockstep (gp_exp.cuh, same constants and result as gp_exp_signed)
+            double tt[NE], rr[NE], pl[NE];
+            int kk[NE];
+#pragma unroll
+            for (int x = 0; x < NE; ++x) e[x] = gp_exp_clamp(e[x] + lg[x / (2 * NG)][x & 1]);
+#pragma unroll
+            for (int x = 0; x < NE; ++x) tt[x] = fma(e[x], GP_EXP_SCALE, GP_EXP_SHIFT);
+#pragma unroll
+            for (int x = 0; x < NE; ++x) { kk[x] = __double2loint(tt[x]); tt[x] = tt[x] - GP_EXP_SHIFT; }
+#pragma unroll
+            for (int x = 0; x < NE; ++x) { rr[x] = fma(tt[x], GP_EXP_NEG_STEP, e[x]); tt[x] = tab[(kk[x] & (GP_EXP_TAB - 1)) * EMBM_TAB_REP]; }
+#pragma unroll
+            for (int x = 0; x < NE; ++x) pl[x] = fma(rr[x], GP_EXP_C3, GP_EXP_C2);
+#pragma unroll
+            for (int x = 0; x < NE; ++x) pl[x] = fma(pl[x], rr[x], GP_EXP_C1);
+#pragma unroll
+            for (int x = 0; x < NE; ++x) pl[x] = fma(pl[x], rr[x], GP_EXP_C0);
+#pragma unroll
+            for (int x = 0; x < NE; ++x) pl[x] = tt[x] * pl[x];
+#pragma unroll
+            for (int x = 0; x < NE; ++x) {
+                int m = kk[x] >> GP_EXP_LOG2_TAB;
+                m = m < -1021 ? -1021 : m;
+                e[x] = __hiloint2double((__double2hiint(pl[x]) + (m << 20)) ^ sg[x / (2 * NG)][x & 1], __double2loint(pl[x]));
+            }
+#pragma unroll
+            for (int v = 0; v < US; ++v) {
+                const double *rs = R + (j0 + 8 * v) * 4 + off_s;
+#pragma unroll
+                for (int tt2 = 0; tt2 < NT; ++tt2) {
+                    const double b0 = rs[tt2 * (2 * CP * 4)], b1 = rs[tt2 * (2 * CP * 4) + 16];
+#pragma unroll
+                    for (int u = 0; u < NG; ++u) {
+                        embm_dmma(acc[u][tt2], e[(v * NG + u) * 2], b0);
+                        embm_dmma(acc[u][tt2], e[(v * NG + u) * 2 + 1], b1);
+                    }
+                }
+            }
+        }
+        __syncthreads();      // every warp is done reading stage s
+        if (tid == 0 && t + EMBM_STAGES < nchunks) issue(t + EMBM_STAGES);
+    }
+
+    // ---- epilogue: the sums of the warp through shared memory (the ring is free now), then one (point, q) per lane-task
+    double *out = smem + (size_t)warp * NG * 8 * OUTW;
+#pragma unroll
+    for (int u = 0; u < NG; ++u)
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            out[(8 * u + g) * OUTW + 8 * t + 2 * k] = acc[u][t][0];
+            out[(8 * u + g) * OUTW + 8 * t + 2 * k + 1] = acc[u][t][1];
+        }
+    __syncwarp();
+    if (p.fuse_finish) {
+        for (int task = lane; task < 8 * NG * Q; task += 32) {
+            const int gg = task / Q, q = task - gg * Q;
+            const int64_t ii = i_base + gg;
+            if (ii >= p.i1) continue;
+            const double2 mw = *reinterpret_cast<const double2 *>(p.rec2 + ii * R2 + 2 * q);
+            const double *p1 = p.psi1_part + (size_t)ii * (2 * Q + 1);
+            const int64_t o = ii * Q + q;
+            gp_embed_finish_one(mw.x, mw.y, mw.x - p.glob->center[q], out[gg * OUTW + q], out[gg * OUTW + Q + q],
+                                out[gg * OUTW + 2 * Q], p1[q], p1[Q + q], p.s_pos[o], p.s_sig[o], p.gx_mu + o, p.gx_s + o,
+                                p.grad_latest + o, p.grad_latest + p.n * Q + o);
+        }
+        return;
+    }
+    for (int task = lane; task < 8 * NG * (2 * Q + 1); task += 32) {
+        const int gg = task / (2 * Q + 1), f = task - gg * (2 * Q + 1);
+        const int64_t ii = i_base + gg;
+        if (ii >= p.i1) continue;
+        p.partial[((size_t)blockIdx.y * p.pstride + (ii - p.pbase)) * (2 * Q + 1) + f] = out[gg * OUTW + f];
+    }
+}
+
+int gp_embed_psi2m_points_per_cta() { return EMBM_WARPS * 8 * EMBM_NG; }
+
+template <int Q> static size_t smem_m()
+{
+    constexpr int NT = GP_PAIR_R_TILES(Q), RD = 2 * NT * GP_PAIR_CHUNK * 4;
+    const size_t ring = (size_t)EMBM_STAGES * (RD + 2 * GP_PAIR_CHUNK), outd = (size_t)EMBM_WARPS * EMBM_NG * 8 * (8 * NT + 1);
+    return ((ring > outd ? ring : outd) + (size_t)GP_EXP_TAB * EMBM_TAB_REP) * sizeof(double);
+}
+template <int Q> static int occ_m(int *occ)
+{
+    GP_CUDA(cudaFuncSetAttribute(embed_psi2m_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m<Q>()));
+    GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, embed_psi2m_kernel<Q>, EMBM_WARPS * 32, smem_m<Q>()));
+    return GPARML_OK;
+}
+template <int Q> static int launch_m(gparml_ctx *c, const EmbedParams &p, int ntiles, int splits)
+{
+    dim3 grid((unsigned)ntiles, splits);
+    embed_psi2m_kernel<Q><<<grid, EMBM_WARPS * 32, smem_m<Q>(), c->stream>>>(p);
+    GP_LAUNCH_CHECK(c);
+    return GPARML_OK;
+}
+
+#define EMBM_ALL_Q(F) F(5) F(6) F(7) F(8) F(9) F(10)
+
+int gp_embed_psi2m_occupancy(int Q, int *occ)
+{
+    switch (Q) {
+#define CASE_Q(q) case q: return occ_m<q>(occ);
+        EMBM_ALL_Q(CASE_Q)
+#undef CASE_Q
+    }
+    gp_set_error("embed_psi2m: unsupported Q=%d", Q);
+    return GPARML_ERR_ARG;
+}
+
+int gp_launch_embed_psi2m(gparml_ctx *c, const EmbedParams &p, int ntiles, int splits)
+{
+    switch (c->Q) {
+#define CASE_Q(q) case q: return launch_m<q>(c, p, ntiles, splits);
+        EMBM_ALL_Q(CASE_Q)
+#undef CASE_Q
+    }
+    gp_set_error("embed_psi2m: unsupported Q=%d", c->Q);
+    return GPARML_ERR_ARG;
+}

@@ -285,7 +285,8 @@ int gp_launch_prep(gparml_ctx *c)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pair_table_kernel(const double *__restrict__ Z, int M, int Q, const GlobalsDev *__restrict__ glob,
                                                          int2 *__restrict__ pair_idx, double *__restrict__ pair_lk,
-                                                         double2 *__restrict__ pair_zz, double *__restrict__ pair_zc)
+                                                         double2 *__restrict__ pair_zz, double *__restrict__ pair_zc,
+                                                         double *__restrict__ pair_r)
 {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)M * M) return;
@@ -306,12 +307,21 @@ __global__ void __launch_bounds__(256) pair_table_kernel(const double *__restric
         pair_zc[p * QP + q] = zc;
     }
     if (QP > Q) pair_zc[p * QP + Q] = 0.0;
+    if (pair_r) {       // features (zc, zc^2, 1) of embed_psi2m: chunk [p / 64], element (feature / 4, p % 64, feature % 4)
+        const int NB = 2 * GP_PAIR_R_TILES(Q);
+        double *blk = pair_r + (size_t)(p / GP_PAIR_CHUNK) * NB * GP_PAIR_CHUNK * 4 + (p % GP_PAIR_CHUNK) * 4;
+        for (int f = 0; f <= 2 * Q; ++f) {
+            const int q = f < Q ? f : f - Q;
+            const double zc = 0.5 * (Z[a * Q + q] + Z[b * Q + q]) - glob->center[q];
+            blk[(size_t)(f >> 2) * GP_PAIR_CHUNK * 4 + (f & 3)] = f == 2 * Q ? 1.0 : (f < Q ? zc : zc * zc);
+        }
+    }
 }
 
 int gp_launch_pair_table(gparml_ctx *c)
 {
     const int64_t total = (int64_t)c->M * c->M;
-    pair_table_kernel<<<(int)((total + 255) / 256), 256, 0, c->stream>>>(c->Z, c->M, c->Q, c->d_glob, c->pair_idx, c->pair_lk, c->pair_zz, c->pair_zc);
+    pair_table_kernel<<<(int)((total + 255) / 256), 256, 0, c->stream>>>(c->Z, c->M, c->Q, c->d_glob, c->pair_idx, c->pair_lk, c->pair_zz, c->pair_zc, c->pair_r);
     GP_LAUNCH_CHECK(c);
     return GPARML_OK;
 }

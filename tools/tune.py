@@ -24,10 +24,12 @@ from gparml_b200.build import SOURCES as ALL  # noqa: E402
 # name -> {source: [defines]}
 VARIANTS = {
     "base": {},
-    "prep_minb4": {"prep.cu": ["PREP_MINB=4"]},
-    "prep_minb3": {"prep.cu": ["PREP_MINB=3"]},
-    "prep_minb6": {"prep.cu": ["PREP_MINB=6"]},
-    "prep_tp64": {"prep.cu": ["PREP_TP=64"]},
+    "k5m_minb3": {"embed_m.cu": ["EMBM_MINB=3"]},
+    "k5m_w4_minb6": {"embed_m.cu": ["EMBM_WARPS=4", "EMBM_MINB=6"]},
+    "k5m_w4_minb5": {"embed_m.cu": ["EMBM_WARPS=4", "EMBM_MINB=5"]},
+    "k5m_w6_minb3": {"embed_m.cu": ["EMBM_WARPS=6", "EMBM_MINB=3"]},
+    "k5m_w6_minb4": {"embed_m.cu": ["EMBM_WARPS=6", "EMBM_MINB=4"]},
+    "k5m_exp6": {"embed_m.cu": ["GP_EXP_LOG2_TAB=6"]},
     # e.g. "p2_compiler": {"psi2.cu": ["PSI2_COMPILER_ORDER"]},  "emx_cp32": {"embed_x.cu": ["EMBX_CP=32", "EMBX_STAGES=3"]},
     #      "p1m_tp32": {"psi1_mma.cu": ["P1M_TP=32"]},  a leading "-" passes an nvcc flag instead of a -D macro
 }
