@@ -95,11 +95,11 @@ def launches(csv_path, tag):
 def sass(tag):
     lib = os.path.join(ROOT, "gparml_b200", "libgparml_b200.so")
     out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
-    want = ["prep_points_kernel", "psi1_mma_kernelILi10ELi1ELi2E", "psi2x_stats_kernelILi10ELb0E", "psi2_stats_kernelILi12E", "embed_psi2x_kernelILi10E",
+    want = ["prep_points_kernel", "psi1_mma_kernelILi10ELi1ELi2E", "psi2x_stats_kernelILi10ELb0E", "psi2_stats_kernelILi12E", "embed_psi2x_kernelILi10E", "embed_psi2m_kernelILi10E", "embed_psi2x_kernelILi12E",
             "embed_psi1_kernelILi10E", "global_step_kernel", "psi2_stats_f32_kernelILi10E", "embed_psi2_f32_kernelILi10E",
             "gsl_gemm_kernel", "scg_reduce_kernel", "scg_update_kernel", "init_scatter_kernel", "psi1_wide_kernelILi10E",
             "global_step_tail_kernel", "stats_allreduce_kernel", "gsl_panel_kernel", "gsl_grad_z_kernel"]
-    mn = ["DFMA", "DADD", "DMUL", "DMMA", "DSETP", "FFMA", "MUFU", "UBLKCP", "SYNCS", "LDGSTS", "LDS", "STS", "LDG", "STG", "BAR", "SHFL", "IMAD"]
+    mn = ["DFMA", "DADD", "DMUL", "DMMA", "DMMA.8x8x4", "DSETP", "FFMA", "MUFU", "UBLKCP", "SYNCS", "LDGSTS", "LDS", "STS", "LDG", "STG", "BAR", "SHFL", "IMAD"]
     lines = ["# SASS evidence (cuobjdump -sass gparml_b200/libgparml_b200.so, sm_100a), %s" % tag,
              "# per kernel: instruction counts of the mnemonics that matter for this path",
              "#   DFMA/DADD/DMUL = FP64 pipe;  DMMA = FP64 tensor-core MMA (mma.sync m8n8k4 f64);  UBLKCP = cp.async.bulk (TMA unit,",
