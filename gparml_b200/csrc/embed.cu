@@ -236,6 +236,12 @@ static int launch_q(gparml_ctx *c, int64_t i0, int64_t i1)
     // round, which costs more the fewer rounds there are: below 4 rounds the whole part is cut to whole rounds)
     int64_t per_sm = fp32 ? 0 : ntiles / c->sm_count;
     if (per_sm < 4 * occ) per_sm -= per_sm % occ;
+    // ... and the last whole round joins the split part: the tail of the master step (one CTA, ~0.2 ms, side stream)
+    // takes an SM away from this kernel for a while, and only small, dynamically scheduled CTAs at the end absorb that
+    // (8 GPUs at c3 with exactly 6 tiles per SM: 2.48 ms instead of 2.30)
+#ifndef EMB_EXACT_FIT
+    per_sm = per_sm >= 2 * occ ? per_sm - occ : 0;
+#endif
     int64_t full_tiles = per_sm * c->sm_count;
 #ifdef EMB_NO_FUSE
     full_tiles = 0;
@@ -278,24 +284,35 @@ static int launch_q(gparml_ctx *c, int64_t i0, int64_t i1)
     if (fp32) {
         GP_TRY(gp_launch_embed_psi2_f32(c, p.m_bounds, splits, p.partial, i0, i1));   // opt-in fp32 evaluation of the Psi2 part
     } else {
-        if (full_tiles > 0) {                              // whole rounds, one pair range, fused finish
-            EmbedParams pf = p;
-            pf.i1 = t0;
-            pf.p_bounds[0] = 0; pf.p_bounds[1] = use_m ? (int)pchunks : (int)Pn;
-            pf.fuse_finish = 1;
-            if (use_m) GP_TRY(gp_launch_embed_psi2m(c, pf, (int)full_tiles, 1));
-            else GP_TRY(gp_launch_embed_psi2x(c, pf, (int)full_tiles, 1));
-        }
-        if (tail_cnt > 0) {
-            EmbedParams pt = p;
-            pt.i0 = t0;
-            for (int s = 0; s <= splits; ++s) pt.p_bounds[s] = (int)((use_m ? pchunks : Pn) * s / splits);   // pair (chunk) splits
+        if (use_m) {
+            // one launch: whole tiles first, then the (tile, pair split) CTAs of the split part
+            EmbedParams pm = p;
+            pm.full_tiles = (int)full_tiles;
+            pm.tail_splits = splits;
+            for (int s = 0; s <= splits; ++s) pm.p_bounds[s] = (int)(pchunks * s / splits);      // chunk splits
 #ifndef EMB_NO_FUSE
-            pt.fuse_finish = splits == 1 ? 1 : 0;
+            pm.fuse_finish = splits == 1 ? 1 : 0;
 #endif
-            if (use_m) GP_TRY(gp_launch_embed_psi2m(c, pt, (int)tail_tiles, splits));
-            else GP_TRY(gp_launch_embed_psi2x(c, pt, (int)tail_tiles, splits));
-            if (pt.fuse_finish) return GPARML_OK;
+            GP_TRY(gp_launch_embed_psi2m(c, pm, (int)(full_tiles + tail_tiles * splits)));
+            if (pm.fuse_finish) return GPARML_OK;
+        } else {
+            if (full_tiles > 0) {                              // whole rounds, one pair range, fused finish
+                EmbedParams pf = p;
+                pf.i1 = t0;
+                pf.p_bounds[0] = 0; pf.p_bounds[1] = (int)Pn;
+                pf.fuse_finish = 1;
+                GP_TRY(gp_launch_embed_psi2x(c, pf, (int)full_tiles, 1));
+            }
+            if (tail_cnt > 0) {
+                EmbedParams pt = p;
+                pt.i0 = t0;
+                for (int s = 0; s <= splits; ++s) pt.p_bounds[s] = (int)(Pn * s / splits);   // pair splits
+#ifndef EMB_NO_FUSE
+                pt.fuse_finish = splits == 1 ? 1 : 0;
+#endif
+                GP_TRY(gp_launch_embed_psi2x(c, pt, (int)tail_tiles, splits));
+                if (pt.fuse_finish) return GPARML_OK;
+            }
         }
     }
     if (tail_cnt <= 0) return GPARML_OK;

@@ -22,6 +22,9 @@ struct EmbedParams {
     int p_bounds[EMB_MAX_SPLITS + 1];   // pair splits (expanded-basis kernel)
     double *partial;     // [splits][pstride][2Q + 1]  (AM, AS, AH) resp. (BZ, BZZ, AH); row of point i: i - pbase
     int64_t pstride, pbase;
+    // embed_psi2m, one launch: CTAs [0, full_tiles) take a whole point tile with the full pair range and finish the
+    // gradients themselves; the others are (tile, pair split) = (full_tiles + r / tail_splits, r % tail_splits)
+    int full_tiles, tail_splits;
     double *psi1_part;   // [n][2Q + 1]          (sum_m h1 ad_q, sum_m h1 (ad_q^2 - a_q), -),  h1 = B Psi1
     // fused finish (expanded-basis kernel with ONE pair split): the epilogue of embed_psi2x writes the gradients itself
     int fuse_finish;
@@ -54,4 +57,4 @@ int gp_launch_embed_psi2x(gparml_ctx *c, const EmbedParams &p, int ntiles, int s
 // embed_m.cu: the same sums on the FP64 tensor-core instruction; p_bounds are in chunks of GP_PAIR_CHUNK pairs
 int gp_embed_psi2m_points_per_cta();
 int gp_embed_psi2m_occupancy(int Q, int *occ);
-int gp_launch_embed_psi2m(gparml_ctx *c, const EmbedParams &p, int ntiles, int splits);
+int gp_launch_embed_psi2m(gparml_ctx *c, const EmbedParams &p, int ctas);

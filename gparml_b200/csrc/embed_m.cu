@@ -73,7 +73,12 @@ embed_psi2m_kernel(EmbedParams p)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, k = lane & 3;
-    const int c_lo = p.p_bounds[blockIdx.y], c_hi = p.p_bounds[blockIdx.y + 1];      // chunks of CP pairs
+    // whole tiles first (they are dispatched first), then the split ones: small CTAs that fill the machine at the end
+    const bool whole = (int)blockIdx.x < p.full_tiles;
+    const int rest = (int)blockIdx.x - p.full_tiles;
+    const int tile = whole ? (int)blockIdx.x : p.full_tiles + rest / p.tail_splits;
+    const int split = whole ? 0 : rest % p.tail_splits;
+    const int c_lo = whole ? 0 : p.p_bounds[split], c_hi = whole ? p.p_bounds[p.tail_splits] : p.p_bounds[split + 1];      // chunks of CP pairs
     const int nchunks = c_hi - c_lo;
 
     for (int idx = tid; idx < GP_EXP_TAB * EMBM_TAB_REP; idx += EMBM_WARPS * 32) exp_tab[idx] = gp_exp_table_const[idx / EMBM_TAB_REP];
@@ -94,7 +99,7 @@ embed_psi2m_kernel(EmbedParams p)
         for (int t = 0; t < EMBM_STAGES && t < nchunks; ++t) issue(t);
 
     // ---- per-point features: X[f] = 2 w mc (f < Q), -w (Q <= f < 2Q), 0 beyond; kn = lc2 - sum_q w mc^2 ----------
-    const int64_t i_base = p.i0 + ((int64_t)blockIdx.x * EMBM_WARPS + warp) * (8 * NG);
+    const int64_t i_base = p.i0 + ((int64_t)tile * EMBM_WARPS + warp) * (8 * NG);
     double kn[NG], xa[NG][KS], acc[NG][NT][2];
 #pragma unroll
     for (int u = 0; u < NG; ++u) {
@@ -213,7 +218,7 @@ embed_psi2m_kernel(EmbedParams p)
             out[(8 * u + g) * OUTW + 8 * t + 2 * k + 1] = acc[u][t][1];
         }
     __syncwarp();
-    if (p.fuse_finish) {
+    if (whole || p.fuse_finish) {
         for (int task = lane; task < 8 * NG * Q; task += 32) {
             const int gg = task / Q, q = task - gg * Q;
             const int64_t ii = i_base + gg;
@@ -231,7 +236,7 @@ embed_psi2m_kernel(EmbedParams p)
         const int gg = task / (2 * Q + 1), f = task - gg * (2 * Q + 1);
         const int64_t ii = i_base + gg;
         if (ii >= p.i1) continue;
-        p.partial[((size_t)blockIdx.y * p.pstride + (ii - p.pbase)) * (2 * Q + 1) + f] = out[gg * OUTW + f];
+        p.partial[((size_t)split * p.pstride + (ii - p.pbase)) * (2 * Q + 1) + f] = out[gg * OUTW + f];
     }
 }
 
@@ -249,10 +254,9 @@ template <int Q> static int occ_m(int *occ)
     GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, embed_psi2m_kernel<Q>, EMBM_WARPS * 32, smem_m<Q>()));
     return GPARML_OK;
 }
-template <int Q> static int launch_m(gparml_ctx *c, const EmbedParams &p, int ntiles, int splits)
+template <int Q> static int launch_m(gparml_ctx *c, const EmbedParams &p, int ctas)
 {
-    dim3 grid((unsigned)ntiles, splits);
-    embed_psi2m_kernel<Q><<<grid, EMBM_WARPS * 32, smem_m<Q>(), c->stream>>>(p);
+    embed_psi2m_kernel<Q><<<(unsigned)ctas, EMBM_WARPS * 32, smem_m<Q>(), c->stream>>>(p);
     GP_LAUNCH_CHECK(c);
     return GPARML_OK;
 }
@@ -270,10 +274,10 @@ int gp_embed_psi2m_occupancy(int Q, int *occ)
     return GPARML_ERR_ARG;
 }
 
-int gp_launch_embed_psi2m(gparml_ctx *c, const EmbedParams &p, int ntiles, int splits)
+int gp_launch_embed_psi2m(gparml_ctx *c, const EmbedParams &p, int ctas)
 {
     switch (c->Q) {
-#define CASE_Q(q) case q: return launch_m<q>(c, p, ntiles, splits);
+#define CASE_Q(q) case q: return launch_m<q>(c, p, ctas);
         EMBM_ALL_Q(CASE_Q)
 #undef CASE_Q
     }
