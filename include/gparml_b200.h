@@ -117,7 +117,7 @@ int gparml_set_n_total(gparml_ctx *ctx, int64_t n_total);
 /* Copies Y (n,D), X_mu (n,Q), X_S (n,Q) host -> device; replaces the per-evaluation
  * genfromtxt + load of local_MapReduce.py:195-201 / 323-329.  Also computes
  * sum_n y_n.y_n (partial_terms.py:40).  May be called again with a different n.
- * Asynchronous: the copies run on the context's copy stream (X_mu / X_S in up to eight row ranges,
+ * Asynchronous: the copies run on the context's copy stream (X_mu / X_S in up to eight row ranges that double in size,
  * then Y) and the next gparml_statistics starts on the first range while the others are still in
  * flight; every other entry point waits for them.  Pageable host arrays may be reused when the call
  * returns, pinned ones must stay valid until the next call that synchronises (gparml_statistics with
@@ -197,7 +197,8 @@ int gparml_embedding_grads(gparml_ctx *ctx);
 /* The same map followed by the download of GRAD_LATEST (2, n, Q) into caller-owned (ideally
  * pinned) host memory -- the `.grad_latest.npy` the reference writes (local_MapReduce.py:359-360).
  * The points are processed in `chunks` ranges (1..8) and the device-to-host copy of one range
- * overlaps the kernels of the next.  Returns when the host array is complete. */
+ * overlaps the kernels of the next; the ranges shrink geometrically by the copy / kernel time ratio
+ * the previous call measured (0.7 on the first call).  Returns when the host array is complete. */
 int gparml_embedding_grads_download(gparml_ctx *ctx, double *host_grad_latest, int chunks);
 
 /* ---- partial_terms helper surface ------------------------------------------ */
