@@ -46,7 +46,32 @@
 #define EMBM_US 1               // steps of 8 pairs whose exps are evaluated together
 #endif
 #define EMBM_STAGES 2
+// exp of this kernel: every DFMA-pipe instruction of it queues behind the other warps' MMAs, so the table is larger
+// (4096 entries = 2^(j/4096), built per CTA as the product of the 256-entry table and 16 sub-steps: one more rounding,
+// 1.1e-16) and the polynomial shorter (degree 2, near-minimax on |r| <= ln2/8192: 2.5e-14) than in gp_exp.cuh:
+// 6 instead of 7 FP64 instructions (EMBM_EXP12 0 keeps the 256-entry table in 16 conflict-free copies)
+#ifndef EMBM_EXP12
+#define EMBM_EXP12 1
+#endif
+#if EMBM_EXP12
+#define EMBM_TAB_ENTRIES 4096
+#define EMBM_TAB_REP 1
+#define EMBM_LOG2_TAB 12
+#define EMBM_SCALE 5909.278887481194              // 4096 / ln2
+#define EMBM_NEG_STEP -0.0001692253858788929      // -ln2 / 4096
+#define EMBM_C1 1.0000000008949057
+#define EMBM_C2 0.500000000025057
+static __device__ const double embm_sub_table[16] = {
+    1.0, 1.0001692397053021, 1.0003385080526823, 1.0005078050469876, 1.0006771306930664, 1.0008464849957674,
+    1.001015867959941, 1.0011852795904375, 1.0013547198921082, 1.0015241888698057, 1.0016936865283832,
+    1.0018632128726943, 1.002032767907594, 1.002202351637938, 1.0023719640685822, 1.0025416052043845};
+#else
+#define EMBM_TAB_ENTRIES GP_EXP_TAB
 #define EMBM_TAB_REP 16        // copies of the exp table, one per 8-byte bank slot: lane l reads copy l % 16, no bank conflicts
+#define EMBM_LOG2_TAB GP_EXP_LOG2_TAB
+#define EMBM_SCALE GP_EXP_SCALE
+#define EMBM_NEG_STEP GP_EXP_NEG_STEP
+#endif
 
 __device__ __forceinline__ void embm_dmma(double (&c)[2], double a, double b)
 {
@@ -81,7 +106,12 @@ embed_psi2m_kernel(EmbedParams p)
     const int c_lo = whole ? 0 : p.p_bounds[split], c_hi = whole ? p.p_bounds[p.tail_splits] : p.p_bounds[split + 1];      // chunks of CP pairs
     const int nchunks = c_hi - c_lo;
 
+#if EMBM_EXP12
+    static_assert(GP_EXP_LOG2_TAB == 8, "the 4096-entry table is built from the 256-entry one");
+    for (int idx = tid; idx < EMBM_TAB_ENTRIES; idx += EMBM_WARPS * 32) exp_tab[idx] = gp_exp_table_const[idx >> 4] * embm_sub_table[idx & 15];
+#else
     for (int idx = tid; idx < GP_EXP_TAB * EMBM_TAB_REP; idx += EMBM_WARPS * 32) exp_tab[idx] = gp_exp_table_const[idx / EMBM_TAB_REP];
+#endif
     if (tid == 0) {
         for (int s = 0; s < EMBM_STAGES; ++s) gp_mbar_init(&bar[s], 1);
         gp_fence_mbar_init();
@@ -171,22 +201,29 @@ embed_psi2m_kernel(EmbedParams p)
 #pragma unroll
             for (int x = 0; x < NE; ++x) e[x] = gp_exp_clamp(e[x] + lg[x / (2 * NG)][x & 1]);
 #pragma unroll
-            for (int x = 0; x < NE; ++x) tt[x] = fma(e[x], GP_EXP_SCALE, GP_EXP_SHIFT);
+            for (int x = 0; x < NE; ++x) tt[x] = fma(e[x], EMBM_SCALE, GP_EXP_SHIFT);
 #pragma unroll
             for (int x = 0; x < NE; ++x) { kk[x] = __double2loint(tt[x]); tt[x] = tt[x] - GP_EXP_SHIFT; }
 #pragma unroll
-            for (int x = 0; x < NE; ++x) { rr[x] = fma(tt[x], GP_EXP_NEG_STEP, e[x]); tt[x] = tab[(kk[x] & (GP_EXP_TAB - 1)) * EMBM_TAB_REP]; }
+            for (int x = 0; x < NE; ++x) { rr[x] = fma(tt[x], EMBM_NEG_STEP, e[x]); tt[x] = tab[(kk[x] & (EMBM_TAB_ENTRIES - 1)) * EMBM_TAB_REP]; }
+#if EMBM_EXP12
+#pragma unroll
+            for (int x = 0; x < NE; ++x) pl[x] = fma(rr[x], EMBM_C2, EMBM_C1);
+#pragma unroll
+            for (int x = 0; x < NE; ++x) pl[x] = fma(pl[x], rr[x], 1.0);
+#else
 #pragma unroll
             for (int x = 0; x < NE; ++x) pl[x] = fma(rr[x], GP_EXP_C3, GP_EXP_C2);
 #pragma unroll
             for (int x = 0; x < NE; ++x) pl[x] = fma(pl[x], rr[x], GP_EXP_C1);
 #pragma unroll
             for (int x = 0; x < NE; ++x) pl[x] = fma(pl[x], rr[x], GP_EXP_C0);
+#endif
 #pragma unroll
             for (int x = 0; x < NE; ++x) pl[x] = tt[x] * pl[x];
 #pragma unroll
             for (int x = 0; x < NE; ++x) {
-                int m = kk[x] >> GP_EXP_LOG2_TAB;
+                int m = kk[x] >> EMBM_LOG2_TAB;
                 m = m < -1021 ? -1021 : m;
                 e[x] = __hiloint2double((__double2hiint(pl[x]) + (m << 20)) ^ sg[x / (2 * NG)][x & 1], __double2loint(pl[x]));
             }
@@ -246,7 +283,7 @@ template <int Q> static size_t smem_m()
 {
     constexpr int NT = GP_PAIR_R_TILES(Q), RD = 2 * NT * GP_PAIR_CHUNK * 4;
     const size_t ring = (size_t)EMBM_STAGES * (RD + 2 * GP_PAIR_CHUNK), outd = (size_t)EMBM_WARPS * EMBM_NG * 8 * (8 * NT + 1);
-    return ((ring > outd ? ring : outd) + (size_t)GP_EXP_TAB * EMBM_TAB_REP) * sizeof(double);
+    return ((ring > outd ? ring : outd) + (size_t)EMBM_TAB_ENTRIES * EMBM_TAB_REP) * sizeof(double);
 }
 template <int Q> static int occ_m(int *occ)
 {
