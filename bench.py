@@ -503,8 +503,8 @@ def run_config(env, cfg_name, steps, warmup, args, main_line):
     if not fixed and med.get("embed_grads", 0) > 0:
         t_emb = med["embed_grads"] * 1e-3
         k5m = 5 <= Q <= 10 and not args.fp32                  # embed_psi2m: both products on the FP64 tensor-core instruction
-        if k5m:      # per (point, pair): (ceil(2Q/4) + 2 ceil((2Q+1)/8)) MMAs of 256 FMAs per 64 items + 7 (exp) + 1 (add)
-            per_pair = ((2 * Q + 3) // 4 + 2 * ((2 * Q + 8) // 8)) * 4 + 8
+        if k5m:      # per (point, pair): (ceil(2Q/4) + 2 ceil((2Q+1)/8)) MMAs of 256 FMAs per 64 items + 6 (exp)
+            per_pair = ((2 * Q + 3) // 4 + 2 * ((2 * Q + 8) // 8)) * 4 + 6
         else:
             per_pair = 4 * Q + 9                                # embed_psi2x; exp = 7 instructions (256-entry table)
         x_emb = n_loc * (P * per_pair + M * (6 * Q + 10 + 2 * D))

@@ -140,7 +140,9 @@ extern "C" int gparml_create(gparml_ctx **out, int device, int M, int Q, int D, 
         if (Q >= GP_PSI2M_MIN_Q && Q <= GP_PSI2M_MAX_Q) {
             const size_t count = chunks * GP_PAIR_R_TILES(Q) * 2 * GP_PAIR_CHUNK * 4;
             A_(c->pair_r, count);
-            if (cudaMemsetAsync(c->pair_r, 0, count * sizeof(double), c->stream) != cudaSuccess) { gp_set_error("memset failed"); return fail(GPARML_ERR_CUDA); }
+            A_(c->pair_ra, count);
+            if (cudaMemsetAsync(c->pair_r, 0, count * sizeof(double), c->stream) != cudaSuccess ||
+                cudaMemsetAsync(c->pair_ra, 0, count * sizeof(double), c->stream) != cudaSuccess) { gp_set_error("memset failed"); return fail(GPARML_ERR_CUDA); }
         }
     }
     A_(c->stats, (size_t)c->L.count);
@@ -168,7 +170,7 @@ extern "C" int gparml_destroy(gparml_ctx *c)
     void *ptrs[] = {c->Y, c->x_mu, c->x_s, c->grad_d, c->grad_latest, c->grad_new, c->grad_old, c->rec1, c->rec2, c->s_pos, c->s_sig,
                     c->gx_mu, c->gx_s, c->psi1, c->Z, c->d_glob, c->pair_idx, c->pair_lk, c->pair_g, c->pair_zz, c->pair_zc, c->pair_h, c->stats, c->ws, c->red_ws,
                     c->d_status, c->kmm, c->kmm_inv, c->a_inv, c->g_k, c->g_1, c->g_2, c->scratch_x, c->scratch_w, c->c_mat,
-                    c->glob_out, c->named_tmp, c->psi2_full, c->gsl_ws, c->rec2f, c->d_yyt, c->rec2x, c->pair_r};
+                    c->glob_out, c->named_tmp, c->psi2_full, c->gsl_ws, c->rec2f, c->d_yyt, c->rec2x, c->pair_r, c->pair_ra};
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->gs_stream) cudaStreamSynchronize(c->gs_stream);
     for (void *p : ptrs) if (p) cudaFree(p);

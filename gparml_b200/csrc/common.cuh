@@ -169,6 +169,8 @@ struct gparml_ctx {
     double2 *pair_zz = nullptr; // (P, Q) (zbar_q - center_q, (zbar_q - center_q)^2) for embed_grads
     double *pair_zc = nullptr;  // (P, Q rounded up to even) zbar_q - center_q alone: the exponent of embed_psi2x reads only this
     double *pair_r = nullptr;   // blocked pair feature table of embed_psi2m (GP_PSI2M_MIN_Q <= Q <= GP_PSI2M_MAX_Q), zero padded
+    double *pair_ra = nullptr;  // the same table times sign(Gs) exp(lk + log|Gs|) per pair: rebuilt after every master step
+    bool pair_ra_stale = true;
 
     // statistics
     StatLayout L;

@@ -251,7 +251,7 @@ static int launch_q(gparml_ctx *c, int64_t i0, int64_t i1)
     const int splits = tail_tiles > 0 ? pick_splits(tail_tiles, slots, max_splits) : 1;
     EmbedParams p;
     p.rec1 = c->rec1; p.rec2 = c->rec2; p.Y = c->Y; p.Z = c->Z; p.G1 = c->g_1; p.pair_g = c->pair_g;
-    p.pair_zz = c->pair_zz; p.pair_zc = c->pair_zc; p.pair_h = c->pair_h; p.pair_r = c->pair_r; p.glob = c->d_glob;
+    p.pair_zz = c->pair_zz; p.pair_zc = c->pair_zc; p.pair_h = c->pair_h; p.pair_r = c->pair_r; p.pair_ra = c->pair_ra; p.glob = c->d_glob;
     p.n = c->n; p.i0 = i0; p.i1 = i1; p.M = c->M; p.D = c->D;
     // row splits (fp32 kernel): every split owns about P / splits pairs (row m has M - m pairs)
     const double P = (double)c->L.P;
@@ -285,6 +285,10 @@ static int launch_q(gparml_ctx *c, int64_t i0, int64_t i1)
         GP_TRY(gp_launch_embed_psi2_f32(c, p.m_bounds, splits, p.partial, i0, i1));   // opt-in fp32 evaluation of the Psi2 part
     } else {
         if (use_m) {
+            if (c->pair_ra_stale) {
+                GP_TRY(gp_launch_pair_ra(c));
+                c->pair_ra_stale = false;
+            }
             // one launch: whole tiles first, then the (tile, pair split) CTAs of the split part
             EmbedParams pm = p;
             pm.full_tiles = (int)full_tiles;

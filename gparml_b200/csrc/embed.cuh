@@ -14,6 +14,7 @@ struct EmbedParams {
     const double2 *pair_zz;    // (P, Q) (zc, zc^2), zc = zbar - center
     const double *pair_zc;     // (P, Q rounded up to even) zc alone
     const double *pair_r;      // blocked feature table of embed_psi2m (common.cuh)
+    const double *pair_ra;     // pair_r times sign(Gs) exp(lk + log|Gs|)
     const GlobalsDev *glob;
     int64_t n;           // points in the shard (stride of the partial buffers)
     int64_t i0, i1;      // this launch covers points [i0, i1)
@@ -58,3 +59,4 @@ int gp_launch_embed_psi2x(gparml_ctx *c, const EmbedParams &p, int ntiles, int s
 int gp_embed_psi2m_points_per_cta();
 int gp_embed_psi2m_occupancy(int Q, int *occ);
 int gp_launch_embed_psi2m(gparml_ctx *c, const EmbedParams &p, int ctas);
+int gp_launch_pair_ra(gparml_ctx *c);      // pair_ra from pair_r and pair_h, once per master step

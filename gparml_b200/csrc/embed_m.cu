@@ -2,21 +2,25 @@
 //
 // Replaces partial_terms.py:367-431 (the Psi2 terms of grad_X_mu / grad_X_S), like embed_psi2x (embed_x.cu), whose
 // arithmetic it shares: in the expanded basis centred on c = column means of Z (mc = mu - c, zc = zbar - c)
-//   exponent[n, p] = kn_n + lkg_p + sum_q (2 w mc)_nq zc_pq + sum_q (-w)_nq zc_pq^2      h[n, p] = sign_p exp(exponent)
-//   sums[n, :]     = sum_p h[n, p] (zc_p1 .. zc_pQ, zc_p1^2 .. zc_pQ^2, 1)
+//   exponent[n, p] = kn_n + sum_q (2 w mc)_nq zc_pq + sum_q (-w)_nq zc_pq^2              h[n, p] = exp(exponent)
+//   sums[n, :]     = sum_p h[n, p] G_p (zc_p1 .. zc_pQ, zc_p1^2 .. zc_pQ^2, 1),   G_p = Gs_p exp(lk_p) = sign exp(lk + log|Gs|)
 // Both lines are matrix products between a per-point feature matrix X (n x 2Q) and a per-pair feature matrix
 // R (P x (2Q + 1)), with an exp between them:
 //   E = X R^T        (8 points x 8 pairs per warp step, K = 2Q:  ceil(2Q / 4) mma.sync m8n8k4 f64)
-//   S += h R         (8 points x 8 NT features, K = 8 pairs:     2 NT MMAs, NT = ceil((2Q + 1) / 8))
+//   S += h (G R)     (8 points x 8 NT features, K = 8 pairs:     2 NT MMAs, NT = ceil((2Q + 1) / 8))
+// The pair factor G is folded into the second product's matrix (pair_ra = G R, rebuilt by pair_ra_kernel after every
+// master step: 1 MB at c3) instead of into the exponent: no per-item add of lk + log|Gs|, no sign handling.
 // On B200 the FP64 MMA runs at the DFMA rate (same pipe) but reads 4 register operands per 256 FMAs, so it does
 // not hit the register-file limit that holds the DFMA formulation at ~75 % of the pipe.  Per
-// 64 (point, pair) items at Q = 10: 5 + 6 MMAs (176 pipe cycles) + 2 x 7 DFMA-pipe instructions per lane for the
-// two exps + 2 adds (32 cycles) = 208 cycles; embed_psi2x issues 49 DFMAs per item = 196 cycles at 100 % and needs 264.
-// Measured (B200, c3, tools/tune.py): 255 cycles per 64 items -- 17.7 ms against 18.4 for embed_psi2x.  Without the
-// exps the MMA stream runs at 96 % (184 cycles); the 16 DFMA-pipe instructions of the exps cost 71 cycles instead of
-// 32 because each queues behind the other warps' 16-cycle MMAs (ncu: tensor pipe 69 % + FP64 pipe 12.7 % busy,
-// stall reason math_pipe_throttle).  Tried without gain: all warps of an SM in the same phase (block barriers around
-// the exps), the exps of 2 / 4 steps evaluated together (more independent chains), one row group per warp with 3 CTAs.
+// 64 (point, pair) items at Q = 10: 5 + 6 MMAs (176 pipe cycles) + 2 x 6 DFMA-pipe instructions per lane for the
+// two exps (24 cycles) = 200 cycles; embed_psi2x issues 49 DFMAs per item = 196 cycles at 100 % and needs 264.
+// Measured (B200, c3, tools/tune.py, embed phase incl. 0.7 ms of embed_psi1): embed_psi2x 18.4 ms; this kernel 17.7 with
+// the 7-instruction exp of gp_exp.cuh and lk + log|Gs| added to the exponent per item (255 cycles per 64 items), 17.1
+// with the 6-instruction exp below, 16.3 with the pair factor folded into G R (231 cycles).  Without the exps the MMA
+// stream runs at 96 % (184 cycles): every DFMA-pipe instruction between the MMAs costs ~4.4 cycles instead of 2 because
+// it queues behind the other warps' 16-cycle MMAs (ncu: stall reason math_pipe_throttle) -- hence the effort to remove
+// them.  Tried without gain: all warps of an SM in the same phase (block barriers around the exps), the exps of 2 / 4
+// steps evaluated together (more independent chains), one row group per warp with 3 CTAs, 4- / 6- / 12- / 16-warp CTAs.
 //
 // Fragments (lane = 4 g + k):  A[row g][col k], B[row k][col g], C[row g][cols 2k, 2k + 1].
 //   E step s:   A = X[point g][feature 4s + k] (registers, constant over the pair loop),
@@ -25,9 +29,8 @@
 //      fragments of the two accumulation MMAs (K = pairs 0..3, then 4..7) -- h never leaves its lane.
 //   S tile t:   B = R[pair k (resp. 4 + k)][feature 8t + g]
 // R lives in shared memory as [feature / 4][pair][4]: both access patterns are conflict-free (32 lanes = 32
-// consecutive doubles resp. two runs of 16).  The table is point-independent and static per set_globals
-// (pair_table_kernel writes it in 64-pair chunks, one 1-D bulk copy per stage); only (lk + log|Gs|, sign Gs) per pair
-// comes from the master step.
+// consecutive doubles resp. two runs of 16).  R is point-independent and static per set_globals (pair_table_kernel
+// writes it in 64-pair chunks; a stage = one 1-D bulk copy of its first ceil(2Q/4) blocks plus one of the chunk of G R).
 #include <math.h>
 
 #include "embed.cuh"
@@ -88,11 +91,13 @@ embed_psi2m_kernel(EmbedParams p)
     constexpr int KS = (2 * Q + 3) / 4;                  // K steps of the exponent product
     constexpr int NT = GP_PAIR_R_TILES(Q), NB = 2 * NT;  // feature tiles of 8 / blocks of 4
     constexpr int CP = GP_PAIR_CHUNK, NG = EMBM_NG, US = EMBM_US;
-    constexpr int RD = NB * CP * 4;                      // doubles of R per stage
+    constexpr int RD = NB * CP * 4;                      // doubles of a chunk of R resp. G R
+    constexpr int RE = KS * CP * 4;                      // of which the exponent product reads the first KS blocks
+    constexpr int STG = RE + RD;                         // doubles per stage: [R blocks 0..KS) | G R]
     constexpr int OUTW = 8 * NT + 1;                     // padded row of the epilogue staging
-    constexpr int RING_D = EMBM_STAGES * (RD + 2 * CP);
+    constexpr int RING_D = EMBM_STAGES * STG;
     constexpr int OUT_D = EMBM_WARPS * NG * 8 * OUTW;
-    extern __shared__ __align__(16) double smem[];       // ring: [stage][R | (lkg, sign) x CP]; reused by the epilogue; then the exp table copies
+    extern __shared__ __align__(16) double smem[];       // ring: [stage][R | G R]; reused by the epilogue; then the exp table
     __shared__ __align__(8) uint64_t bar[EMBM_STAGES];
     double *exp_tab = smem + (RING_D > OUT_D ? RING_D : OUT_D);
 
@@ -120,10 +125,10 @@ embed_psi2m_kernel(EmbedParams p)
     auto issue = [&](int t) {
         const int s = t % EMBM_STAGES;
         const size_t chunk = (size_t)(c_lo + t);
-        double *dst = smem + (size_t)s * (RD + 2 * CP);
-        gp_mbar_expect_tx(&bar[s], (uint32_t)(RD * sizeof(double) + CP * sizeof(double2)));
-        gp_bulk_g2s(dst, p.pair_r + chunk * RD, (uint32_t)(RD * sizeof(double)), &bar[s]);
-        gp_bulk_g2s(dst + RD, p.pair_h + chunk * CP, (uint32_t)(CP * sizeof(double2)), &bar[s]);
+        double *dst = smem + (size_t)s * STG;
+        gp_mbar_expect_tx(&bar[s], (uint32_t)(STG * sizeof(double)));
+        gp_bulk_g2s(dst, p.pair_r + chunk * RD, (uint32_t)(RE * sizeof(double)), &bar[s]);
+        gp_bulk_g2s(dst + RE, p.pair_ra + chunk * RD, (uint32_t)(RD * sizeof(double)), &bar[s]);
     };
     if (tid == 0)
         for (int t = 0; t < EMBM_STAGES && t < nchunks; ++t) issue(t);
@@ -166,16 +171,15 @@ embed_psi2m_kernel(EmbedParams p)
     for (int t = 0; t < nchunks; ++t) {
         const int s = t % EMBM_STAGES;
         gp_mbar_wait(&bar[s], (uint32_t)((t / EMBM_STAGES) & 1));
-        const double *R = smem + (size_t)s * (RD + 2 * CP);
-        const double *H = R + RD;                        // (lk + log|Gs|, sign Gs) per pair
+        const double *R = smem + (size_t)s * STG;
+        const double *RA = R + RE;                       // G R
         // EMBM_US steps of 8 pairs at a time: all their exponent MMAs, then all their exps interleaved step by step (a
         // dependent DFMA queues behind the other warps' MMAs -- ~36 cycles per step of the chain -- so the pipe stays
         // fed only with enough independent chains in flight: 2 NG EMBM_US per warp), then all their accumulation MMAs
 #pragma unroll 1
         for (int j0 = 0; j0 < CP; j0 += 8 * US) {
             constexpr int NE = US * NG * 2;
-            double e[NE], lg[US][2];
-            int sg[US][2];
+            double e[NE];
 #pragma unroll
             for (int v = 0; v < US; ++v) {
                 const double *re = R + (j0 + 8 * v) * 4 + off_e;
@@ -190,16 +194,12 @@ embed_psi2m_kernel(EmbedParams p)
                         embm_dmma(c2, xa[u][ks], b);
                     }
                 }
-                lg[v][0] = H[2 * (j0 + 8 * v + k)];
-                lg[v][1] = H[2 * (j0 + 8 * v + 4 + k)];
-                sg[v][0] = reinterpret_cast<const int *>(H)[4 * (j0 + 8 * v + k) + 3] & 0x80000000;
-                sg[v][1] = reinterpret_cast<const int *>(H)[4 * (j0 + 8 * v + 4 + k) + 3] & 0x80000000;
             }
             // exp of the NE exponents in lockstep (gp_exp.cuh, same constants and result as gp_exp_signed)
             double tt[NE], rr[NE], pl[NE];
             int kk[NE];
 #pragma unroll
-            for (int x = 0; x < NE; ++x) e[x] = gp_exp_clamp(e[x] + lg[x / (2 * NG)][x & 1]);
+            for (int x = 0; x < NE; ++x) e[x] = gp_exp_clamp(e[x]);
 #pragma unroll
             for (int x = 0; x < NE; ++x) tt[x] = fma(e[x], EMBM_SCALE, GP_EXP_SHIFT);
 #pragma unroll
@@ -225,11 +225,11 @@ embed_psi2m_kernel(EmbedParams p)
             for (int x = 0; x < NE; ++x) {
                 int m = kk[x] >> EMBM_LOG2_TAB;
                 m = m < -1021 ? -1021 : m;
-                e[x] = __hiloint2double((__double2hiint(pl[x]) + (m << 20)) ^ sg[x / (2 * NG)][x & 1], __double2loint(pl[x]));
+                e[x] = __hiloint2double(__double2hiint(pl[x]) + (m << 20), __double2loint(pl[x]));
             }
 #pragma unroll
             for (int v = 0; v < US; ++v) {
-                const double *rs = R + (j0 + 8 * v) * 4 + off_s;
+                const double *rs = RA + (j0 + 8 * v) * 4 + off_s;
 #pragma unroll
                 for (int tt2 = 0; tt2 < NT; ++tt2) {
                     const double b0 = rs[tt2 * (2 * CP * 4)], b1 = rs[tt2 * (2 * CP * 4) + 16];
@@ -277,12 +277,38 @@ embed_psi2m_kernel(EmbedParams p)
     }
 }
 
+// pair_ra = G_p pair_r, G_p = sign(Gs) exp(lk + log|Gs|) from pair_h (written by the head of the master step); one thread
+// per (pair, block of 4 features).  Pairs beyond P keep their zeros.
+__global__ void __launch_bounds__(256) pair_ra_kernel(const double *__restrict__ pair_r, const double2 *__restrict__ pair_h,
+                                                      double *__restrict__ pair_ra, int64_t P, int NB)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t pr = idx / NB;
+    const int blk = (int)(idx - pr * NB);
+    if (pr >= P) return;
+    const double2 h = pair_h[pr];
+    const double gf = h.y < 0.0 ? -exp(h.x) : exp(h.x);
+    const size_t off = ((size_t)(pr / GP_PAIR_CHUNK) * NB + blk) * GP_PAIR_CHUNK * 4 + (size_t)(pr % GP_PAIR_CHUNK) * 4;
+    const double2 a = *reinterpret_cast<const double2 *>(pair_r + off), b = *reinterpret_cast<const double2 *>(pair_r + off + 2);
+    *reinterpret_cast<double2 *>(pair_ra + off) = make_double2(gf * a.x, gf * a.y);
+    *reinterpret_cast<double2 *>(pair_ra + off + 2) = make_double2(gf * b.x, gf * b.y);
+}
+
+int gp_launch_pair_ra(gparml_ctx *c)
+{
+    const int NB = 2 * GP_PAIR_R_TILES(c->Q);
+    const int64_t total = c->L.P * NB;
+    pair_ra_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(c->pair_r, c->pair_h, c->pair_ra, c->L.P, NB);
+    GP_LAUNCH_CHECK(c);
+    return GPARML_OK;
+}
+
 int gp_embed_psi2m_points_per_cta() { return EMBM_WARPS * 8 * EMBM_NG; }
 
 template <int Q> static size_t smem_m()
 {
-    constexpr int NT = GP_PAIR_R_TILES(Q), RD = 2 * NT * GP_PAIR_CHUNK * 4;
-    const size_t ring = (size_t)EMBM_STAGES * (RD + 2 * GP_PAIR_CHUNK), outd = (size_t)EMBM_WARPS * EMBM_NG * 8 * (8 * NT + 1);
+    constexpr int NT = GP_PAIR_R_TILES(Q), RD = 2 * NT * GP_PAIR_CHUNK * 4, RE = ((2 * Q + 3) / 4) * GP_PAIR_CHUNK * 4;
+    const size_t ring = (size_t)EMBM_STAGES * (RE + RD), outd = (size_t)EMBM_WARPS * EMBM_NG * 8 * (8 * NT + 1);
     return ((ring > outd ? ring : outd) + (size_t)EMBM_TAB_ENTRIES * EMBM_TAB_REP) * sizeof(double);
 }
 template <int Q> static int occ_m(int *occ)

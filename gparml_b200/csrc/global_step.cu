@@ -439,6 +439,7 @@ static int launch_gs(gparml_ctx *c, bool kmm_only, int phase)
 {
     GsParams p;
     p.phase = phase;
+    if (!kmm_only && phase != 2) c->pair_ra_stale = true;      // the head rewrites pair_h: embed_psi2m's scaled table follows
     p.M = c->M; p.Q = c->Q; p.D = c->D; p.P = c->L.P;
     p.n_total = (double)c->n_total;
     p.fixed_beta = (c->flags & GPARML_FLAG_FIXED_BETA) ? 1 : 0;
