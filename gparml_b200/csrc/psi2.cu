@@ -36,9 +36,6 @@
 #ifndef PSI2_THREADS
 #define PSI2_THREADS 256
 #endif
-#ifndef PSI2_MINB
-#define PSI2_MINB 2      // resident CTAs per SM the register budget is tuned for
-#endif
 #ifndef PSI2_UNROLL
 #define PSI2_UNROLL 2    // points in flight per thread
 #endif
@@ -202,7 +199,7 @@ psi2_stats_kernel(const double *__restrict__ rec2, int64_t n, const double *__re
 // One point for the two pairs of the thread.  Measured alternatives (B200, c3, ms per launch; this form 21.47 at 64
 // points per stage): one exponent chain per pair instead of two 24.4; the first operands of the next point loaded
 // during the accumulations 22.8; t / u / e skewed by two dimensions 22.2; 128-thread CTAs x 2 per SM 22.1.  ptxas
-// reorders the FMAs of this function whatever the source order (also through volatile asm), so unlike psi2_step it is
+// reorders the FMAs of this function whatever the source order (also through volatile asm), so unlike embx_step (embed_x.cu) it is
 // not written in issue order; what it keeps is the pairing (pair 0, pair 1) that shares the record operand.
 template <int Q, bool ROBUST>
 __device__ __forceinline__ void psi2x_point(const double *__restrict__ rp, const double (&lk)[2], const double (&zc)[2][Q],

@@ -24,8 +24,7 @@ from gparml_b200.build import SOURCES as ALL  # noqa: E402
 # name -> {source: [defines]}
 VARIANTS = {
     "base": {},
-    "k5m_exp8": {"embed_m.cu": ["EMBM_EXP12=0"]},
-    # e.g. "p2_compiler": {"psi2.cu": ["PSI2_COMPILER_ORDER"]},  "emx_cp32": {"embed_x.cu": ["EMBX_CP=32", "EMBX_STAGES=3"]},
+    # e.g. "x_tn64": {"psi2.cu": ["PSI2X_TN=64"]},  "k5_dfma": {"embed.cu": ["EMB_NO_MMA"]},  "k5m_exp8": {"embed_m.cu": ["EMBM_EXP12=0"]},
     #      "p1m_tp32": {"psi1_mma.cu": ["P1M_TP=32"]},  a leading "-" passes an nvcc flag instead of a -D macro
 }
 
