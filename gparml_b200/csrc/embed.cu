@@ -13,12 +13,14 @@
 //   g_mu[n,q] = -mu_nq - sum_m B Psi1 ad_q - 2 sum_p Gs Psi2_n wd_q
 //   g_S[n,q]  = -1/2 (1 - 1/S_nq) + 1/2 sum_m B Psi1 (ad_q^2 - a_nq) + sum_p Gs Psi2_n (2 wd_q^2 - w_nq)
 //
-// Psi2 part (>97 % of the work): embed_psi2x_kernel in embed_x.cu for fp64 (expanded basis, below),
-// embed_psi2_f32_kernel in psi2_f32.cu for the opt-in fp32 path (sqrt(w) basis: u_q = sqrt(w_q) (mu_q - zbar_q),
+// Psi2 part (>95 % of the work), all in the expanded basis described below: embed_psi2m_kernel in embed_m.cu (5 <= Q <= 10:
+// exponent and sums as two products on the FP64 tensor-core instruction), embed_psi2x_kernel in embed_x.cu (other Q:
+// DFMA), embed_psi2_f32_kernel in psi2_f32.cu for the opt-in fp32 path (sqrt(w) basis: u_q = sqrt(w_q) (mu_q - zbar_q),
 // partial sums AM_q = sum_p h u_q, AS_q = sum_p h u_q^2, AH = sum_p h; embed_finish basis 0).  The reduction
-// runs over pairs for each point (the opposite direction to psi2_stats), so a thread owns points.
-// Grid = (point tiles) x (splits of the pair range); split partials are combined in a fixed order by
-// embed_finish.
+// runs over pairs for each point (the opposite direction to psi2_stats), so a thread / a warp row owns points.
+// Launch (launch_q): the point tiles that make whole rounds per SM take the full pair range and finish the gradients in
+// their epilogue; the remaining tiles are split over the pair range so that they fill the machine, their partials are
+// combined in a fixed order by embed_finish.
 //
 // Psi1 part (embed_psi1_kernel): thread per point, loop over the M inducing points.
 //
@@ -37,7 +39,7 @@
 #endif
 
 // ---------------------------------------------------------------------------------------------
-// Expanded-basis Psi2 part (the fp64 default; kernel in embed_x.cu).  With mc = mu - center,
+// Expanded-basis Psi2 part (the fp64 default; kernels in embed_m.cu and embed_x.cu).  With mc = mu - center,
 // zc = zbar - center:
 //   -sum_q w_q (mc_q - zc_q)^2 = -sum_q w_q mc_q^2 + sum_q (2 w_q mc_q) zc_q - sum_q w_q zc_q^2
 // so the exponent of a (point, pair) is a dot product of the per-point vector (A_q = 2 w mc, W_q = w;
@@ -47,7 +49,8 @@
 //   sum_p h wd_q   = w_q (mc_q AH - BZ_q)
 //   sum_p h wd_q^2 = w_q^2 (mc_q^2 AH - 2 mc_q BZ_q + BZZ_q)            (embed_finish, basis 1)
 // another 2Q FMAs; with Gs folded into the exponent (pair_h: lk + log|Gs| and the sign, applied by an
-// integer XOR) 4Q + 11 FP64 instructions per (point, pair) instead of 5Q + 12.  Centring on the
+// integer XOR) 4Q + 9 FP64 instructions per (point, pair) in embed_psi2x (embed_psi2m: both dot products as MMAs, the
+// pair factor folded into the second one's matrix).  Centring on the
 // column means of Z keeps the cancellation in these differences at the scale of the spread of Z,
 // not of its offset from the origin.  The pair table (P x 2Q doubles, 808 kB at M = 100, Q = 10) does
 // not fit shared memory: every CTA walks its pair range in order and stages it through a ring of
